@@ -1,0 +1,877 @@
+// api.cu -- the C ABI of include/fusionsim.h: handle lifetime, out.set() conversions, the
+// step()/density() orchestration and the accessors.  Host code + small layout-conversion kernels.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace fsim {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[1024];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line,
+             what);
+    set_error(buf);
+    return FSIM_ERR_CUDA;
+}
+
+int upload_shape(const double *shape64, const double *shape32);
+int upload_costab(const double *c);
+
+static int fail(int code, const std::string &msg)
+{
+    set_error(msg);
+    return code;
+}
+
+int ensure_stage(fsim_sim *s, size_t bytes)
+{
+    if (bytes <= s->stage_bytes) return FSIM_OK;
+    if (s->stage) FSIM_CUDA(cudaFree(s->stage));
+    s->stage = nullptr;
+    s->stage_bytes = 0;
+    FSIM_CUDA(cudaMalloc(&s->stage, bytes));
+    s->stage_bytes = bytes;
+    return FSIM_OK;
+}
+
+// N(num) = num.toFixed(20) (empic.js:23-25), parsed back as the GLSL compiler would
+static double tofixed20(double x)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%.20f", x);
+    return strtod(buf, nullptr);
+}
+
+// ---- layout-conversion kernels ------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// default rand / entropy when the caller supplies none (the reference uses Math.random and
+// window.crypto, empic.js:148-173: unseeded).  kind 0: [0,1) like Math.random; kind 1:
+// uint32 / 0xFFFFFFFF like empic.js:151-154.
+template <typename Real>
+__global__ void fill_random_kernel(Real *out, int64_t n, int64_t stride, uint64_t seed, int kind)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint64_t hsh = splitmix64(seed ^ splitmix64((uint64_t)k));
+    double v = kind ? (double)(uint32_t)(hsh >> 32) / (double)0xFFFFFFFFu
+                    : (double)(hsh >> 11) * (1.0 / 9007199254740992.0);
+    out[k * stride] = (Real)v;
+}
+
+template <typename Real>
+__global__ void iota_ids_kernel(uint32_t *id, int64_t n, uint32_t base)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) id[k] = base + (uint32_t)k;
+}
+
+// host [nr][nz][3] doubles -> local table [cell][3], cell = i + (j-row0)*nr  (empic.js:1162)
+template <typename Real>
+__global__ void field_in_kernel(const double *__restrict__ in, Real *__restrict__ out, int nr, int nz,
+                                int row0, int rows)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (int64_t)nr * rows) return;
+    const int i = (int)(c % nr), j = (int)(c / nr) + row0;
+    const double *p = in + 3 * ((size_t)i * nz + j);
+    out[3 * c] = (Real)p[0]; out[3 * c + 1] = (Real)p[1]; out[3 * c + 2] = (Real)p[2];
+}
+
+// value.position / value.velocity: [N][3] doubles * (factor_r, factor_r, factor_z), stored to the
+// typed array (empic.js:1202-1205, :1226-1229); particle id -> storage slot through pid[].
+template <typename Real>
+__global__ void part3_in_kernel(const double *__restrict__ in, Real *a0, Real *a1, Real *a2,
+                                const uint32_t *__restrict__ pid, uint32_t id_base, int64_t n, double f0,
+                                double f1, double f2, uint8_t *alive, int by_id)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const size_t src = by_id ? (size_t)(pid[p] - id_base) : (size_t)p;
+    a0[p] = (Real)(in[3 * src] * f0);
+    a1[p] = (Real)(in[3 * src + 1] * f1);
+    a2[p] = (Real)(in[3 * src + 2] * f2);
+    if (alive) alive[p] = 1;  // position.w = 1.0, empic.js:1205
+}
+
+template <typename Real>
+__global__ void part4_in_kernel(const double *__restrict__ in, Real *a0, Real *a1, Real *a2, Real *a3,
+                                const uint32_t *__restrict__ pid, uint32_t id_base, int64_t n, int by_id)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const size_t src = by_id ? (size_t)(pid[p] - id_base) : (size_t)p;
+    a0[p] = (Real)in[4 * src]; a1[p] = (Real)in[4 * src + 1];
+    a2[p] = (Real)in[4 * src + 2]; a3[p] = (Real)in[4 * src + 3];
+}
+
+// storage order -> id order (or storage order when by_id == 0)
+template <typename Real>
+__global__ void part_out_kernel(double *__restrict__ out, int width, const Real *a0, const Real *a1,
+                                const Real *a2, const Real *a3, const uint8_t *alive,
+                                const uint32_t *__restrict__ pid, uint32_t id_base, int64_t n, int by_id)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const size_t d = by_id ? (size_t)(pid[p] - id_base) : (size_t)p;
+    out[width * d] = (double)a0[p];
+    out[width * d + 1] = (double)a1[p];
+    out[width * d + 2] = (double)a2[p];
+    if (width == 4) out[4 * d + 3] = alive ? (double)alive[p] : (double)a3[p];
+}
+
+template <typename Real>
+__global__ void cells_out_kernel(int64_t *__restrict__ out, const Real *x, const Real *y, const Real *z,
+                                 const uint32_t *__restrict__ pid, uint32_t id_base, int64_t n, int nr,
+                                 int nz, int by_id)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const size_t d = by_id ? (size_t)(pid[p] - id_base) : (size_t)p;
+    const Real r = fsqrt(x[p] * x[p] + y[p] * y[p]);
+    out[d] = (int64_t)tex_idx(r, nr) + (int64_t)nr * tex_idx(z[p], nz);
+}
+
+template <typename Real>
+__global__ void convert_in_kernel(const double *__restrict__ in, Real *__restrict__ out, int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (Real)in[k];
+}
+template <typename Real>
+__global__ void convert_out_kernel(const Real *__restrict__ in, double *__restrict__ out, int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (double)in[k];
+}
+
+// value.sink_mask [nr][nz] -> 1 byte per global cell i + j*nr; the shader tests .r > 0.5 (:719)
+__global__ void sink_in_kernel(const double *__restrict__ in, uint8_t *__restrict__ out, int nr, int nz)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (int64_t)nr * nz) return;
+    const int i = (int)(c % nr), j = (int)(c / nr);
+    out[c] = in[(size_t)i * nz + j] > 0.5 ? 1 : 0;
+}
+
+// ---- host-side restatement of the source_pdf -> inverse-cdf table build (empic.js:1268-1339) --
+static int build_inv_cdf(const double *pdf, int64_t n0, int64_t n1, std::vector<double> &out)
+{
+    std::vector<double> cdf_y((size_t)(n0 * n1)), cdf_x((size_t)n0);
+    double sum_x = 0.0;
+    for (int64_t i = 0; i < n0; ++i) {
+        double sum_y = 0.0;
+        double *row = cdf_y.data() + i * n1;
+        for (int64_t j = 0; j < n1; ++j) {
+            sum_y += pdf[i * n1 + j];
+            row[j] = sum_y;
+        }
+        for (int64_t j = 0; j < n1; ++j) row[j] /= sum_y;  // 0/0 = NaN rows stay NaN, as in JS
+        sum_x += sum_y;
+        cdf_x[i] = sum_x;
+    }
+    for (int64_t i = 0; i < n0; ++i) cdf_x[i] /= sum_x;
+    const int T = FSIM_N_INVCDF;
+    out.assign((size_t)T * T * 2, 0.0);
+    for (int ti = 0; ti < T; ++ti) {
+        const double f1 = (double)ti / 511.0;
+        if (f1 < 0 || f1 > 1) return fail(FSIM_ERR_RANGE, "function out of range");  // :1294-1296
+        int64_t i = 0;
+        while (i < n0 && cdf_x[i] < f1) ++i;
+        double x;
+        if (i >= n0) x = NAN;
+        else if (i == 0) x = (f1 / cdf_x[0]) / (double)n0;
+        else x = ((double)i + (f1 - cdf_x[i - 1]) / (cdf_x[i] - cdf_x[i - 1])) / (double)n0;
+        const double fi = floor(x * (double)n0);
+        const int64_t iy = (fi < (double)(n0 - 1)) ? (int64_t)fi : n0 - 1;
+        for (int tj = 0; tj < T; ++tj) {
+            const double f2 = (double)tj / 511.0;
+            double y;
+            if (!(fi == fi) || iy < 0) y = NAN;
+            else {
+                const double *cy = cdf_y.data() + iy * n1;
+                int64_t j = 0;
+                while (j < n1 && cy[j] < f2) ++j;
+                if (j >= n1) y = NAN;
+                else if (j == 0) y = (f2 / cy[0]) / (double)n1;
+                else y = ((double)j + (f2 - cy[j - 1]) / (cy[j] - cy[j - 1])) / (double)n1;
+            }
+            out[2 * ((size_t)ti + (size_t)tj * T)] = x;
+            out[2 * ((size_t)ti + (size_t)tj * T) + 1] = y;
+        }
+    }
+    return FSIM_OK;
+}
+
+// deposit footprint, empic.js:949-971 (as_f32: with the Float32Array round trips)
+static void build_shape(double *out, bool as_f32)
+{
+    const int n = FSIM_NSHAPE;
+    const double mid = (n - 1) / 2.0;
+    double sum = 0.0;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            const double d = sqrt(pow(i - mid, 2) + pow(j - mid, 2));
+            const double c = cos(0.5 * M_PI * d / mid);
+            double v = pow(c > 0.0 ? c : 0.0, 2);
+            if (as_f32) v = (double)(float)v;
+            out[i + n * j] = v;
+            sum += v;
+        }
+    for (int k = 0; k < n * n; ++k) {
+        const double v = out[k] / sum;
+        out[k] = as_f32 ? (double)(float)v : v;
+    }
+}
+
+static int check(fsim_sim *s)
+{
+    if (!s) return fail(FSIM_ERR_INVALID, "null simulation handle");
+    if (s->sticky_error) return fail(FSIM_ERR_CUDA, "handle is in a sticky CUDA error state: " + g_last_error);
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    return FSIM_OK;
+}
+
+static int finish(fsim_sim *s, int rc)
+{
+    if (rc == FSIM_ERR_CUDA) s->sticky_error = true;
+    return rc;
+}
+
+template <typename T>
+static int dalloc(T **p, size_t count, bool zero = true)
+{
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    FSIM_CUDA(cudaMalloc((void **)p, bytes));
+    if (zero) FSIM_CUDA(cudaMemset(*p, 0, bytes));
+    return FSIM_OK;
+}
+static int dalloc_bytes(void **p, size_t bytes, bool zero = true)
+{
+    bytes = std::max<size_t>(bytes, 16);
+    FSIM_CUDA(cudaMalloc(p, bytes));
+    if (zero) FSIM_CUDA(cudaMemset(*p, 0, bytes));
+    return FSIM_OK;
+}
+
+static int stage_in(fsim_sim *s, const void *host, size_t bytes)
+{
+    FSIM_TRY(ensure_stage(s, bytes));
+    FSIM_CUDA(cudaMemcpyAsync(s->stage, host, bytes, cudaMemcpyHostToDevice, s->stream));
+    return FSIM_OK;
+}
+static int stage_out(fsim_sim *s, void *host, size_t bytes)
+{
+    FSIM_CUDA(cudaMemcpyAsync(host, s->stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+static int create_impl(const fsim_spec *sp, fsim_sim *s)
+{
+    s->spec = *sp;
+    s->prec = sp->precision;
+    s->rs = sp->precision == FSIM_F64 ? 8 : 4;
+    s->device = sp->device;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(FSIM_ERR_CUDA, std::string("no CUDA device: libfusionsim has no CPU fallback (") +
+                                       cudaGetErrorString(e) + ")");
+    if (sp->device < 0 || sp->device >= ndev) return fail(FSIM_ERR_INVALID, ".device <- no such CUDA device");
+    FSIM_CUDA(cudaSetDevice(s->device));
+    FSIM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+
+    s->nr = (int)sp->nr;
+    s->nz = (int)sp->nz;
+    s->ncell_global = (int64_t)s->nr * s->nz;
+    if (sp->slab_rows > 0) {
+        s->slab = true;
+        s->own0 = (int)sp->slab_row0;
+        s->own_rows = (int)sp->slab_rows;
+        const int lo = std::max<int64_t>(0, sp->slab_row0 - sp->halo_rows);
+        const int hi = std::min<int64_t>(s->nz, sp->slab_row0 + sp->slab_rows + sp->halo_rows);
+        s->row0 = lo;
+        s->rows = hi - lo;
+    } else {
+        s->own0 = 0; s->own_rows = s->nz; s->row0 = 0; s->rows = s->nz;
+    }
+    s->ncell_local = (int64_t)s->nr * s->rows;
+
+    // physical quantities, empic.js:44-46, :852 and the toFixed(20) literals of :527,:606,:647
+    s->h = sp->particle_charge * sp->dt / (2 * sp->particle_mass);
+    s->factor_r = 1 / sp->radius;
+    s->factor_z = 1 / sp->height;
+    s->step_factor = sp->dt * FSIM_C_LIGHT;
+    s->k13 = tofixed20(s->factor_r / s->factor_z);
+    s->k31 = tofixed20(s->factor_z / s->factor_r);
+    s->kr = tofixed20(s->factor_r);
+    s->kz = tofixed20(s->factor_z);
+
+    s->n = sp->nparticles_total > 0 ? sp->nparticles_total : sp->nparticles * sp->nparticles;
+    s->cap = std::max<int64_t>(sp->capacity, s->n);
+    s->cap = (s->cap + 1023) / 1024 * 1024 + 1024;
+    s->id_base = (uint32_t)sp->id_base;
+
+    for (int b = 0; b < 2; ++b) {
+        for (int k = 0; k < NPART_ARRAYS; ++k) FSIM_TRY(dalloc_bytes(&s->part[b][k], s->rs * s->cap));
+        FSIM_TRY(dalloc(&s->alive[b], s->cap));
+        FSIM_TRY(dalloc(&s->pid[b], s->cap));
+    }
+    FSIM_TRY(dalloc(&s->key, s->cap));
+    FSIM_TRY(dalloc(&s->counts, s->ncell_local + 1));
+    FSIM_TRY(dalloc(&s->starts, s->ncell_local + 2));
+    FSIM_TRY(dalloc(&s->cursor, s->ncell_local + 1));
+    FSIM_TRY(dalloc(&s->blocksums, s->ncell_local / 2048 + 2));
+    FSIM_TRY(dalloc_bytes(&s->cellrec, s->rs * FSIM_CELLREC * s->ncell_local));
+    FSIM_TRY(dalloc_bytes(&s->E, s->rs * 3 * s->ncell_local));
+    FSIM_TRY(dalloc_bytes(&s->B, s->rs * 3 * s->ncell_local));
+    FSIM_TRY(dalloc(&s->sink, s->ncell_global));
+    FSIM_TRY(dalloc_bytes(&s->entropy, s->rs * 4 * FSIM_N_ENTROPY * FSIM_N_ENTROPY));
+    FSIM_TRY(dalloc_bytes(&s->invcdf, s->rs * 2 * FSIM_N_INVCDF * FSIM_N_INVCDF));
+    FSIM_TRY(dalloc_bytes(&s->cellsum, s->rs * 4 * s->ncell_local));
+    FSIM_TRY(dalloc(&s->cellcount, s->ncell_local));
+    FSIM_TRY(dalloc_bytes(&s->avg, s->rs * 4 * s->ncell_local));
+    if (sp->flags & FSIM_FLAG_KEEP_MOMENTS) {
+        FSIM_TRY(dalloc_bytes(&s->mom, s->rs * 4 * s->ncell_local));
+        FSIM_TRY(dalloc_bytes(&s->norm, s->rs * 4 * s->ncell_local));
+    }
+    FSIM_TRY(dalloc(&s->heavy_list, s->cap / 64 + 2));
+    FSIM_TRY(dalloc(&s->heavy_n, 1));
+    FSIM_TRY(dalloc(&s->oob, 1));
+
+    // host-computed constant tables (libm): deposit footprint and quadrature cosines
+    double shape64[FSIM_NSHAPE * FSIM_NSHAPE], shape32[FSIM_NSHAPE * FSIM_NSHAPE];
+    build_shape(shape64, false);
+    build_shape(shape32, true);
+    FSIM_TRY(upload_shape(shape64, shape32));
+    double costab[FSIM_NQUAD];
+    for (int k = 0; k < FSIM_NQUAD; ++k) costab[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);  // :317
+    FSIM_TRY(upload_costab(costab));
+
+    // ids, default rand / entropy
+    const uint64_t seed = 0x5EEDF0510Cull;
+    int rc = dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        if (s->n) {
+            for (int b = 0; b < 2; ++b)
+                iota_ids_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(s->pid[b], s->n, s->id_base);
+            for (int q = 0; q < 4; ++q)
+                fill_random_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+                    (Real *)s->part[0][AQ0 + q], s->n, 1, seed + 17 * (q + 1) + ((uint64_t)s->id_base << 20), 0);
+        }
+        const int64_t ne = 4ll * FSIM_N_ENTROPY * FSIM_N_ENTROPY;
+        fill_random_kernel<Real><<<grid_for(ne, 256), 256, 0, s->stream>>>((Real *)s->entropy, ne, 1, seed, 1);
+        FSIM_CUDA(cudaGetLastError());
+        return (int)FSIM_OK;
+    });
+    FSIM_TRY(rc);
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+static void free_all(fsim_sim *s)
+{
+    for (int b = 0; b < 2; ++b) {
+        for (int k = 0; k < NPART_ARRAYS; ++k) cudaFree(s->part[b][k]);
+        cudaFree(s->alive[b]);
+        cudaFree(s->pid[b]);
+    }
+    void *ptrs[] = {s->key, s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
+                    s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
+                    s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr};
+    for (void *p : ptrs) cudaFree(p);
+    if (s->hstage) cudaFreeHost(s->hstage);
+    for (auto &kv : s->timers)
+        for (auto &pe : kv.second.pending) {
+            cudaEventDestroy(pe.first);
+            cudaEventDestroy(pe.second);
+        }
+    if (s->stream) cudaStreamDestroy(s->stream);
+}
+
+static int particles_in3(fsim_sim *s, const double *host, int a0, double f0, double f1, double f2,
+                         bool set_alive)
+{
+    if (!host) return fail(FSIM_ERR_INVALID, "null array");
+    if (s->slab && !s->ids_identity)
+        return fail(FSIM_ERR_STATE, "set position/velocity after migration is not defined in slab mode");
+    if (s->n == 0) return FSIM_OK;
+    FSIM_TRY(stage_in(s, host, sizeof(double) * 3 * s->n));
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        part3_in_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+            (const double *)s->stage, (Real *)s->part[s->cur][a0], (Real *)s->part[s->cur][a0 + 1],
+            (Real *)s->part[s->cur][a0 + 2], s->pid[s->cur], s->id_base, s->n, f0, f1, f2,
+            set_alive ? s->alive[s->cur] : nullptr, s->slab ? 0 : 1);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+}
+
+static int field_in(fsim_sim *s, const double *host, void *dst)
+{
+    if (!host) return fail(FSIM_ERR_INVALID, "null array");
+    FSIM_TRY(stage_in(s, host, sizeof(double) * 3 * s->ncell_global));
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        field_in_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
+            (const double *)s->stage, (Real *)dst, s->nr, s->nz, s->row0, s->rows);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+}
+
+static int table_in(fsim_sim *s, const double *host, void *dst, int64_t count)
+{
+    if (!host) return fail(FSIM_ERR_INVALID, "null array");
+    FSIM_TRY(stage_in(s, host, sizeof(double) * count));
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        convert_in_kernel<Real><<<grid_for(count, 256), 256, 0, s->stream>>>((const double *)s->stage,
+                                                                            (Real *)dst, count);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+}
+
+static int table_out(fsim_sim *s, const void *src, double *host, int64_t count)
+{
+    if (!host) return fail(FSIM_ERR_INVALID, "null array");
+    FSIM_TRY(ensure_stage(s, sizeof(double) * count));
+    int rc = dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        convert_out_kernel<Real><<<grid_for(count, 256), 256, 0, s->stream>>>((const Real *)src,
+                                                                             (double *)s->stage, count);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+    FSIM_TRY(rc);
+    return stage_out(s, host, sizeof(double) * count);
+}
+
+static int collect_timers(fsim_sim *s)
+{
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    for (auto &kv : s->timers) {
+        for (auto &pe : kv.second.pending) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pe.first, pe.second);
+            kv.second.ms += ms;
+            cudaEventDestroy(pe.first);
+            cudaEventDestroy(pe.second);
+        }
+        kv.second.pending.clear();
+    }
+    return FSIM_OK;
+}
+
+}  // namespace fsim
+
+using namespace fsim;
+
+extern "C" {
+
+const char *fsim_last_error(void) { return g_last_error.c_str(); }
+int fsim_abi_version(void) { return FSIM_ABI_VERSION; }
+
+int fsim_create(const fsim_spec *sp, fsim_sim **out)
+{
+    if (!sp || !out) return fail(FSIM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    // spec validation: the reference checks that each property is a number (empic.js:31-41,
+    // utilities.js:118-127); here they are numbers by type, so reject what cannot be simulated.
+    auto bad = [](double v) { return !(v == v) || isinf(v); };
+    if (bad(sp->radius) || sp->radius == 0) return fail(FSIM_ERR_INVALID, ".radius <- must be a finite non-zero number");
+    if (bad(sp->height) || sp->height == 0) return fail(FSIM_ERR_INVALID, ".height <- must be a finite non-zero number");
+    if (sp->nr < 1 || sp->nr > (1 << 20)) return fail(FSIM_ERR_INVALID, ".nr <- must be in [1, 2^20]");
+    if (sp->nz < 1 || sp->nz > (1 << 20)) return fail(FSIM_ERR_INVALID, ".nz <- must be in [1, 2^20]");
+    if (sp->nr * sp->nz > (1ll << 31) - 2) return fail(FSIM_ERR_INVALID, ".nr <- nr*nz exceeds 2^31 cells");
+    if (bad(sp->dt)) return fail(FSIM_ERR_INVALID, ".dt <- must be a finite number");
+    if (sp->nparticles < 0 || sp->nparticles > 65535) return fail(FSIM_ERR_INVALID, ".nparticles <- must be in [0, 65535]");
+    if (bad(sp->particle_mass) || sp->particle_mass == 0) return fail(FSIM_ERR_INVALID, ".particle_mass <- must be a finite non-zero number");
+    if (bad(sp->particle_charge)) return fail(FSIM_ERR_INVALID, ".particle_charge <- must be a finite number");
+    if (sp->precision != FSIM_F64 && sp->precision != FSIM_F32) return fail(FSIM_ERR_INVALID, ".precision <- must be FSIM_F64 or FSIM_F32");
+    if (sp->nparticles_total < 0 || sp->nparticles_total > 0xfffffff0ll) return fail(FSIM_ERR_INVALID, ".nparticles_total <- out of range");
+    if (sp->slab_rows < 0 || sp->slab_row0 < 0 || sp->slab_row0 + sp->slab_rows > sp->nz)
+        return fail(FSIM_ERR_INVALID, ".slab_rows <- slab outside the grid");
+    if (sp->slab_rows > 0 && sp->halo_rows < FSIM_SHAPE_MID)
+        return fail(FSIM_ERR_INVALID, ".halo_rows <- slab mode needs at least 5 halo rows (deposit footprint)");
+    fsim_sim *s = new fsim_sim();
+    int rc = create_impl(sp, s);
+    if (rc != FSIM_OK) {
+        free_all(s);
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return FSIM_OK;
+}
+
+int fsim_destroy(fsim_sim *s)
+{
+    if (!s) return FSIM_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    free_all(s);
+    delete s;
+    return FSIM_OK;
+}
+
+int fsim_set_E(fsim_sim *s, const double *E)
+{
+    FSIM_TRY(check(s));
+    return finish(s, field_in(s, E, s->E));
+}
+int fsim_set_B(fsim_sim *s, const double *B)
+{
+    FSIM_TRY(check(s));
+    return finish(s, field_in(s, B, s->B));
+}
+int fsim_set_position(fsim_sim *s, const double *pos)
+{
+    FSIM_TRY(check(s));
+    s->sorted = false;
+    return finish(s, particles_in3(s, pos, AX, s->factor_r, s->factor_r, s->factor_z, true));
+}
+int fsim_set_velocity(fsim_sim *s, const double *vel)
+{
+    FSIM_TRY(check(s));
+    return finish(s, particles_in3(s, vel, AVX, s->factor_r, s->factor_r, s->factor_z, false));
+}
+int fsim_set_sink_mask(fsim_sim *s, const double *mask)
+{
+    FSIM_TRY(check(s));
+    if (!mask) return fail(FSIM_ERR_INVALID, "null array");
+    FSIM_TRY(finish(s, stage_in(s, mask, sizeof(double) * s->ncell_global)));
+    sink_in_kernel<<<grid_for(s->ncell_global, 256), 256, 0, s->stream>>>((const double *)s->stage, s->sink,
+                                                                         s->nr, s->nz);
+    s->launches++;
+    FSIM_CUDA(cudaGetLastError());
+    return FSIM_OK;
+}
+int fsim_set_source_pdf(fsim_sim *s, const double *pdf, int64_t n0, int64_t n1)
+{
+    FSIM_TRY(check(s));
+    if (!pdf || n0 < 1 || n1 < 1) return fail(FSIM_ERR_INVALID, ".source_pdf <- empty");
+    std::vector<double> tab;
+    FSIM_TRY(build_inv_cdf(pdf, n0, n1, tab));
+    return finish(s, table_in(s, tab.data(), s->invcdf, (int64_t)tab.size()));
+}
+int fsim_set_inv_cdf(fsim_sim *s, const double *table)
+{
+    FSIM_TRY(check(s));
+    return finish(s, table_in(s, table, s->invcdf, 2ll * FSIM_N_INVCDF * FSIM_N_INVCDF));
+}
+int fsim_set_entropy(fsim_sim *s, const double *entropy)
+{
+    FSIM_TRY(check(s));
+    return finish(s, table_in(s, entropy, s->entropy, 4ll * FSIM_N_ENTROPY * FSIM_N_ENTROPY));
+}
+int fsim_set_rand(fsim_sim *s, const double *rnd)
+{
+    FSIM_TRY(check(s));
+    if (!rnd) return fail(FSIM_ERR_INVALID, "null array");
+    if (s->slab && !s->ids_identity) return fail(FSIM_ERR_STATE, "set rand after migration is not defined in slab mode");
+    if (s->n == 0) return FSIM_OK;
+    FSIM_TRY(finish(s, stage_in(s, rnd, sizeof(double) * 4 * s->n)));
+    return finish(s, dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        part4_in_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+            (const double *)s->stage, (Real *)s->part[s->cur][AQ0], (Real *)s->part[s->cur][AQ1],
+            (Real *)s->part[s->cur][AQ2], (Real *)s->part[s->cur][AQ3], s->pid[s->cur], s->id_base, s->n,
+            s->slab ? 0 : 1);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    }));
+}
+int fsim_set_particle_count(fsim_sim *s, int64_t n)
+{
+    FSIM_TRY(check(s));
+    if (n < 0 || n > s->cap - 1024) return fail(FSIM_ERR_RANGE, "particle count exceeds capacity");
+    s->n = n;
+    s->sorted = false;
+    return FSIM_OK;
+}
+int fsim_set_ids(fsim_sim *s, const uint64_t *ids)
+{
+    FSIM_TRY(check(s));
+    if (!ids) return fail(FSIM_ERR_INVALID, "null array");
+    std::vector<uint32_t> tmp((size_t)s->n);
+    for (int64_t k = 0; k < s->n; ++k) tmp[k] = (uint32_t)ids[k];
+    FSIM_CUDA(cudaMemcpyAsync(s->pid[s->cur], tmp.data(), sizeof(uint32_t) * s->n, cudaMemcpyHostToDevice, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+int fsim_add_current_loop(fsim_sim *s, double r, double z, double I)
+{
+    FSIM_TRY(check(s));
+    // u_R = r*factor_r, u_Z = z*factor_z, empic.js:1355-1357
+    return finish(s, launch_add_loop(s, r * s->factor_r, z * s->factor_z, I));
+}
+int fsim_add_current_z(fsim_sim *s, double I)
+{
+    FSIM_TRY(check(s));
+    return finish(s, launch_add_uniform(s, 0, I));
+}
+int fsim_add_bz(fsim_sim *s, double Bz)
+{
+    FSIM_TRY(check(s));
+    return finish(s, launch_add_uniform(s, 1, Bz));
+}
+int fsim_add_btheta(fsim_sim *s, double Bt)
+{
+    FSIM_TRY(check(s));
+    return finish(s, launch_add_uniform(s, 2, Bt));
+}
+int fsim_add_spindle_cusp_plasma_field(fsim_sim *s, double, double, double)
+{
+    FSIM_TRY(check(s));
+    // spindle.makeSpindleCuspPlasmaField references undefined names and a shader that does not
+    // compile (spindle.js:57,328,333,624,643,651): calling it throws in the reference too.
+    return fail(FSIM_ERR_UNSUPPORTED, "addSpindleCuspPlasmaField: spindle.js does not run in the reference");
+}
+
+int fsim_precalc(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(finish(s, launch_precalc(s)));
+    s->have_precalc = true;
+    return FSIM_OK;
+}
+
+int fsim_half_step(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(finish(s, launch_push(s)));
+    s->sorted = false;
+    return FSIM_OK;
+}
+
+int fsim_step(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    // out.step, empic.js:1436-1469: B-buffers then A-buffers = two half-steps
+    FSIM_TRY(finish(s, launch_push(s)));
+    FSIM_TRY(finish(s, launch_push(s)));
+    s->sorted = false;
+    s->steps_since_sort++;
+    if (s->spec.sort_interval > 0 && s->steps_since_sort >= s->spec.sort_interval)
+        FSIM_TRY(finish(s, launch_sort(s)));
+    return FSIM_OK;
+}
+
+int fsim_sort(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    return finish(s, launch_sort(s));
+}
+
+int fsim_density_begin(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    if (!s->sorted) FSIM_TRY(finish(s, launch_sort(s)));
+    return finish(s, launch_cellsum(s));
+}
+int fsim_density_end(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    return finish(s, launch_conv(s));
+}
+int fsim_density(fsim_sim *s)
+{
+    FSIM_TRY(fsim_density_begin(s));
+    return fsim_density_end(s);
+}
+
+int fsim_render_rgba8(fsim_sim *s, uint8_t *rgba)
+{
+    FSIM_TRY(check(s));
+    if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
+    const size_t bytes = 4 * (size_t)s->ncell_global;
+    FSIM_TRY(finish(s, ensure_stage(s, bytes)));
+    if (s->slab) FSIM_CUDA(cudaMemsetAsync(s->stage, 0, bytes, s->stream));
+    FSIM_TRY(finish(s, launch_render(s, (uint8_t *)s->stage)));
+    return finish(s, stage_out(s, rgba, bytes));
+}
+
+int fsim_sync(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    uint32_t oob = 0;
+    FSIM_CUDA(cudaMemcpy(&oob, s->oob, sizeof oob, cudaMemcpyDeviceToHost));
+    if (oob) {
+        cudaMemset(s->oob, 0, sizeof oob);
+        char buf[256];
+        snprintf(buf, sizeof buf, "%u particle pushes gathered outside the local slab table (halo_rows too small "
+                 "or migration overdue)", oob);
+        return fail(FSIM_ERR_RANGE, buf);
+    }
+    return FSIM_OK;
+}
+
+int64_t fsim_particle_count(const fsim_sim *s) { return s ? s->n : -1; }
+int64_t fsim_local_cells(const fsim_sim *s) { return s ? s->ncell_local : -1; }
+int64_t fsim_launch_count(const fsim_sim *s) { return s ? s->launches : -1; }
+
+static int part_out(fsim_sim *s, double *out, int width, int a0, bool with_alive)
+{
+    if (!out) return fail(FSIM_ERR_INVALID, "null array");
+    if (s->n == 0) return FSIM_OK;
+    FSIM_TRY(ensure_stage(s, sizeof(double) * width * s->n));
+    int rc = dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        const int c = s->cur;
+        part_out_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+            (double *)s->stage, width, (const Real *)s->part[c][a0], (const Real *)s->part[c][a0 + 1],
+            (const Real *)s->part[c][a0 + 2], width == 4 && !with_alive ? (const Real *)s->part[c][a0 + 3] : nullptr,
+            with_alive ? s->alive[c] : nullptr, s->pid[c], s->id_base, s->n, s->slab ? 0 : 1);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+    FSIM_TRY(rc);
+    return stage_out(s, out, sizeof(double) * width * s->n);
+}
+
+int fsim_get_position(fsim_sim *s, double *out)
+{
+    FSIM_TRY(check(s));
+    return finish(s, part_out(s, out, 4, AX, true));
+}
+int fsim_get_velocity(fsim_sim *s, double *out)
+{
+    FSIM_TRY(check(s));
+    return finish(s, part_out(s, out, 3, AVX, false));
+}
+int fsim_get_rand(fsim_sim *s, double *out)
+{
+    FSIM_TRY(check(s));
+    return finish(s, part_out(s, out, 4, AQ0, false));
+}
+int fsim_get_ids(fsim_sim *s, uint64_t *out)
+{
+    FSIM_TRY(check(s));
+    if (!out) return fail(FSIM_ERR_INVALID, "null array");
+    std::vector<uint32_t> tmp((size_t)s->n);
+    FSIM_CUDA(cudaMemcpyAsync(tmp.data(), s->pid[s->cur], sizeof(uint32_t) * s->n, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    for (int64_t k = 0; k < s->n; ++k) out[k] = tmp[k];
+    return FSIM_OK;
+}
+int fsim_get_cells(fsim_sim *s, int64_t *out)
+{
+    FSIM_TRY(check(s));
+    if (!out) return fail(FSIM_ERR_INVALID, "null array");
+    if (s->n == 0) return FSIM_OK;
+    FSIM_TRY(finish(s, ensure_stage(s, sizeof(int64_t) * s->n)));
+    int rc = dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        const int c = s->cur;
+        cells_out_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+            (int64_t *)s->stage, (const Real *)s->part[c][AX], (const Real *)s->part[c][AY],
+            (const Real *)s->part[c][AZ], s->pid[c], s->id_base, s->n, s->nr, s->nz, s->slab ? 0 : 1);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+    FSIM_TRY(finish(s, rc));
+    return finish(s, stage_out(s, out, sizeof(int64_t) * s->n));
+}
+
+int fsim_get_field(fsim_sim *s, const char *name, double *out)
+{
+    FSIM_TRY(check(s));
+    if (!name) return fail(FSIM_ERR_INVALID, "null field name");
+    const std::string n(name);
+    const int64_t nc = s->ncell_local;
+    if (n == "E") return finish(s, table_out(s, s->E, out, 3 * nc));
+    if (n == "B") return finish(s, table_out(s, s->B, out, 3 * nc));
+    if (n == "R1" || n == "R2" || n == "R3" || n == "A") {
+        std::vector<double> rec((size_t)(FSIM_CELLREC * nc));
+        FSIM_TRY(finish(s, table_out(s, s->cellrec, rec.data(), FSIM_CELLREC * nc)));
+        const int off = n == "R1" ? 0 : n == "R2" ? 3 : n == "R3" ? 6 : 9;
+        for (int64_t c = 0; c < nc; ++c)
+            for (int k = 0; k < 3; ++k) out[3 * c + k] = rec[FSIM_CELLREC * c + off + k];
+        return FSIM_OK;
+    }
+    if (n == "cell_sums") return finish(s, table_out(s, s->cellsum, out, 4 * nc));
+    if (n == "moments01_avg") return finish(s, table_out(s, s->avg, out, 4 * nc));
+    if (n == "moments01" || n == "moments01_norm") {
+        if (!s->mom) return fail(FSIM_ERR_STATE, "moments01/moments01_norm are kept only with FSIM_FLAG_KEEP_MOMENTS");
+        return finish(s, table_out(s, n == "moments01" ? s->mom : s->norm, out, 4 * nc));
+    }
+    if (n == "inv_cdf") return finish(s, table_out(s, s->invcdf, out, 2ll * FSIM_N_INVCDF * FSIM_N_INVCDF));
+    if (n == "entropy") return finish(s, table_out(s, s->entropy, out, 4ll * FSIM_N_ENTROPY * FSIM_N_ENTROPY));
+    return fail(FSIM_ERR_INVALID, "unknown field name: " + n);
+}
+int fsim_get_cell_count(fsim_sim *s, uint32_t *out)
+{
+    FSIM_TRY(check(s));
+    if (!out) return fail(FSIM_ERR_INVALID, "null array");
+    FSIM_CUDA(cudaMemcpyAsync(out, s->cellcount, sizeof(uint32_t) * s->ncell_local, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+int fsim_get_sink_mask(fsim_sim *s, uint8_t *out)
+{
+    FSIM_TRY(check(s));
+    if (!out) return fail(FSIM_ERR_INVALID, "null array");
+    FSIM_CUDA(cudaMemcpyAsync(out, s->sink, (size_t)s->ncell_global, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+int fsim_timing_enable(fsim_sim *s, int on)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(collect_timers(s));
+    s->timing = on != 0;
+    return FSIM_OK;
+}
+int fsim_timing_reset(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(collect_timers(s));
+    for (auto &kv : s->timers) {
+        kv.second.ms = 0;
+        kv.second.launches = 0;
+    }
+    return FSIM_OK;
+}
+int fsim_timing_get(fsim_sim *s, const char *name, double *ms, int64_t *launches)
+{
+    FSIM_TRY(check(s));
+    if (!name) return fail(FSIM_ERR_INVALID, "null kernel name");
+    FSIM_TRY(collect_timers(s));
+    auto it = s->timers.find(name);
+    if (ms) *ms = it == s->timers.end() ? 0.0 : it->second.ms;
+    if (launches) *launches = it == s->timers.end() ? 0 : it->second.launches;
+    return FSIM_OK;
+}
+
+}  // extern "C"

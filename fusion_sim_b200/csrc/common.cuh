@@ -1,0 +1,187 @@
+// common.cuh -- shared state and helpers of libfusionsim.so (sm_100a only).
+//
+// The engine behind the C ABI of include/fusionsim.h.  Data layout in HBM:
+//   particles : structure of arrays, 10 reals + 1 alive byte + 1 u32 id per particle,
+//               two copies (the counting sort is out of place);
+//   cell table: array of 12-real records R1.xyz R2.xyz R3.xyz A.xyz, index i + j*nr
+//               (empic.js:1162), rows [row0, row0+rows) of the global grid;
+//   sink mask : 1 byte per GLOBAL cell; entropy 1024^2 x 4 reals; inv_cdf 512^2 x 2 reals.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fsim_constants.h"
+#include "../../include/fusionsim.h"
+
+namespace fsim {
+
+constexpr int NPART_ARRAYS = 10;  // x y z vx vy vz q0 q1 q2 q3
+enum { AX = 0, AY, AZ, AVX, AVY, AVZ, AQ0, AQ1, AQ2, AQ3 };
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FSIM_CUDA(call)                                                         \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return fsim::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define FSIM_TRY(call)                  \
+    do {                                \
+        int rc__ = (call);              \
+        if (rc__ != FSIM_OK) return rc__; \
+    } while (0)
+
+struct KernelTimer {
+    double ms = 0.0;
+    int64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+}  // namespace fsim
+
+// The opaque handle of include/fusionsim.h.
+struct fsim_sim {
+    fsim_spec spec{};
+    int prec = FSIM_F64;
+    size_t rs = 8;  // sizeof(real)
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool sticky_error = false;
+
+    // geometry
+    int nr = 0, nz = 0;       // global grid
+    int row0 = 0, rows = 0;   // local table rows (owned + halo, clipped to the grid)
+    int own0 = 0, own_rows = 0;  // owned rows (== whole grid on one GPU)
+    int64_t ncell_local = 0, ncell_global = 0;
+    bool slab = false;
+
+    // physical constants (host doubles, empic.js:44-46, :852)
+    double h = 0, factor_r = 0, factor_z = 0, step_factor = 0;
+    double k13 = 0, k31 = 0, kr = 0, kz = 0;  // N(...) literals of empic.js:527,606,647
+
+    // particles
+    int64_t n = 0, cap = 0;
+    void *part[2][fsim::NPART_ARRAYS] = {};
+    uint8_t *alive[2] = {};
+    uint32_t *pid[2] = {};
+    int cur = 0;
+    bool ids_identity = true;   // storage order == id order
+    uint32_t id_base = 0;
+
+    // sort scratch
+    uint32_t *key = nullptr;      // [cap] gather cell of each particle (local index)
+    uint32_t *counts = nullptr;   // [ncell_local + 1]
+    uint32_t *starts = nullptr;   // [ncell_local + 2]
+    uint32_t *cursor = nullptr;   // [ncell_local + 1]
+    uint32_t *blocksums = nullptr;
+    bool sorted = false;          // particle storage is sorted by cell and starts[] is valid
+    int steps_since_sort = 0;
+
+    // tables
+    void *cellrec = nullptr;   // [ncell_local][12]
+    void *E = nullptr, *B = nullptr;  // [ncell_local][3]
+    uint8_t *sink = nullptr;   // [ncell_global]
+    void *entropy = nullptr;   // [1024*1024][4]
+    void *invcdf = nullptr;    // [512*512][2]
+    void *costab = nullptr;    // [1000]
+    void *shape = nullptr;     // [121]
+    bool have_precalc = false;
+
+    // deposit
+    void *cellsum = nullptr;     // [ncell_local][4]
+    uint32_t *cellcount = nullptr;  // [ncell_local]
+    void *mom = nullptr, *norm = nullptr;  // [ncell_local][4] (FSIM_FLAG_KEEP_MOMENTS)
+    void *avg = nullptr;         // [ncell_local][4]
+    uint32_t *heavy_list = nullptr;  // cells whose population exceeds the per-thread limit
+    uint32_t *heavy_n = nullptr;
+    uint32_t *oob = nullptr;     // particles whose gather row fell outside the local table
+
+    // staging
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    void *hstage = nullptr;
+    size_t hstage_bytes = 0;
+    void *migr = nullptr;
+    size_t migr_bytes = 0;
+
+    // measurement
+    bool timing = false;
+    std::map<std::string, fsim::KernelTimer> timers;
+    int64_t launches = 0;
+};
+
+namespace fsim {
+
+int ensure_stage(fsim_sim *s, size_t bytes);
+
+// RAII kernel bracket: counts the launch and, when timing is on, records CUDA events on the
+// handle's stream (the stream the kernel is launched on).
+struct Bracket {
+    fsim_sim *s;
+    KernelTimer *t = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    Bracket(fsim_sim *sim, const char *name) : s(sim)
+    {
+        s->launches++;
+        KernelTimer &kt = s->timers[name];
+        kt.launches++;
+        if (s->timing) {
+            t = &kt;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, s->stream);
+        }
+    }
+    ~Bracket()
+    {
+        if (t) {
+            cudaEventRecord(e1, s->stream);
+            t->pending.emplace_back(e0, e1);
+        }
+    }
+};
+
+// precision dispatch: f(double{}) or f(float{})
+template <typename F>
+inline int dispatch(const fsim_sim *s, F &&f)
+{
+    if (s->prec == FSIM_F64) return f(double{});
+    return f(float{});
+}
+
+// ---- device helpers --------------------------------------------------------------------
+// NEAREST + CLAMP_TO_EDGE texel index (utilities.js:528-531); NaN samples texel 0.
+template <typename Real>
+__device__ __forceinline__ int tex_idx(Real u, int n)
+{
+    Real t = u * (Real)n;
+    if (!(t > (Real)0)) return 0;
+    if (t >= (Real)n) return n - 1;
+    return (int)t;
+}
+
+__device__ __forceinline__ double fsqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double ffloor(double x) { return floor(x); }
+__device__ __forceinline__ float ffloor(float x) { return floorf(x); }
+
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// kernels / host stages implemented in the other translation units
+int launch_push(fsim_sim *s);
+int launch_sort(fsim_sim *s);
+int launch_cellsum(fsim_sim *s);
+int launch_conv(fsim_sim *s);
+int launch_precalc(fsim_sim *s);
+int launch_add_loop(fsim_sim *s, double R, double Z, double I);
+int launch_add_uniform(fsim_sim *s, int kind, double val);
+int launch_render(fsim_sim *s, uint8_t *dev_rgba);
+
+}  // namespace fsim

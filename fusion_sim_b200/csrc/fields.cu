@@ -1,0 +1,179 @@
+// fields.cu -- per-cell maps: precalc() and the static-field builders (sm_100a).
+//
+// precalc  : programPre1/2/3 + programPreA (empic.js:506-659, out.precalc :1413-1434) fused into
+//            one pass: (E,B) -> the 12-real cell record R1.xyz R2.xyz R3.xyz A.xyz.
+// add_loop : out.addCurrentLoop (empic.js:1352-1363).  The reference renders two Biot-Savart
+//            tables (programCurrentLoopShape :308-326, u_R = 0.5 and 0.1) and samples them NEAREST
+//            at a scaled coordinate (programCurrentLoop :367-377).  The sampled texel value is a
+//            pure function of the texel index, so it is evaluated on the fly for exactly the
+//            texel the reference would fetch: same arithmetic, no 2 x nr x nz tables held in HBM
+//            and no dependence on which slab of the grid a GPU owns.
+// add_uniform : addCurrentZ :404, addBZ :429, addBTheta :454.
+#include "common.cuh"
+
+namespace fsim {
+
+__constant__ double c_cos_f64[FSIM_NQUAD];
+__constant__ float c_cos_f32[FSIM_NQUAD];
+template <typename Real> __device__ __forceinline__ Real cos_tab(int k);
+template <> __device__ __forceinline__ double cos_tab<double>(int k) { return c_cos_f64[k]; }
+template <> __device__ __forceinline__ float cos_tab<float>(int k) { return c_cos_f32[k]; }
+
+int upload_costab(const double *c)
+{
+    float f[FSIM_NQUAD];
+    for (int k = 0; k < FSIM_NQUAD; ++k) f[k] = (float)c[k];
+    FSIM_CUDA(cudaMemcpyToSymbol(c_cos_f64, c, sizeof(double) * FSIM_NQUAD));
+    FSIM_CUDA(cudaMemcpyToSymbol(c_cos_f32, f, sizeof(f)));
+    return FSIM_OK;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+precalc_kernel(const Real *__restrict__ E, const Real *__restrict__ B, Real *__restrict__ rec,
+               int64_t ncell, Real h, Real k13, Real k31, Real kr, Real kz, int corrected)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const Real Bx = B[3 * c], By = B[3 * c + 1], Bz = B[3 * c + 2];
+    const Real Ex = E[3 * c], Ey = E[3 * c + 1], Ez = E[3 * c + 2];
+    const Real Bmag = fsqrt(Bx * Bx + By * By + Bz * Bz);  // length(B)
+    const Real hB2 = h * h * Bmag * Bmag;
+    const Real f = (Real)2.0 / ((Real)1.0 + hB2);
+    const Real one_m = (Real)1.0 - hB2 * f;
+    Real *o = rec + FSIM_CELLREC * c;
+    // programPre1, empic.js:524-527
+    o[0] = one_m + f * h * h * Bx * Bx;
+    o[1] = f * h * (Bz + h * Bx * By);
+    o[2] = (f * h * (-By + h * Bx * Bz)) * k13;
+    // programPre2, empic.js:563-566
+    o[3] = f * h * (-Bz + h * By * Bx);
+    o[4] = one_m + f * h * h * By * By;
+    o[5] = (f * h * (Bx + h * By * Bz)) * k13;
+    // programPre3, empic.js:603-606
+    o[6] = (f * h * (By + h * Bz * Bx)) * k31;
+    o[7] = (f * h * (-Bx + h * Bz * By)) * k31;
+    o[8] = one_m + f * h * h * Bz * Bz;
+    // programPreA, empic.js:645-647
+    const Real cx = Ey * Bz - Ez * By;
+    const Real cy = Ez * Bx - Ex * Bz;
+    const Real cz = Ex * By - Ey * Bx;
+    const Real d = Ex * Bx + Ey * By + Ez * Bz;
+    const Real t1 = h * ((Real)2.0 - hB2 * f);
+    const Real t2 = h * h * f;
+    Real ax, ay, az;
+    if (corrected) {  // FSIM_FLAG_CORRECTED_PREA: textbook h (E.B) B
+        ax = (t1 * Ex + t2 * (cx + h * d * Bx)) / (Real)FSIM_C_LIGHT;
+        ay = (t1 * Ey + t2 * (cy + h * d * By)) / (Real)FSIM_C_LIGHT;
+        az = (t1 * Ez + t2 * (cz + h * d * Bz)) / (Real)FSIM_C_LIGHT;
+    } else {  // as written in the reference: scalar u_h*dot(E,B) added to each component
+        const Real hd = h * d;
+        ax = (t1 * Ex + t2 * (cx + hd)) / (Real)FSIM_C_LIGHT;
+        ay = (t1 * Ey + t2 * (cy + hd)) / (Real)FSIM_C_LIGHT;
+        az = (t1 * Ez + t2 * (cz + hd)) / (Real)FSIM_C_LIGHT;
+    }
+    o[9] = ax * kr;
+    o[10] = ay * kr;
+    o[11] = az * kz;
+}
+
+int launch_precalc(fsim_sim *s)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        Bracket b(s, "precalc");
+        precalc_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
+            (const Real *)s->E, (const Real *)s->B, (Real *)s->cellrec, s->ncell_local, (Real)s->h,
+            (Real)s->k13, (Real)s->k31, (Real)s->kr, (Real)s->kz,
+            (s->spec.flags & FSIM_FLAG_CORRECTED_PREA) ? 1 : 0);
+        FSIM_CUDA(cudaGetLastError());
+        return (int)FSIM_OK;
+    });
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128)
+add_loop_kernel(Real *__restrict__ B, int nr, int nz, int row0, int rows, Real R, Real Z, Real I)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (int64_t)nr * rows) return;
+    const int i = (int)(c % nr), j = (int)(c / nr) + row0;
+    const Real u = ((Real)i + (Real)0.5) / (Real)nr;
+    const Real v = ((Real)j + (Real)0.5) / (Real)nz;
+    // programCurrentLoop, empic.js:367-377
+    const Real a = u / R;
+    const Real b = (v - Z) / R;
+    const Real sgn = (b > (Real)0) ? (Real)1 : ((b < (Real)0) ? (Real)-1 : (Real)0);
+    const Real ab = (b < (Real)0) ? -b : b;
+    Real Rt;
+    int ti, tj;
+    if (a > (Real)FSIM_LOOP_FAR || b > (Real)FSIM_LOOP_FAR) {
+        Rt = (Real)0.1;  // u_shape_tenth, empic.js:341
+        ti = tex_idx(a / (Real)10.0, nr);
+        tj = tex_idx(ab / (Real)10.0, nz);
+    } else {
+        Rt = (Real)0.5;  // u_shape_half, empic.js:336
+        ti = tex_idx(a / (Real)2.0, nr);
+        tj = tex_idx(ab / (Real)2.0, nz);
+    }
+    // programCurrentLoopShape evaluated at texel (ti,tj), empic.js:308-326
+    const Real tu = ((Real)ti + (Real)0.5) / (Real)nr;
+    const Real tv = ((Real)tj + (Real)0.5) / (Real)nz;
+    const Real constant = Rt * (Real)FSIM_QUAD_SCALE * (Real)FSIM_MU0 / ((Real)4.0 * (Real)FSIM_PI_GLSL);
+    Real Bx = (Real)0, Bz = (Real)0;
+    for (int k = 0; k < FSIM_NQUAD; ++k) {
+        const Real cosine = cos_tab<Real>(k);
+        const Real r = fsqrt(Rt * Rt + tu * tu + tv * tv - (Real)2.0 * tu * Rt * cosine);
+        const Real factor = (r > (Real)0) ? constant * (Real)1.0 / (r * r * r) : (Real)0;
+        Bx += tv * factor * cosine;
+        Bz += factor * (Rt - tu * cosine);
+    }
+    // field = u_I * vec4(sign(b),1,1,1) * texel, blended ONE,ONE (table .y is 0)
+    Real *o = B + 3 * c;
+    o[0] = o[0] + (I * sgn) * Bx;
+    o[1] = o[1] + (I * (Real)1.0) * (Real)0.0;
+    o[2] = o[2] + (I * (Real)1.0) * Bz;
+}
+
+int launch_add_loop(fsim_sim *s, double R, double Z, double I)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        Bracket b(s, "add_loop");
+        add_loop_kernel<Real><<<grid_for(s->ncell_local, 128), 128, 0, s->stream>>>(
+            (Real *)s->B, s->nr, s->nz, s->row0, s->rows, (Real)R, (Real)Z, (Real)I);
+        FSIM_CUDA(cudaGetLastError());
+        return (int)FSIM_OK;
+    });
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+add_uniform_kernel(Real *__restrict__ B, int nr, int64_t ncell, int kind, Real val)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int i = (int)(c % nr);
+    const Real u = ((Real)i + (Real)0.5) / (Real)nr;
+    Real *o = B + 3 * c;
+    if (kind == 0)  // addCurrentZ, empic.js:404
+        o[1] = o[1] + val * (Real)FSIM_MU0 / ((Real)2.0 * (Real)FSIM_PI_GLSL * u);
+    else if (kind == 1)  // addBZ, empic.js:429
+        o[2] = o[2] + val;
+    else  // addBTheta, empic.js:454
+        o[1] = o[1] + val;
+}
+
+int launch_add_uniform(fsim_sim *s, int kind, double val)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        Bracket b(s, "add_uniform");
+        add_uniform_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
+            (Real *)s->B, s->nr, s->ncell_local, kind, (Real)val);
+        FSIM_CUDA(cudaGetLastError());
+        return (int)FSIM_OK;
+    });
+}
+
+}  // namespace fsim

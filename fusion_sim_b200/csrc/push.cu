@@ -1,0 +1,251 @@
+// push.cu -- the fused leap-frog half-step kernel (sm_100a).
+//
+// One launch = programStepRand + programStepVelocity + programStepPosition of the reference
+// (empic.js:1438-1451 or :1454-1467) for every particle: per-particle RNG update, nearest-grid-
+// point gather of the Boris rows R1..R3 and the half-kick A, rotation in cylindrical components,
+// push, sink-mask absorption and inverse-cdf respawn.  The three shaders of a half-step all read
+// the rand texture from BEFORE the update (bindings empic.js:819,832,849 / :894,907,924) and the
+// position shader reads the old position with the new velocity (:847-848), so the fusion is
+// exact and the update can be done in place (a particle touches only its own state).
+//
+// HBM-bound: 10 reals + 1 byte read and written per particle, streamed with 128-bit loads and
+// stores (ld.global.cs / st.global.cs keep the 126 MB L2 for the entropy and cell tables);
+// tables come through the read-only path.  Arithmetic is IEEE, left to right as the GLSL is
+// written, compiled with -fmad=false so it rounds exactly like the CPU oracle.
+#include "common.cuh"
+
+namespace fsim {
+
+template <typename Real>
+struct PushArgs {
+    Real *a[NPART_ARRAYS];
+    uint8_t *alive;
+    const Real *__restrict__ ent;
+    const Real *__restrict__ cellrec;
+    const uint8_t *__restrict__ sink;
+    const Real *__restrict__ invcdf;
+    uint32_t *key;      // optional: gather cell of the NEW position (+ histogram)
+    uint32_t *counts;
+    uint32_t *oob;
+    int64_t n;
+    int nr, nz, row0, rows;
+    Real sf;
+};
+
+template <typename Real, int V> struct Vec;
+template <> struct Vec<double, 2> { using T = double2; };
+template <> struct Vec<float, 4> { using T = float4; };
+template <> struct Vec<double, 1> { using T = double; };
+template <> struct Vec<float, 1> { using T = float; };
+
+template <typename Real, int V>
+__device__ __forceinline__ void ld_stream(const Real *p, Real (&o)[V])
+{
+    typename Vec<Real, V>::T t = __ldcs(reinterpret_cast<const typename Vec<Real, V>::T *>(p));
+    const Real *q = reinterpret_cast<const Real *>(&t);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = q[k];
+}
+template <typename Real, int V>
+__device__ __forceinline__ void st_stream(Real *p, const Real (&o)[V])
+{
+    typename Vec<Real, V>::T t;
+    Real *q = reinterpret_cast<Real *>(&t);
+#pragma unroll
+    for (int k = 0; k < V; ++k) q[k] = o[k];
+    __stcs(reinterpret_cast<typename Vec<Real, V>::T *>(p), t);
+}
+
+// 4 reals of one entropy texel / 12 reals of one cell record through the read-only path
+__device__ __forceinline__ void ld_ro4(const double *p, double (&o)[4])
+{
+    double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+__device__ __forceinline__ void ld_ro4(const float *p, float (&o)[4])
+{
+    float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+__device__ __forceinline__ void ld_ro12(const double *p, double (&o)[12])
+{
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double2 a = __ldg(reinterpret_cast<const double2 *>(p) + k);
+        o[2 * k] = a.x; o[2 * k + 1] = a.y;
+    }
+}
+__device__ __forceinline__ void ld_ro12(const float *p, float (&o)[12])
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(p) + k);
+        o[4 * k] = a.x; o[4 * k + 1] = a.y; o[4 * k + 2] = a.z; o[4 * k + 3] = a.w;
+    }
+}
+__device__ __forceinline__ void ld_ro2(const double *p, double &a, double &b)
+{
+    double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+    a = t.x; b = t.y;
+}
+__device__ __forceinline__ void ld_ro2(const float *p, float &a, float &b)
+{
+    float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    a = t.x; b = t.y;
+}
+
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) push_kernel(const PushArgs<Real> a)
+{
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (p0 >= a.n) return;
+
+    Real x[V], y[V], z[V], vx[V], vy[V], vz[V], q0[V], q1[V], q2[V], q3[V];
+    uint8_t al[V];
+    ld_stream<Real, V>(a.a[AQ2] + p0, q2);
+    ld_stream<Real, V>(a.a[AQ3] + p0, q3);
+    ld_stream<Real, V>(a.a[AX] + p0, x);
+    ld_stream<Real, V>(a.a[AY] + p0, y);
+    ld_stream<Real, V>(a.a[AZ] + p0, z);
+    ld_stream<Real, V>(a.a[AQ0] + p0, q0);
+    ld_stream<Real, V>(a.a[AQ1] + p0, q1);
+    ld_stream<Real, V>(a.a[AVX] + p0, vx);
+    ld_stream<Real, V>(a.a[AVY] + p0, vy);
+    ld_stream<Real, V>(a.a[AVZ] + p0, vz);
+#pragma unroll
+    for (int k = 0; k < V; ++k) al[k] = a.alive[p0 + k];
+
+    // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
+    Real e[V][4], rec[V][12], dx[V], dy[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int ie = tex_idx(q2[k], FSIM_N_ENTROPY) + FSIM_N_ENTROPY * tex_idx(q3[k], FSIM_N_ENTROPY);
+        ld_ro4(a.ent + 4 * (size_t)ie, e[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const Real r = fsqrt(x[k] * x[k] + y[k] * y[k]);  // :755
+        dx[k] = x[k] / r;                                 // :756
+        dy[k] = y[k] / r;
+        const int ci = tex_idx(r, a.nr);
+        int cj = tex_idx(z[k], a.nz) - a.row0;
+        if (cj < 0 || cj >= a.rows) {  // slab mode: particle outside the local table
+            if (p0 + k < a.n) atomicAdd(a.oob, 1u);
+            cj = cj < 0 ? 0 : a.rows - 1;
+        }
+        ld_ro12(a.cellrec + FSIM_CELLREC * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
+    }
+
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        // ---- programStepRandA/B, empic.js:800-807 ----
+        const Real x0 = (Real)FSIM_RNG_KEEP * q2[k] + (Real)FSIM_RNG_MIX * e[k][2];
+        const Real x1 = (Real)FSIM_RNG_KEEP * q3[k] + (Real)FSIM_RNG_MIX * e[k][3];
+        const Real m0 = q0[k] + e[k][0];
+        const Real m1 = q1[k] + e[k][1];
+        const Real o0 = q0[k], o1 = q1[k], o2 = q2[k];  // shaders below read the OLD rand
+        q0[k] = (m0 > (Real)1.0) ? m0 - (Real)1.0 : m0;
+        q1[k] = (m1 > (Real)1.0) ? m1 - (Real)1.0 : m1;
+        q2[k] = (Real)4.0 * x0 * ((Real)1.0 - x0);
+        q3[k] = (Real)4.0 * x1 * ((Real)1.0 - x1);
+
+        // ---- step_velocity_frag, empic.js:758-772 ----
+        const Real vr = vx[k] * dx[k] + vy[k] * dy[k];
+        const Real va = vy[k] * dx[k] - vx[k] * dy[k];
+        const Real *R = rec[k];
+        const Real c0 = (R[0] * vr + R[1] * va + R[2] * vz[k]) + R[9];
+        const Real c1 = (R[3] * vr + R[4] * va + R[5] * vz[k]) + R[10];
+        const Real c2 = (R[6] * vr + R[7] * va + R[8] * vz[k]) + R[11];
+        Real nvx, nvy, nvz;
+        if (al[k]) {
+            nvx = c0 * dx[k] - c1 * dy[k];
+            nvy = c0 * dy[k] + c1 * dx[k];
+            nvz = c2;
+        } else {  // just respawned: fresh random velocity (:772)
+            nvx = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o0 - (Real)1.0);
+            nvy = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o1 - (Real)1.0);
+            nvz = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o2 - (Real)1.0);
+        }
+        vx[k] = nvx; vy[k] = nvy; vz[k] = nvz;
+
+        // ---- step_position_frag, empic.js:714-719 ----
+        const Real nx = x[k] + a.sf * nvx;
+        const Real ny = y[k] + a.sf * nvy;
+        const Real nzp = z[k] + a.sf * nvz;
+        const Real rn = fsqrt(nx * nx + ny * ny);
+        bool keep = false;
+        if (rn == rn && nzp == nzp)  // NaN position => absorbed (documented rule)
+            keep = __ldg(a.sink + ((size_t)tex_idx(rn, a.nr) + (size_t)tex_idx(nzp, a.nz) * a.nr)) != 0;
+        if (keep) {
+            x[k] = nx; y[k] = ny; z[k] = nzp; al[k] = 1;
+        } else {
+            const int it = tex_idx(o0, FSIM_N_INVCDF) + FSIM_N_INVCDF * tex_idx(o1, FSIM_N_INVCDF);
+            Real sx, sz;
+            ld_ro2(a.invcdf + 2 * (size_t)it, sx, sz);
+            x[k] = sx; y[k] = (Real)0.0; z[k] = sz; al[k] = 0;
+        }
+    }
+
+    st_stream<Real, V>(a.a[AX] + p0, x);
+    st_stream<Real, V>(a.a[AY] + p0, y);
+    st_stream<Real, V>(a.a[AZ] + p0, z);
+    st_stream<Real, V>(a.a[AVX] + p0, vx);
+    st_stream<Real, V>(a.a[AVY] + p0, vy);
+    st_stream<Real, V>(a.a[AVZ] + p0, vz);
+    st_stream<Real, V>(a.a[AQ0] + p0, q0);
+    st_stream<Real, V>(a.a[AQ1] + p0, q1);
+    st_stream<Real, V>(a.a[AQ2] + p0, q2);
+    st_stream<Real, V>(a.a[AQ3] + p0, q3);
+#pragma unroll
+    for (int k = 0; k < V; ++k) a.alive[p0 + k] = al[k];
+
+    if (a.key) {  // fused first pass of the counting sort: key + histogram of the NEW cell
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (p0 + k >= a.n) break;
+            const Real r = fsqrt(x[k] * x[k] + y[k] * y[k]);
+            int cj = tex_idx(z[k], a.nz) - a.row0;
+            cj = cj < 0 ? 0 : (cj >= a.rows ? a.rows - 1 : cj);
+            const uint32_t c = (uint32_t)tex_idx(r, a.nr) + (uint32_t)cj * a.nr;
+            a.key[p0 + k] = c;
+            atomicAdd(a.counts + c, 1u);
+        }
+    }
+}
+
+template <typename Real, int V>
+static int push_impl(fsim_sim *s, bool with_hist)
+{
+    PushArgs<Real> a;
+    for (int k = 0; k < NPART_ARRAYS; ++k) a.a[k] = (Real *)s->part[s->cur][k];
+    a.alive = s->alive[s->cur];
+    a.ent = (const Real *)s->entropy;
+    a.cellrec = (const Real *)s->cellrec;
+    a.sink = s->sink;
+    a.invcdf = (const Real *)s->invcdf;
+    a.key = with_hist ? s->key : nullptr;
+    a.counts = s->counts;
+    a.oob = s->oob;
+    a.n = s->n;
+    a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
+    a.sf = (Real)s->step_factor;
+    const int block = 256;
+    const int64_t nvec = (s->n + V - 1) / V;
+    if (nvec == 0) return FSIM_OK;
+    Bracket b(s, "push");
+    push_kernel<Real, V><<<grid_for(nvec, block), block, 0, s->stream>>>(a);
+    FSIM_CUDA(cudaGetLastError());
+    return FSIM_OK;
+}
+
+int launch_push(fsim_sim *s)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        constexpr int V = 16 / sizeof(Real);  // 128-bit loads and stores
+        return push_impl<Real, V>(s, false);
+    });
+}
+
+}  // namespace fsim

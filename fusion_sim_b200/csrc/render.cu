@@ -1,0 +1,71 @@
+// render.cu -- out.canvas: what the page draws each frame (sm_100a).
+//
+// programBMag (empic.js:479-482) drawn to the RGBA8 canvas without blending, then
+// programDensity (empic.js:1101-1105) blended SRC_ALPHA,ONE (out.density :1497-1504).  The canvas
+// is a fixed-point target: each draw's colour is clamped to [0,1] and stored as round(255 c);
+// NaN converts to 0.  Rows are written in canvas order (top row = GL row nz-1).
+#include "common.cuh"
+
+namespace fsim {
+
+template <typename Real>
+__device__ __forceinline__ Real clamp01(Real v)
+{
+    if (!(v > (Real)0)) return (Real)0;
+    if (v > (Real)1) return (Real)1;
+    return v;
+}
+template <typename Real>
+__device__ __forceinline__ Real quant8(Real v)
+{
+    return ffloor(v * (Real)255.0 + (Real)0.5);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+render_kernel(const Real *__restrict__ B, const Real *__restrict__ avg, uint8_t *__restrict__ rgba,
+              int nr, int nz, int row0, int own0, int own_rows)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nr * own_rows) return;
+    const int i = (int)(t % nr), j = own0 + (int)(t / nr);
+    const size_t c = (size_t)i + (size_t)(j - row0) * nr;
+    const Real Bx = B[3 * c], By = B[3 * c + 1], Bz = B[3 * c + 2];
+    const Real mag = fsqrt(Bx * Bx + By * By + Bz * Bz);
+    const Real dx = Bx / mag, dz = Bz / mag;
+    const Real mn = (dz < (Real)0) ? dz : (Real)0;
+    const Real mx = (dz > (Real)0) ? dz : (Real)0;
+    Real c1[4];
+    c1[0] = mag * ((mn < (Real)0) ? -mn : mn);
+    c1[1] = mag * dx;
+    c1[2] = mag * ((mx < (Real)0) ? -mx : mx);
+    c1[3] = (Real)1.0;
+    const Real a = avg[4 * c + 3];
+    const Real sc = (Real)FSIM_RENDER_DENSITY * a;
+    const Real src[4] = {sc, sc, sc, (Real)FSIM_RENDER_DENSITY * (Real)1.0};
+    const Real sa = clamp01(src[3]);
+    uchar4 o;
+    uint8_t *po = reinterpret_cast<uint8_t *>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const Real dst = quant8(clamp01(c1[q])) / (Real)255.0;
+        const Real out = clamp01(src[q]) * sa + dst;
+        po[q] = (uint8_t)quant8(clamp01(out));
+    }
+    reinterpret_cast<uchar4 *>(rgba)[(size_t)i + (size_t)(nz - 1 - j) * nr] = o;
+}
+
+int launch_render(fsim_sim *s, uint8_t *dev_rgba)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        Bracket b(s, "render");
+        render_kernel<Real><<<grid_for((int64_t)s->nr * s->own_rows, 256), 256, 0, s->stream>>>(
+            (const Real *)s->B, (const Real *)s->avg, dev_rgba, s->nr, s->nz, s->row0, s->own0,
+            s->own_rows);
+        FSIM_CUDA(cudaGetLastError());
+        return (int)FSIM_OK;
+    });
+}
+
+}  // namespace fsim

@@ -1,0 +1,227 @@
+"""Headless host driver: the simulation object of the reference, backed by libfusionsim.so.
+
+``makeCylindricalParticlePusher(spec)`` mirrors ``empic.makeCylindricalParticlePusher``
+(public/javascripts/empic.js:30) and returns an object with the reference's ten members
+(empic.js:60, :1157-:1526): ``canvas, set, addCurrentLoop, addSpindleCuspPlasmaField,
+addCurrentZ, addBZ, addBTheta, precalc, step, density`` -- same names, argument meaning, units
+and error behaviour (a synchronous ``Error``).  Beside them sit the accessors the reference
+lacks and the seeding inputs (row 4).
+
+All arithmetic happens in the CUDA library; this file only re-shapes arrays.  There is no
+CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numbers
+
+import numpy as np
+
+from . import _lib
+from ._lib import Error, FsimSpec, check, lib, ptr
+
+_REQUIRED = ("radius", "height", "nr", "nz", "dt", "nparticles", "particle_mass", "particle_charge")
+_EXT = ("precision", "device", "flags", "sort_interval", "nparticles_total", "capacity", "slab_row0",
+        "slab_rows", "halo_rows", "id_base", "seed", "corrected_preA", "keep_moments")
+
+
+def validate_object(test: dict, control: dict):
+    """utilities.validate_object / validate_property (utilities.js:11-127) for 'number' controls."""
+    for prop, kind in control.items():
+        v = test.get(prop) if isinstance(test, dict) else getattr(test, prop, None)
+        if v is None:
+            raise Error("." + prop + " <- Non-optional property is undefined!", _lib.ERR_INVALID)
+        if kind == "number" and (isinstance(v, bool) or not isinstance(v, numbers.Real)):
+            raise Error("." + prop + " <- Property does not match any given possible types!",
+                        _lib.ERR_INVALID)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        if a.size != int(np.prod(shape)):
+            raise Error(f"array has {a.size} elements, expected shape {tuple(shape)}", _lib.ERR_INVALID)
+        a = a.reshape(shape)
+    return a
+
+
+class CylindricalParticlePusher:
+    """Object returned by :func:`makeCylindricalParticlePusher`."""
+
+    def __init__(self, spec: dict):
+        validate_object(spec, {k: "number" for k in _REQUIRED})
+        self.spec = dict(spec)
+        cs = FsimSpec()
+        for k in _REQUIRED:
+            setattr(cs, k, spec[k])
+        prec = spec.get("precision", "f64")
+        cs.precision = {"f64": 0, "f32": 1, 0: 0, 1: 1}[prec]
+        flags = int(spec.get("flags", 0))
+        if spec.get("corrected_preA"):
+            flags |= _lib.FLAG_CORRECTED_PREA
+        if spec.get("keep_moments"):
+            flags |= _lib.FLAG_KEEP_MOMENTS
+        cs.flags = flags
+        for k in ("device", "sort_interval", "nparticles_total", "capacity", "slab_row0", "slab_rows",
+                  "halo_rows", "id_base"):
+            setattr(cs, k, int(spec.get(k, 0)))
+        self.precision = "f64" if cs.precision == 0 else "f32"
+        self.nr, self.nz = int(spec["nr"]), int(spec["nz"])
+        self._h = C.c_void_p()
+        check(lib().fsim_create(C.byref(cs), C.byref(self._h)))
+        self.ncell_local = int(lib().fsim_local_cells(self._h))
+        seed = spec.get("seed")
+        if seed is not None:
+            from .scenes import seeded_rand_entropy
+            r, e = seeded_rand_entropy(int(seed), self.n)
+            self.set({"rand": r, "entropy": e})
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def destroy(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().fsim_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def n(self) -> int:
+        return int(lib().fsim_particle_count(self._h))
+
+    # -- out.set(value), empic.js:1157-1350 -------------------------------------------------
+    def set(self, value: dict):
+        L, h = lib(), self._h
+        if value.get("E") is not None:
+            check(L.fsim_set_E(h, ptr(_f64(value["E"], (self.nr, self.nz, 3)))))
+        if value.get("B") is not None:
+            check(L.fsim_set_B(h, ptr(_f64(value["B"], (self.nr, self.nz, 3)))))
+        if value.get("position") is not None:
+            check(L.fsim_set_position(h, ptr(_f64(value["position"], (self.n, 3)))))
+        if value.get("velocity") is not None:
+            check(L.fsim_set_velocity(h, ptr(_f64(value["velocity"], (self.n, 3)))))
+        if value.get("sink_mask") is not None:
+            check(L.fsim_set_sink_mask(h, ptr(_f64(value["sink_mask"], (self.nr, self.nz)))))
+        if value.get("source_pdf") is not None:
+            pdf = _f64(value["source_pdf"])
+            if pdf.ndim != 2:
+                raise Error(".source_pdf <- must be a 2-D array", _lib.ERR_INVALID)
+            check(L.fsim_set_source_pdf(h, ptr(pdf), pdf.shape[0], pdf.shape[1]))
+        # extensions (seeding; raw inverse-cdf table)
+        if value.get("rand") is not None:
+            check(L.fsim_set_rand(h, ptr(_f64(value["rand"], (self.n, 4)))))
+        if value.get("entropy") is not None:
+            check(L.fsim_set_entropy(h, ptr(_f64(value["entropy"], (1024 * 1024, 4)))))
+        if value.get("inv_cdf") is not None:
+            check(L.fsim_set_inv_cdf(h, ptr(_f64(value["inv_cdf"], (512 * 512, 2)))))
+
+    # -- static field builders, empic.js:1352-1411 -----------------------------------------
+    def addCurrentLoop(self, r, z, I):
+        check(lib().fsim_add_current_loop(self._h, r, z, I))
+
+    def addSpindleCuspPlasmaField(self, r, B_c, beta_c=0.0):
+        check(lib().fsim_add_spindle_cusp_plasma_field(self._h, r, B_c, beta_c))
+
+    def addCurrentZ(self, I):
+        check(lib().fsim_add_current_z(self._h, I))
+
+    def addBZ(self, Bz):
+        check(lib().fsim_add_bz(self._h, Bz))
+
+    def addBTheta(self, Btheta):
+        check(lib().fsim_add_btheta(self._h, Btheta))
+
+    # -- precalc / step / density / canvas, empic.js:1413-1505 --------------------------------
+    def precalc(self):
+        check(lib().fsim_precalc(self._h))
+
+    def step(self):
+        check(lib().fsim_step(self._h))
+
+    def half_step(self):
+        check(lib().fsim_half_step(self._h))
+
+    def density(self):
+        check(lib().fsim_density(self._h))
+
+    def render(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.nz, self.nr, 4), np.uint8)
+        check(lib().fsim_render_rgba8(self._h, ptr(out)))
+        return out
+
+    @property
+    def canvas(self) -> np.ndarray:
+        """RGBA8 image [nz][nr][4], top row first: what `drawImage(simulation.canvas)` shows."""
+        return self.render()
+
+    def sort(self):
+        check(lib().fsim_sort(self._h))
+
+    def sync(self):
+        check(lib().fsim_sync(self._h))
+
+    # -- accessors (extension) -----------------------------------------------------------------
+    def _get(self, fn, shape, dtype=np.float64):
+        out = np.empty(shape, dtype)
+        check(fn(self._h, ptr(out)))
+        return out
+
+    def getPosition(self):
+        """[N][4] normalised x, y, z and the alive flag (position.w of the reference)."""
+        return self._get(lib().fsim_get_position, (self.n, 4))
+
+    def getVelocity(self):
+        return self._get(lib().fsim_get_velocity, (self.n, 3))
+
+    def getRand(self):
+        return self._get(lib().fsim_get_rand, (self.n, 4))
+
+    def getIds(self):
+        return self._get(lib().fsim_get_ids, (self.n,), np.uint64)
+
+    def getCells(self):
+        return self._get(lib().fsim_get_cells, (self.n,), np.int64)
+
+    def getField(self, name: str):
+        nc = self.ncell_local
+        if name == "cell_count":
+            return self._get(lib().fsim_get_cell_count, (nc,), np.uint32)
+        if name == "sink_mask":
+            return self._get(lib().fsim_get_sink_mask, (self.nr * self.nz,), np.uint8)
+        shape = {"E": (nc, 3), "B": (nc, 3), "R1": (nc, 3), "R2": (nc, 3), "R3": (nc, 3), "A": (nc, 3),
+                 "cell_sums": (nc, 4), "moments01": (nc, 4), "moments01_norm": (nc, 4),
+                 "moments01_avg": (nc, 4), "inv_cdf": (512 * 512, 2), "entropy": (1024 * 1024, 4)}.get(name)
+        if shape is None:
+            raise Error("unknown field name: " + name, _lib.ERR_INVALID)
+        out = np.empty(shape, np.float64)
+        check(lib().fsim_get_field(self._h, name.encode(), ptr(out)))
+        return out
+
+    # -- measurement hooks ---------------------------------------------------------------------
+    def timing(self, on: bool):
+        check(lib().fsim_timing_enable(self._h, 1 if on else 0))
+
+    def timing_reset(self):
+        check(lib().fsim_timing_reset(self._h))
+
+    def timing_get(self, name: str):
+        ms, n = C.c_double(), C.c_int64()
+        check(lib().fsim_timing_get(self._h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().fsim_launch_count(self._h))
+
+
+def makeCylindricalParticlePusher(spec: dict) -> CylindricalParticlePusher:
+    """empic.makeCylindricalParticlePusher(spec), empic.js:30."""
+    return CylindricalParticlePusher(spec)

@@ -1,0 +1,152 @@
+/* fusionsim.h -- C ABI of libfusionsim.so, the B200-native particle-step engine that
+ * replaces the WebGL back end of kcdodd/fusion-sim's
+ *     empic.makeCylindricalParticlePusher(spec)      (public/javascripts/empic.js:30)
+ * One fsim_* entry point per member of the object that constructor returns
+ * (empic.js:60, :1157-:1526).  Plain pointers and sizes only; all array arguments are
+ * HOST pointers (doubles = JS Numbers) copied during the call; the handle owns every
+ * device buffer.  Every function returns 0 on success or an FSIM_ERR_* code;
+ * fsim_last_error() gives the message the JS shim turns into `throw new Error(msg)`
+ * (the reference reports every failure by a synchronous throw: utilities.js:118-127,
+ * :213-260, :678-680).  There is no CPU fallback: without a CUDA device fsim_create
+ * fails with FSIM_ERR_CUDA.
+ *
+ * Array conventions (flattened JS nesting, row-major):
+ *   field  value.E / value.B          [nr][nz][3]  -> (i*nz + j)*3 + k   empic.js:1160-1166
+ *   grid   value.sink_mask/source_pdf [nr][nz]     -> i*nz + j           empic.js:1247-1250
+ *   particle value.position/velocity  [N][3]       -> 3*p + k            empic.js:1201-1205
+ * Units as in the reference: positions in metres, velocities in units of c, fields in
+ * tesla and V/m; fsim_set_* normalises exactly as empic.js:1202-1204, :1226-1228.
+ * Accessors return the NORMALISED device state (r in [0,1], z in [0,1]).
+ * Device textures are addressed texel (i,j) -> i + j*nr (empic.js:1162): cell-indexed
+ * accessors use that order.
+ */
+#ifndef FUSIONSIM_H
+#define FUSIONSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSIM_ABI_VERSION 1
+
+enum {
+    FSIM_OK = 0,
+    FSIM_ERR_INVALID = 1,     /* bad argument / spec validation (utilities.js:118-127)      */
+    FSIM_ERR_CUDA = 2,        /* CUDA runtime failure; sticky on the handle                 */
+    FSIM_ERR_UNSUPPORTED = 3, /* addSpindleCuspPlasmaField: does not run in the reference   */
+    FSIM_ERR_STATE = 4,       /* call order violated (e.g. step before precalc)             */
+    FSIM_ERR_RANGE = 5        /* "function out of range" (empic.js:1294-1296), capacity     */
+};
+
+enum { FSIM_F64 = 0, FSIM_F32 = 1 };
+
+/* flags */
+#define FSIM_FLAG_CORRECTED_PREA  1u /* textbook h(E.B)B instead of the scalar add of empic.js:645 */
+#define FSIM_FLAG_KEEP_MOMENTS    2u /* density() also stores moments01 and moments01_norm          */
+#define FSIM_FLAG_ATOMIC_DEPOSIT  4u /* measured alternative: global-atomic per-cell sums           */
+
+typedef struct fsim_sim fsim_sim;
+
+/* spec of empic.js:31-41 (first 8 fields, same names) plus the extension fields the
+ * headless build needs.                       */
+typedef struct fsim_spec {
+    double radius;          /* metres                                                     */
+    double height;          /* metres                                                     */
+    int64_t nr;             /* grid cells along r                                         */
+    int64_t nz;             /* grid cells along z (GLOBAL grid)                           */
+    double dt;              /* seconds                                                    */
+    int64_t nparticles;     /* SIDE of the particle texture: N = nparticles^2 (:107-109)  */
+    double particle_mass;   /* kg                                                         */
+    double particle_charge; /* C                                                          */
+    /* ---- extensions ---- */
+    int32_t precision;      /* FSIM_F64 (default) | FSIM_F32 (mirrors RGBA32F storage)    */
+    int32_t device;         /* CUDA device ordinal                                        */
+    uint32_t flags;         /* FSIM_FLAG_*                                                */
+    int32_t sort_interval;  /* re-sort particles by cell every k step() calls, 0 = only in density() */
+    int64_t nparticles_total; /* if > 0: particle count, overrides nparticles^2           */
+    int64_t capacity;       /* particle slots to allocate (>= count; 0 = count)           */
+    int64_t slab_row0;      /* multi-GPU slab: first grid row (z index) owned             */
+    int64_t slab_rows;      /* rows owned; 0 = whole grid (single GPU)                    */
+    int64_t halo_rows;      /* extra table rows kept either side of the slab              */
+    uint64_t id_base;       /* global index of local particle 0 (multi-GPU)               */
+} fsim_spec;
+
+const char *fsim_last_error(void);
+int fsim_abi_version(void);
+
+/* ---- constructor / destructor : empic.js:30 (the reference never frees) ---------------- */
+int fsim_create(const fsim_spec *spec, fsim_sim **out);
+int fsim_destroy(fsim_sim *sim);
+
+/* ---- out.set(value), empic.js:1157-1350; one call per optional property ----------------- */
+int fsim_set_E(fsim_sim *sim, const double *E);                 /* value.E         :1159-1177 */
+int fsim_set_B(fsim_sim *sim, const double *B);                 /* value.B         :1179-1197 */
+int fsim_set_position(fsim_sim *sim, const double *pos);        /* value.position  :1199-1221 */
+int fsim_set_velocity(fsim_sim *sim, const double *vel);        /* value.velocity  :1223-1244 */
+int fsim_set_sink_mask(fsim_sim *sim, const double *mask);      /* value.sink_mask :1246-1260 */
+int fsim_set_source_pdf(fsim_sim *sim, const double *pdf, int64_t n0, int64_t n1); /* :1263-1349 */
+/* extensions: the reference draws these from Math.random / window.crypto (empic.js:148-173) */
+int fsim_set_rand(fsim_sim *sim, const double *rnd);            /* [N][4] in [0,1]            */
+int fsim_set_entropy(fsim_sim *sim, const double *entropy);     /* [1024*1024][4] in [0,1]    */
+int fsim_set_inv_cdf(fsim_sim *sim, const double *table);       /* [512*512][2], texel i+j*512 */
+int fsim_set_particle_count(fsim_sim *sim, int64_t n);          /* multi-GPU: live count <= capacity */
+int fsim_set_ids(fsim_sim *sim, const uint64_t *ids);           /* multi-GPU: global particle ids */
+
+/* ---- static field builders, blended ONE,ONE into B ---------------------------------------- */
+int fsim_add_current_loop(fsim_sim *sim, double r, double z, double I); /* addCurrentLoop :1352 */
+int fsim_add_current_z(fsim_sim *sim, double I);                        /* addCurrentZ    :1380 */
+int fsim_add_bz(fsim_sim *sim, double Bz);                              /* addBZ          :1391 */
+int fsim_add_btheta(fsim_sim *sim, double Btheta);                      /* addBTheta      :1402 */
+int fsim_add_spindle_cusp_plasma_field(fsim_sim *sim, double r, double B_c, double beta_c); /* :1369 */
+
+/* ---- precalc / step / density / canvas ----------------------------------------------------- */
+int fsim_precalc(fsim_sim *sim);   /* out.precalc :1413-1434: (E,B) -> R1,R2,R3,A per cell      */
+int fsim_step(fsim_sim *sim);      /* out.step    :1436-1469: TWO leap-frog half-steps         */
+int fsim_half_step(fsim_sim *sim); /* extension: one half-step (rand, velocity, position)      */
+int fsim_density(fsim_sim *sim);   /* out.density :1471-1495: deposit, normalise, running avg  */
+int fsim_render_rgba8(fsim_sim *sim, uint8_t *rgba); /* out.canvas :60 after :1497-1504; [nz][nr][4], top row first */
+int fsim_sort(fsim_sim *sim);      /* extension: re-sort particle storage by cell now          */
+int fsim_sync(fsim_sim *sim);      /* wait for the handle's stream                             */
+
+/* ---- accessors (extension; the reference exposes none) ---------- */
+int64_t fsim_particle_count(const fsim_sim *sim);
+int64_t fsim_local_cells(const fsim_sim *sim); /* nr * (slab_rows + 2*halo_rows) or nr*nz      */
+int fsim_get_position(fsim_sim *sim, double *out);  /* [N][4]: x,y,z,alive in particle-id order */
+int fsim_get_velocity(fsim_sim *sim, double *out);  /* [N][3]                                   */
+int fsim_get_rand(fsim_sim *sim, double *out);      /* [N][4]                                   */
+int fsim_get_ids(fsim_sim *sim, uint64_t *out);     /* [N] ids in STORAGE order                 */
+int fsim_get_cells(fsim_sim *sim, int64_t *out);    /* [N] gather cell i+j*nr of each particle  */
+/* name: "E","B","R1","R2","R3","A" -> [cells][3]; "cell_sums","moments01","moments01_norm",
+ * "moments01_avg" -> [cells][4]; "inv_cdf" -> [512*512][2]; "entropy" -> [1024*1024][4]      */
+int fsim_get_field(fsim_sim *sim, const char *name, double *out);
+int fsim_get_cell_count(fsim_sim *sim, uint32_t *out); /* [cells] particles deposited per cell   */
+int fsim_get_sink_mask(fsim_sim *sim, uint8_t *out);   /* [nr*nz] 1 = keep, 0 = absorb           */
+
+/* ---- measurement hooks (extension) ----------------------------------------------------------- */
+/* Per-kernel device time (ms, CUDA events on the handle's stream) accumulated since the last
+ * reset, and launch counts.  names: "push","hist","scan","scatter","cellsum","conv","render".   */
+int fsim_timing_enable(fsim_sim *sim, int on);
+int fsim_timing_reset(fsim_sim *sim);
+int fsim_timing_get(fsim_sim *sim, const char *name, double *ms, int64_t *launches);
+int64_t fsim_launch_count(const fsim_sim *sim); /* kernels launched by this handle so far          */
+
+/* ---- multi-GPU slab exchange (extension) -------------------------------- */
+/* Particles leaving the slab are packed into a device buffer grouped by destination rank;
+ * row_bounds[k]..row_bounds[k+1] are the grid rows rank k owns.  The caller (one process per
+ * GPU) moves the packed records with its own collective and hands them to fsim_migrate_unpack.  */
+int64_t fsim_migrate_record_bytes(const fsim_sim *sim);
+int fsim_migrate_pack(fsim_sim *sim, const int64_t *row_bounds, int32_t nranks, int32_t self,
+                      int64_t *send_counts /* host [nranks] */, void **send_buf_dev);
+int fsim_migrate_unpack(fsim_sim *sim, const void *recv_buf_dev, int64_t nrecv);
+/* Halo of the per-cell sums (5 rows each side) for the slab convolution. */
+int fsim_halo_ptrs(fsim_sim *sim, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi,
+                   int64_t *bytes_each);
+int fsim_density_begin(fsim_sim *sim); /* sort + per-cell sums (before the halo exchange)        */
+int fsim_density_end(fsim_sim *sim);   /* convolution + normalise + running average              */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUSIONSIM_H */

@@ -1,0 +1,135 @@
+/* fsim_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU oracle for the particle-step path of kcdodd/fusion-sim: a restatement of
+ * the reference's GLSL shaders and host-side set() code in plain C.
+ * PARITY UNPINNED (no reference tests/golden vectors exist; the reference
+ * cannot run here) -- see the header of fsim_oracle_impl.h and DESIGN.md.
+ *
+ * Build: oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+ * Callers: tests/, __graft_entry__.smoke(), bench.py cpu_baseline and
+ * --impl reference.  Never the product.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/fsim_constants.h"
+
+static inline double orc_sqrt_f64(double x) { return sqrt(x); }
+static inline float orc_sqrt_f32(float x) { return sqrtf(x); }
+static inline double orc_floor_f64(double x) { return floor(x); }
+static inline float orc_floor_f32(float x) { return floorf(x); }
+
+#define REAL double
+#define SFX f64
+#include "fsim_oracle_impl.h"
+#undef REAL
+#undef SFX
+
+#define REAL float
+#define SFX f32
+#include "fsim_oracle_impl.h"
+#undef REAL
+#undef SFX
+
+/* N(num) = num.toFixed(20) (empic.js:23-25) parsed back by the GLSL compiler. */
+double orc_tofixed20(double x)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%.20f", x);
+    return strtod(buf, NULL);
+}
+
+/* cos(PI*(k+0.5)/1000) of empic.js:317, evaluated in double by the host libm
+ * (the GLSL literal 3.14159265359), one value per quadrature point.          */
+void orc_cos_table(double *out)
+{
+    for (int k = 0; k < FSIM_NQUAD; ++k)
+        out[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);
+}
+
+/* Deposit footprint, empic.js:949-971.  as_f32 != 0 reproduces the
+ * Float32Array round trips of the reference (store, re-read, divide, store). */
+void orc_shape_table(double *out /* 121 */, int as_f32)
+{
+    const int n = FSIM_NSHAPE;
+    const double mid = (n - 1) / 2.0;
+    double sum = 0.0;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            double d = sqrt(pow(i - mid, 2) + pow(j - mid, 2));
+            double c = cos(0.5 * M_PI * d / mid);
+            double v = pow(c > 0.0 ? c : 0.0, 2);
+            if (as_f32) v = (double)(float)v;
+            out[i + n * j] = v;
+            sum += v;
+        }
+    for (int k = 0; k < n * n; ++k) {
+        double v = out[k] / sum;
+        out[k] = as_f32 ? (double)(float)v : v;
+    }
+}
+
+/* source_pdf -> 512x512 inverse-cdf table, empic.js:1268-1339, host doubles.
+ * pdf is [n0][n1] row-major (pdf[i][j], i along r).  out is [512*512][2]
+ * with texel (i,j) at 2*(i + j*512): (x, y).  NaN behaviour of the JS code is
+ * kept (0/0 rows, comparisons with NaN are false).                           */
+int orc_inv_cdf(const double *pdf, int64_t n0, int64_t n1, double *out)
+{
+    double *cdf_y = (double *)malloc(sizeof(double) * (size_t)(n0 * n1));
+    double *cdf_x = (double *)malloc(sizeof(double) * (size_t)n0);
+    if (!cdf_y || !cdf_x) return -1;
+    double sum_x = 0.0;
+    for (int64_t i = 0; i < n0; ++i) {
+        double sum_y = 0.0;
+        for (int64_t j = 0; j < n1; ++j) {
+            sum_y += pdf[i * n1 + j];
+            cdf_y[i * n1 + j] = sum_y;
+        }
+        for (int64_t j = 0; j < n1; ++j) cdf_y[i * n1 + j] /= sum_y;
+        sum_x += sum_y;
+        cdf_x[i] = sum_x;
+    }
+    for (int64_t i = 0; i < n0; ++i) cdf_x[i] /= sum_x;
+
+    const int T = FSIM_N_INVCDF;
+    for (int ti = 0; ti < T; ++ti) {
+        double f1 = (double)ti / 511.0;
+        /* inverse_cdf_x(f1), empic.js:1293-1309 */
+        double x;
+        {
+            int64_t i = 0;
+            while (i < n0 && cdf_x[i] < f1) i++;
+            if (i >= n0) { x = NAN; }
+            else if (i == 0) x = (f1 / cdf_x[0]) / (double)n0;
+            else x = ((double)i + (f1 - cdf_x[i - 1]) / (cdf_x[i] - cdf_x[i - 1])) / (double)n0;
+        }
+        for (int tj = 0; tj < T; ++tj) {
+            double f2 = (double)tj / 511.0;
+            /* inverse_cdf_y(x, f2), empic.js:1311-1326 */
+            double y;
+            {
+                double fi = floor(x * (double)n0);
+                int64_t i = (fi < (double)(n0 - 1)) ? (int64_t)fi : n0 - 1;
+                if (!(fi == fi) || i < 0) { y = NAN; }
+                else {
+                    const double *cy = cdf_y + i * n1;
+                    int64_t j = 0;
+                    while (j < n1 && cy[j] < f2) j++;
+                    if (j >= n1) y = NAN;
+                    else if (j == 0) y = (f2 / cy[0]) / (double)n1;
+                    else y = ((double)j + (f2 - cy[j - 1]) / (cy[j] - cy[j - 1])) / (double)n1;
+                }
+            }
+            out[2 * (ti + tj * T) + 0] = x;
+            out[2 * (ti + tj * T) + 1] = y;
+        }
+    }
+    free(cdf_y);
+    free(cdf_x);
+    return 0;
+}
+
+int orc_abi_version(void) { return 1; }

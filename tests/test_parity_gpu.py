@@ -1,0 +1,204 @@
+"""GPU parity: libfusionsim.so (through the C ABI / host driver) against the CPU oracle on the
+same seeded inputs.  Bar: bit-exact -- the path is IEEE arithmetic in a fixed order on both
+sides (-fmad=false / -ffp-contract=off), so positions, velocities, RNG state, alive flags, cell
+indices, per-cell counts and all grid fields must be identical, in fp64 and in fp32 mode."""
+import numpy as np
+import pytest
+
+from conftest import assert_same, small_scene
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["f64", "f32"]
+
+
+def make_pair(sc, precalc=True):
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene
+    from oracle.oracle import OraclePusher
+    g = makeCylindricalParticlePusher(sc["spec"])
+    o = OraclePusher(sc["spec"], nthreads=4)
+    apply_scene(g, sc, precalc)
+    apply_scene(o, sc, precalc)
+    return g, o
+
+
+def compare_particles(g, o, what):
+    gp, op = g.getPosition(), o.getPosition()
+    assert_same(gp[:, 3], op[:, 3], what + " alive")
+    assert_same(gp, op, what + " position")
+    assert_same(g.getVelocity(), o.getVelocity(), what + " velocity")
+    assert_same(g.getRand(), o.getRand(), what + " rand")
+
+
+def compare_grid(g, o, names, what):
+    for nm in names:
+        assert_same(g.getField(nm), o.getField(nm), f"{what} {nm}")
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_set_conversions(precision):
+    sc = small_scene(precision=precision, with_E=True)
+    g, o = make_pair(sc, precalc=False)
+    compare_particles(g, o, "after set")
+    compare_grid(g, o, ["E", "sink_mask", "inv_cdf", "entropy"], "after set")
+    assert np.isnan(g.getField("inv_cdf")).sum() > 0  # the demo pdf yields NaN texels
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_static_fields_and_precalc(precision):
+    sc = small_scene(precision=precision, with_E=True)
+    sc["current_z"], sc["bz"], sc["btheta"] = 3.0e5, 0.02, -0.01
+    g, o = make_pair(sc)
+    compare_grid(g, o, ["B", "R1", "R2", "R3", "A"], "precalc")
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_corrected_preA(precision):
+    sc = small_scene(precision=precision, with_E=True)
+    sc["spec"]["corrected_preA"] = True
+    g, o = make_pair(sc)
+    compare_grid(g, o, ["A"], "corrected preA")
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_half_steps_bit_exact(precision):
+    sc = small_scene(precision=precision, n=4099)  # not a multiple of the vector width
+    g, o = make_pair(sc)
+    for k in range(30):
+        g.half_step(); o.half_step()
+        if k % 3 == 0 or k > 25:
+            compare_particles(g, o, f"half-step {k}")
+            assert_same(g.getCells(), _cells(o), f"half-step {k} cells")
+    g.sync()
+
+
+def _cells(o):
+    from oracle.numpy_ref import tex
+    p = o.position
+    r = np.sqrt(p[:, 0] * p[:, 0] + p[:, 1] * p[:, 1])
+    return tex(r, o.nr) + o.nr * tex(p[:, 2], o.nz)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_absorb_respawn_and_E(precision):
+    """Fast particles near the wall: absorption, inverse-cdf respawn (NaN texels and r = 0
+    included), fresh random velocity on the next half-step; E != 0 exercises A."""
+    sc = small_scene(precision=precision, n=8192, speed=0.2, with_E=True, blob=(0.6, 0.9))
+    g, o = make_pair(sc)
+    respawned = 0
+    for k in range(24):
+        g.half_step(); o.half_step()
+        respawned += int((o.position[:, 3] == 0).sum())
+        compare_particles(g, o, f"half-step {k}")
+    assert respawned > 100
+    assert np.isnan(o.position).any()  # NaN respawn texels were hit and handled alike
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_density_bit_exact(precision):
+    sc = small_scene(precision=precision, n=20000, speed=0.02, blob=(0.5, 0.8))
+    g, o = make_pair(sc)
+    for frame in range(4):
+        g.step(); o.step()
+        g.density(); o.density()
+        assert_same(g.getField("cell_count"), o.getField("cell_count"), f"frame {frame} counts")
+        compare_grid(g, o, ["cell_sums", "moments01", "moments01_norm", "moments01_avg"], f"frame {frame}")
+        compare_particles(g, o, f"frame {frame}")  # sorting must not disturb identities
+    assert_same(g.canvas, o.canvas, "canvas")
+    assert int(g.getField("cell_count").sum()) > 0
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_crowded_cells(precision):
+    """All particles in a few cells: exercises the block-per-cell (bitonic by id) deposit path."""
+    sc = small_scene(precision=precision, n=6000, speed=0.0005, blob=(0.01, 0.01))
+    g, o = make_pair(sc)
+    for frame in range(2):
+        g.step(); o.step()
+        g.density(); o.density()
+        assert g.getField("cell_count").max() > 64
+        assert_same(g.getField("cell_count"), o.getField("cell_count"), "counts")
+        compare_grid(g, o, ["cell_sums", "moments01_avg"], f"crowded frame {frame}")
+
+
+def test_sort_is_invisible():
+    sc = small_scene(n=5000, speed=0.05, blob=(0.5, 0.8))
+    g, o = make_pair(sc)
+    ids0 = g.getIds()
+    assert_same(ids0, np.arange(5000, dtype=np.uint64), "initial ids")
+    for k in range(6):
+        g.step(); o.step()
+        g.sort()
+        compare_particles(g, o, f"step {k} after sort")
+    ids = g.getIds()
+    assert sorted(ids.tolist()) == list(range(5000))
+    assert not np.array_equal(ids, ids0)
+    # set() after a sort addresses particles by id, not by storage slot
+    g.set({"velocity": sc["velocity"]}); o.set({"velocity": sc["velocity"]})
+    compare_particles(g, o, "set after sort")
+
+
+def test_c1_demo_scene_frames():
+    """Config C1 (fusionsim.js:72-148): 160 000 particles, 400x800 grid, frames of step+density."""
+    from fusion_sim_b200.scenes import c1_scene
+    sc = c1_scene(12345)
+    sc["spec"]["keep_moments"] = True
+    g, o = make_pair(sc)
+    compare_grid(g, o, ["B", "R1", "R2", "R3", "A"], "C1 precalc")
+    for frame in range(5):
+        g.step(); o.step()
+        g.density(); o.density()
+    compare_particles(g, o, "C1 frame 5")
+    assert_same(g.getField("cell_count"), o.getField("cell_count"), "C1 counts")
+    compare_grid(g, o, ["moments01", "moments01_avg"], "C1 frame 5")
+    assert_same(g.canvas, o.canvas, "C1 canvas")
+
+
+def test_errors_are_thrown():
+    from fusion_sim_b200 import Error, makeCylindricalParticlePusher
+    sc = small_scene(n=64)
+    with pytest.raises(Error, match=r"\.nr <- Non-optional property is undefined!"):
+        makeCylindricalParticlePusher({k: v for k, v in sc["spec"].items() if k != "nr"})
+    g = makeCylindricalParticlePusher(sc["spec"])
+    with pytest.raises(Error, match="spindle"):
+        g.addSpindleCuspPlasmaField(1.0, 0.5)
+    with pytest.raises(Error):
+        g.set({"position": np.zeros((3, 3))})
+
+
+def test_full_size_properties():
+    """Config C3 shape (16.7 M particles, 2048^2 grid): size-independent invariants.
+    Physical kinetic energy is conserved by the Boris rotation (E = 0) to rounding; RNG state
+    stays in [0,1]; the deposit accounts for every in-range particle exactly once."""
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene, c1_sink_source, plasma_particles, scaled_loops, scaled_spec
+    n, nr, nz = 1 << 24, 2048, 2048
+    spec = scaled_spec(nr, nz, n)
+    pos, vel = plasma_particles(spec, n, seed=3)
+    sink, source = c1_sink_source(nr, nz)
+    g = makeCylindricalParticlePusher(spec)
+    apply_scene(g, dict(position=pos, velocity=vel, sink_mask=sink, source_pdf=source,
+                        loops=scaled_loops(spec)))
+    fac = np.array([1 / spec["radius"], 1 / spec["radius"], 1 / spec["height"]])
+    e0 = ((g.getVelocity() / fac) ** 2).sum(1)
+    for _ in range(3):
+        g.step()
+    g.density()
+    g.sync()
+    p = g.getPosition()
+    stayed = p[:, 3] == 1
+    e1 = ((g.getVelocity() / fac) ** 2).sum(1)
+    rel = np.abs(e1[stayed] / e0[stayed] - 1)
+    assert stayed.mean() > 0.99
+    assert rel.max() < 1e-12, rel.max()  # tolerance: 6 rotations x a few ulp
+    q = g.getRand()
+    assert q.min() >= 0.0 and q.max() <= 1.0
+    r = np.sqrt(p[:, 0] ** 2 + p[:, 1] ** 2)
+    inside = (r * nr >= 0) & (r * nr < nr) & (p[:, 2] * nz >= 0) & (p[:, 2] * nz < nz)
+    counts = g.getField("cell_count")
+    assert int(counts.sum()) == int(inside.sum())
+    cells = (r[inside] * nr).astype(np.int64) + nr * (p[inside, 2] * nz).astype(np.int64)
+    assert_same(counts, np.bincount(cells, minlength=nr * nz).astype(np.uint32), "C3 per-cell counts")
+    sums = g.getField("cell_sums")
+    np.testing.assert_allclose(sums[:, 3].sum(), 0.001 * inside.sum(), rtol=1e-12)
