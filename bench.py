@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- particle-pushes/s of the full PIC frame (step() + density()) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c5|c3|c2|c1] [--precision f64|f32]
+
+One "step" = one frame of the reference's loop (fusionsim.js:172-174): simulation.step() (two
+leap-frog half-steps, empic.js:1436-1469) + simulation.density() (empic.js:1471-1495) over the
+whole synthetic plasma; 1 push = one half-step of one particle, so a frame is 2*N pushes
+(SURVEY.md section 8d).  Default workload: BASELINE.json configs[4], the weak-scaling shape the
+metric is quoted on -- 64 Mi particles and an 8192 x 2048 slab of cells per GPU.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the engine's stream)
+with the state resident in HBM; `e2e` is the same metric through the public host API with host
+buffers: set(position, velocity) from pinned host memory, K frames, and a canvas read-back per
+frame, all inside the timed region.  `--impl reference` times the CPU restatement of the
+reference's shader arithmetic (oracle/, OpenMP, all host threads) on a bounded sample -- the
+reference itself is WebGL and cannot run headless.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_pushes_per_s_full_pic_step"
+UNIT = "pushes/s"
+
+WORKLOADS = {
+    # name: (particles per GPU, nr, nz per GPU, description)
+    "c5": (1 << 26, 8192, 2048, "C5 weak scaling: 64Mi particles + 8192x2048-cell slab per GPU"),
+    "c3": (1 << 24, 2048, 2048, "C3: 16Mi particles, 2048x2048 grid"),
+    "c2": (1 << 20, 512, 512, "C2: 1Mi particles, 512x512 grid"),
+    "c1": (160000, 400, 800, "C1: default demo scene, 160000 particles, 400x800 grid"),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag = index, False
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+            }
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: record that, never fail the bench
+            self.reasons.add("nvml_unavailable:" + type(e).__name__)
+
+    def result(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def push_algorithmic_bytes(n, ncell, precision):
+    """bytes one half-step launch must move (per GPU)."""
+    if precision == "f64":
+        return 162.0 * n + 97.0 * ncell + 37.7e6
+    return 82.0 * n + 49.0 * ncell + 18.9e6
+
+
+def build_scene(workload, rank, world, seed=2026):
+    """Synthetic plasma of the named shape; with world > 1 the grid is nz*world rows and this
+    rank owns rows [rank*nz, (rank+1)*nz) with the particles inside them."""
+    from fusion_sim_b200.scenes import (c1_scene, c1_sink_source, plasma_particles, scaled_loops,
+                                        scaled_spec)
+    n, nr, nz_local, _ = WORKLOADS[workload]
+    if workload == "c1":
+        assert world == 1, "C1 is a single-GPU scene"
+        return c1_scene(seed)
+    nz = nz_local * world
+    spec = scaled_spec(nr, nz, n * world)
+    lo = max(0.02, rank / world)
+    hi = min(0.98, (rank + 1) / world)
+    pos, vel = plasma_particles(spec, n, seed + rank, z_lo=lo, z_hi=hi)
+    sink, source = c1_sink_source(nr, nz)
+    return dict(spec=spec, position=pos, velocity=vel, sink_mask=sink, source_pdf=source,
+                loops=scaled_loops(spec), n_local=n, nz_local=nz_local)
+
+
+def pinned_copy(a):
+    import torch
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    out = t.numpy()
+    out[...] = a
+    return out, t
+
+
+def cpu_baseline(workload, precision, steps, target_s=12.0, threads=None):
+    """CPU restatement of the reference's shader arithmetic (oracle/, kind "port"), timed on the
+    host cores on a bounded sample: a 1/32 z-slab of the workload (same cell size, same particles
+    per cell)."""
+    from fusion_sim_b200.scenes import apply_scene, c1_scene, c1_sink_source, plasma_particles, scaled_loops, scaled_spec
+    from oracle.oracle import OraclePusher
+    threads = threads or (os.cpu_count() or 1)
+    n, nr, nz, _ = WORKLOADS[workload]
+    if workload == "c1":
+        sc = c1_scene(2026)
+        sc["spec"]["precision"] = precision
+        sample = "whole C1 scene (160000 particles, 400x800 grid)"
+    else:
+        frac = 32 if n >= (1 << 24) else (4 if n >= (1 << 20) else 1)
+        ns, nzs = n // frac, max(16, nz // frac)
+        spec = scaled_spec(nr, nzs, ns, precision=precision)
+        pos, vel = plasma_particles(spec, ns, 99)
+        sink, source = c1_sink_source(nr, nzs)
+        sc = dict(spec=spec, position=pos, velocity=vel, sink_mask=sink, source_pdf=source, loops=scaled_loops(spec))
+        sample = f"1/{frac} z-slab of the workload: {nr}x{nzs} cells, {ns} particles (same particles per cell)"
+    o = OraclePusher(sc["spec"], nthreads=threads)
+    rng = np.random.Generator(np.random.PCG64(5))
+    sc["rand"] = rng.random((o.n, 4))
+    sc["entropy"] = rng.random((1024 * 1024, 4))
+    apply_scene(o, sc)
+
+    def frame():
+        o.step()
+        o.density(timing_mt=True)
+
+    frame()  # warm-up (page faults, OpenMP pool)
+    t0 = time.perf_counter()
+    frame()
+    t1 = time.perf_counter() - t0
+    k = steps if steps else max(3, min(2000, int(target_s / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        frame()
+    dt = time.perf_counter() - t0
+    return {"value": 2.0 * o.n * k / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": sample + f", {k} frames in {dt:.1f} s",
+            "what": "CPU restatement of the reference's shader arithmetic (C, OpenMP); the reference "
+                    "itself is WebGL and has no CPU path"}, dt / k * 1e3, k
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    cb, ms, k = cpu_baseline(args.workload, args.precision, args.steps if args.steps_given else 0, threads=threads)
+    n, nr, nz, desc = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": k, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": desc, "precision": args.precision, "frame": "step()+density()",
+                   "sample": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local = env_int("LOCAL_RANK", 0)
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene
+
+    sc = build_scene(args.workload, rank, world)
+    spec = dict(sc["spec"])
+    spec.update(precision=args.precision, device=local)
+    n_local = sc.get("n_local", len(sc["position"]))
+    if world > 1:
+        from fusion_sim_b200.dist import SlabPusher
+        sim = SlabPusher(spec, sc, rank, world)
+    else:
+        sim = makeCylindricalParticlePusher(spec)
+        pos_h, _keep1 = pinned_copy(sc["position"])
+        vel_h, _keep2 = pinned_copy(sc["velocity"])
+        sc["position"], sc["velocity"] = pos_h, vel_h
+        apply_scene(sim, sc)
+    nr, nz = int(spec["nr"]), int(spec["nz"])
+    ncell_local = sim.ncell_local
+    canvas, _keep3 = None, None
+    if world == 1:
+        t = torch.empty((nz, nr, 4), dtype=torch.uint8, pin_memory=True)
+        canvas, _keep3 = t.numpy(), t
+
+    def frame():
+        sim.step()
+        sim.density()
+
+    def barrier():
+        sim.sync()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing: W warm-up frames, then exactly K frames ----
+    for _ in range(args.warmup):
+        frame()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = sim.launch_count
+    sim.mark(0)
+    for _ in range(args.steps):
+        frame()
+    sim.mark(1)
+    ms_total = sim.elapsed_ms(0, 1)
+    barrier()
+    sampler.stop_flag = True
+    launches = sim.launch_count - l0
+    ms_total = reduce_max(ms_total)
+    sampler.join(timeout=2)
+    n_total = n_local * world
+    value = 2.0 * n_total * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel device times over K more frames (CUDA events around every launch) ----
+    sim.timing(True)
+    sim.timing_reset()
+    for _ in range(args.steps):
+        frame()
+    kern = {}
+    for nm in ("push", "hist", "scan", "scatter", "cellsum", "cellsum_heavy", "conv"):
+        ms, cnt = sim.timing_get(nm)
+        if cnt:
+            kern[nm] = {"ms_per_launch": ms / cnt, "launches_per_step": cnt / args.steps,
+                        "ms_per_step": ms / args.steps}
+    sim.timing(False)
+    peak, peak_kind = measured_peak()
+    push_ms = kern["push"]["ms_per_launch"]
+    alg = push_algorithmic_bytes(n_local, ncell_local, args.precision)
+    achieved = alg / (push_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "push_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(f"{args.workload}_{args.precision}")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "push_kernel (fused rand + gather/Boris + push/absorb/respawn half-step)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_kind": peak_kind + " HBM copy bandwidth",
+                "algorithmic_bytes_per_launch": alg, "ms_per_launch": push_ms, "traffic": traffic,
+                "frac_of_nominal_8000": achieved / 8000.0, "kernels_ms_per_step": kern}
+
+    # ---- end to end through the public host API with host buffers ----
+    e2e = None
+    if world == 1:
+        h2d = 2 * sc["position"].nbytes
+        d2h = canvas.nbytes
+        sim.sync()
+        t0 = time.perf_counter()
+        sim.mark(2)
+        sim.set({"position": sc["position"], "velocity": sc["velocity"]})
+        for _ in range(args.steps):
+            frame()
+            sim.render(canvas)
+        sim.mark(3)
+        ms_e2e = sim.elapsed_ms(2, 3)
+        sim.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(ms_e2e, wall)
+        e2e = {"value": 2.0 * n_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h,
+               "ms_total": ms_e2e,
+               "what": "set(position,velocity) from pinned host arrays once + per frame step(), density(), "
+                       "canvas read-back to pinned host memory; upload amortised over the K frames"}
+    else:
+        e2e = sim.e2e(args.steps, frame) if hasattr(sim, "e2e") else None
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _, _ = cpu_baseline(args.workload, args.precision, 0)
+
+    if rank == 0:
+        n, nr_, nz_, desc = WORKLOADS[args.workload]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": desc, "particles_total": n_total, "grid": [nr, nz],
+                       "precision": args.precision, "frame": "step()+density() = 2 half-steps + deposit",
+                       "l2": "inputs larger than L2 (particle state %.1f GB per GPU)" % (
+                           n_local * (81 if args.precision == "f64" else 41) / 1e9),
+                       "parallelism": "slab%d" % world},
+            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cb,
+            "push_only_pushes_per_s": n_local * world / (push_ms * 1e-3),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 20
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

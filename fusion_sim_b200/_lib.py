@@ -78,6 +78,8 @@ _SIGS = {
     "fsim_timing_reset": (C.c_int, [_P]),
     "fsim_timing_get": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fsim_launch_count": (C.c_int64, [_P]),
+    "fsim_mark": (C.c_int, [_P, C.c_int]),
+    "fsim_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "fsim_migrate_record_bytes": (C.c_int64, [_P]),
     "fsim_migrate_pack": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "fsim_migrate_unpack": (C.c_int, [_P, _P, C.c_int64]),

@@ -404,6 +404,8 @@ static void free_all(fsim_sim *s)
             cudaEventDestroy(pe.first);
             cudaEventDestroy(pe.second);
         }
+    for (auto &m : s->marks)
+        if (m) cudaEventDestroy(m);
     if (s->stream) cudaStreamDestroy(s->stream);
 }
 
@@ -871,6 +873,26 @@ int fsim_timing_get(fsim_sim *s, const char *name, double *ms, int64_t *launches
     auto it = s->timers.find(name);
     if (ms) *ms = it == s->timers.end() ? 0.0 : it->second.ms;
     if (launches) *launches = it == s->timers.end() ? 0 : it->second.launches;
+    return FSIM_OK;
+}
+
+int fsim_mark(fsim_sim *s, int slot)
+{
+    FSIM_TRY(check(s));
+    if (slot < 0 || slot >= 16) return fail(FSIM_ERR_INVALID, "mark slot out of range");
+    if (!s->marks[slot]) FSIM_CUDA(cudaEventCreate(&s->marks[slot]));
+    FSIM_CUDA(cudaEventRecord(s->marks[slot], s->stream));
+    return FSIM_OK;
+}
+int fsim_elapsed_ms(fsim_sim *s, int a, int b, double *ms)
+{
+    FSIM_TRY(check(s));
+    if (a < 0 || a >= 16 || b < 0 || b >= 16 || !s->marks[a] || !s->marks[b] || !ms)
+        return fail(FSIM_ERR_INVALID, "elapsed: unrecorded mark");
+    FSIM_CUDA(cudaEventSynchronize(s->marks[b]));
+    float f = 0.f;
+    FSIM_CUDA(cudaEventElapsedTime(&f, s->marks[a], s->marks[b]));
+    *ms = f;
     return FSIM_OK;
 }
 

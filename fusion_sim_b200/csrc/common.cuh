@@ -115,6 +115,7 @@ struct fsim_sim {
     bool timing = false;
     std::map<std::string, fsim::KernelTimer> timers;
     int64_t launches = 0;
+    cudaEvent_t marks[16] = {};
 };
 
 namespace fsim {

@@ -217,6 +217,14 @@ class CylindricalParticlePusher:
         check(lib().fsim_timing_get(self._h, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def mark(self, slot: int):
+        check(lib().fsim_mark(self._h, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        check(lib().fsim_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
     @property
     def launch_count(self) -> int:
         return int(lib().fsim_launch_count(self._h))

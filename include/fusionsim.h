@@ -131,6 +131,10 @@ int fsim_timing_enable(fsim_sim *sim, int on);
 int fsim_timing_reset(fsim_sim *sim);
 int fsim_timing_get(fsim_sim *sim, const char *name, double *ms, int64_t *launches);
 int64_t fsim_launch_count(const fsim_sim *sim); /* kernels launched by this handle so far          */
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel above is launched on):
+ * fsim_mark records event `slot` (0..15); fsim_elapsed_ms waits for slot b and returns b - a.  */
+int fsim_mark(fsim_sim *sim, int slot);
+int fsim_elapsed_ms(fsim_sim *sim, int slot_a, int slot_b, double *ms);
 
 /* ---- multi-GPU slab exchange (extension) -------------------------------- */
 /* Particles leaving the slab are packed into a device buffer grouped by destination rank;
