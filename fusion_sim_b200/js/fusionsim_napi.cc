@@ -1,0 +1,127 @@
+// fusionsim_napi.cc -- thin N-API addon over include/fusionsim.h (SOURCE ONLY: this image has no
+// Node.js and no node_api.h, so it is not compiled or tested here).
+//
+// Build where Node exists:
+//   g++ -std=c++17 -shared -fPIC -I$(node -p "require('node-addon-api').include_dir") \
+//       -I../../include fusionsim_napi.cc -L../csrc -lfusionsim -Wl,-rpath,'$ORIGIN/../csrc' \
+//       -o fusionsim.node
+// It owns nothing but the fsim_sim handle; typed arrays are passed straight through as host
+// pointers (the library copies during the call, as gl.texImage2D does: utilities.js:585-594).
+#include <napi.h>
+
+#include "fusionsim.h"
+
+namespace {
+
+void check(Napi::Env env, int rc)
+{
+    if (rc != FSIM_OK) throw Napi::Error::New(env, fsim_last_error());  // reference: throw new Error(...)
+}
+
+class Sim : public Napi::ObjectWrap<Sim> {
+  public:
+    static Napi::Function Init(Napi::Env env)
+    {
+        return DefineClass(env, "Sim", {
+            InstanceMethod("setArray", &Sim::SetArray),
+            InstanceMethod("setSourcePdf", &Sim::SetSourcePdf),
+            InstanceMethod("addCurrentLoop", &Sim::AddCurrentLoop),
+            InstanceMethod("addCurrentZ", &Sim::AddCurrentZ),
+            InstanceMethod("addBZ", &Sim::AddBZ),
+            InstanceMethod("addBTheta", &Sim::AddBTheta),
+            InstanceMethod("addSpindleCuspPlasmaField", &Sim::AddSpindle),
+            InstanceMethod("precalc", &Sim::Precalc),
+            InstanceMethod("step", &Sim::Step),
+            InstanceMethod("density", &Sim::Density),
+            InstanceMethod("render", &Sim::Render),
+            InstanceMethod("getArray", &Sim::GetArray),
+            InstanceMethod("destroy", &Sim::Destroy),
+        });
+    }
+
+    explicit Sim(const Napi::CallbackInfo &info) : Napi::ObjectWrap<Sim>(info)
+    {
+        Napi::Object o = info[0].As<Napi::Object>();
+        fsim_spec s{};
+        auto num = [&](const char *k) { return o.Get(k).As<Napi::Number>().DoubleValue(); };
+        s.radius = num("radius"); s.height = num("height");
+        s.nr = (int64_t)num("nr"); s.nz = (int64_t)num("nz");
+        s.dt = num("dt"); s.nparticles = (int64_t)num("nparticles");
+        s.particle_mass = num("particle_mass"); s.particle_charge = num("particle_charge");
+        if (o.Has("precision")) s.precision = o.Get("precision").As<Napi::Number>().Int32Value();
+        if (o.Has("device")) s.device = o.Get("device").As<Napi::Number>().Int32Value();
+        if (o.Has("flags")) s.flags = o.Get("flags").As<Napi::Number>().Uint32Value();
+        check(info.Env(), fsim_create(&s, &sim_));
+    }
+    ~Sim() { fsim_destroy(sim_); }
+
+  private:
+    fsim_sim *sim_ = nullptr;
+
+    // setArray(name, Float64Array): E, B, position, velocity, sink_mask, rand, entropy, inv_cdf
+    Napi::Value SetArray(const Napi::CallbackInfo &info)
+    {
+        std::string name = info[0].As<Napi::String>();
+        const double *p = info[1].As<Napi::Float64Array>().Data();
+        int rc = FSIM_ERR_INVALID;
+        if (name == "E") rc = fsim_set_E(sim_, p);
+        else if (name == "B") rc = fsim_set_B(sim_, p);
+        else if (name == "position") rc = fsim_set_position(sim_, p);
+        else if (name == "velocity") rc = fsim_set_velocity(sim_, p);
+        else if (name == "sink_mask") rc = fsim_set_sink_mask(sim_, p);
+        else if (name == "rand") rc = fsim_set_rand(sim_, p);
+        else if (name == "entropy") rc = fsim_set_entropy(sim_, p);
+        else if (name == "inv_cdf") rc = fsim_set_inv_cdf(sim_, p);
+        check(info.Env(), rc);
+        return info.Env().Undefined();
+    }
+    Napi::Value SetSourcePdf(const Napi::CallbackInfo &info)
+    {
+        check(info.Env(), fsim_set_source_pdf(sim_, info[0].As<Napi::Float64Array>().Data(),
+                                              info[1].As<Napi::Number>().Int64Value(),
+                                              info[2].As<Napi::Number>().Int64Value()));
+        return info.Env().Undefined();
+    }
+    Napi::Value AddCurrentLoop(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_add_current_loop(sim_, i[0].As<Napi::Number>(), i[1].As<Napi::Number>(),
+                                             i[2].As<Napi::Number>()));
+        return i.Env().Undefined();
+    }
+    Napi::Value AddCurrentZ(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_current_z(sim_, i[0].As<Napi::Number>())); return i.Env().Undefined(); }
+    Napi::Value AddBZ(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_bz(sim_, i[0].As<Napi::Number>())); return i.Env().Undefined(); }
+    Napi::Value AddBTheta(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_btheta(sim_, i[0].As<Napi::Number>())); return i.Env().Undefined(); }
+    Napi::Value AddSpindle(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_spindle_cusp_plasma_field(sim_, 0, 0, 0)); return i.Env().Undefined(); }
+    Napi::Value Precalc(const Napi::CallbackInfo &i) { check(i.Env(), fsim_precalc(sim_)); return i.Env().Undefined(); }
+    Napi::Value Step(const Napi::CallbackInfo &i) { check(i.Env(), fsim_step(sim_)); return i.Env().Undefined(); }
+    Napi::Value Density(const Napi::CallbackInfo &i) { check(i.Env(), fsim_density(sim_)); return i.Env().Undefined(); }
+    Napi::Value Render(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_render_rgba8(sim_, i[0].As<Napi::Uint8Array>().Data()));
+        return i.Env().Undefined();
+    }
+    // getArray(name, Float64Array out): position, velocity, rand, or a field name
+    Napi::Value GetArray(const Napi::CallbackInfo &info)
+    {
+        std::string name = info[0].As<Napi::String>();
+        double *p = info[1].As<Napi::Float64Array>().Data();
+        int rc;
+        if (name == "position") rc = fsim_get_position(sim_, p);
+        else if (name == "velocity") rc = fsim_get_velocity(sim_, p);
+        else if (name == "rand") rc = fsim_get_rand(sim_, p);
+        else rc = fsim_get_field(sim_, name.c_str(), p);
+        check(info.Env(), rc);
+        return info.Env().Undefined();
+    }
+    Napi::Value Destroy(const Napi::CallbackInfo &i) { fsim_destroy(sim_); sim_ = nullptr; return i.Env().Undefined(); }
+};
+
+Napi::Object InitAll(Napi::Env env, Napi::Object exports)
+{
+    exports.Set("Sim", Sim::Init(env));
+    return exports;
+}
+
+}  // namespace
+
+NODE_API_MODULE(fusionsim, InitAll)
