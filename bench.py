@@ -275,7 +275,7 @@ def run_ours(args):
     for _ in range(args.steps):
         frame()
     kern = {}
-    for nm in ("push", "hist", "scan", "scatter", "cellsum", "cellsum_heavy", "conv"):
+    for nm in ("push", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_heavy", "conv"):
         ms, cnt = sim.timing_get(nm)
         if cnt:
             kern[nm] = {"ms_per_launch": ms / cnt, "launches_per_step": cnt / args.steps,

@@ -336,6 +336,8 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
         FSIM_TRY(dalloc(&s->pid[b], s->cap));
     }
     FSIM_TRY(dalloc(&s->key, s->cap));
+    FSIM_TRY(dalloc(&s->perm, s->cap));
+    for (int q = 0; q < 3; ++q) FSIM_TRY(dalloc_bytes(&s->dcol[q], s->rs * s->cap));
     FSIM_TRY(dalloc(&s->counts, s->ncell_local + 1));
     FSIM_TRY(dalloc(&s->starts, s->ncell_local + 2));
     FSIM_TRY(dalloc(&s->cursor, s->ncell_local + 1));
@@ -394,7 +396,7 @@ static void free_all(fsim_sim *s)
         cudaFree(s->alive[b]);
         cudaFree(s->pid[b]);
     }
-    void *ptrs[] = {s->key, s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
+    void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->dcol[2], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
                     s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr};
     for (void *p : ptrs) cudaFree(p);
@@ -554,7 +556,8 @@ int fsim_set_B(fsim_sim *s, const double *B)
 int fsim_set_position(fsim_sim *s, const double *pos)
 {
     FSIM_TRY(check(s));
-    s->sorted = false;
+    s->binned = false;
+    s->keys_valid = false;
     return finish(s, particles_in3(s, pos, AX, s->factor_r, s->factor_r, s->factor_z, true));
 }
 int fsim_set_velocity(fsim_sim *s, const double *vel)
@@ -614,7 +617,8 @@ int fsim_set_particle_count(fsim_sim *s, int64_t n)
     FSIM_TRY(check(s));
     if (n < 0 || n > s->cap - 1024) return fail(FSIM_ERR_RANGE, "particle count exceeds capacity");
     s->n = n;
-    s->sorted = false;
+    s->binned = false;
+    s->keys_valid = false;
     return FSIM_OK;
 }
 int fsim_set_ids(fsim_sim *s, const uint64_t *ids)
@@ -665,38 +669,60 @@ int fsim_precalc(fsim_sim *s)
     return FSIM_OK;
 }
 
+// Physical re-sort of the particle storage every `sort_interval` frames (default 8): between
+// re-sorts density() bins through a 4-byte index list and the push tolerates the slowly decaying
+// order (particles move a fraction of a cell per half-step).
+static int sort_interval(const fsim_sim *s) { return s->spec.sort_interval > 0 ? s->spec.sort_interval : 8; }
+
+// keys/colours (prepass) if the push did not emit them, then scan + index scatter
+static int bin_particles(fsim_sim *s)
+{
+    if (s->binned) return FSIM_OK;
+    if (!s->keys_valid) FSIM_TRY(launch_keys(s));
+    return launch_bin(s);
+}
+
+static int physical_sort(fsim_sim *s)
+{
+    FSIM_TRY(bin_particles(s));
+    return launch_apply_perm(s);
+}
+
 int fsim_half_step(fsim_sim *s)
 {
     FSIM_TRY(check(s));
-    FSIM_TRY(finish(s, launch_push(s)));
-    s->sorted = false;
-    return FSIM_OK;
+    return finish(s, launch_push(s, false));
 }
 
 int fsim_step(fsim_sim *s)
 {
     FSIM_TRY(check(s));
-    // out.step, empic.js:1436-1469: B-buffers then A-buffers = two half-steps
-    FSIM_TRY(finish(s, launch_push(s)));
-    FSIM_TRY(finish(s, launch_push(s)));
-    s->sorted = false;
+    // out.step, empic.js:1436-1469: B-buffers then A-buffers = two half-steps.  The second one also
+    // emits the deposit prepass (sort key, sprite colour, histogram) of the new state for the
+    // density() that follows.
+    FSIM_TRY(finish(s, launch_push(s, false)));
+    FSIM_TRY(finish(s, launch_push(s, !s->slab)));
     s->steps_since_sort++;
-    if (s->spec.sort_interval > 0 && s->steps_since_sort >= s->spec.sort_interval)
-        FSIM_TRY(finish(s, launch_sort(s)));
+    if (s->steps_since_sort >= 4 * sort_interval(s))  // push-only loops: keep the gather coherent
+        FSIM_TRY(finish(s, physical_sort(s)));
     return FSIM_OK;
 }
 
 int fsim_sort(fsim_sim *s)
 {
     FSIM_TRY(check(s));
-    return finish(s, launch_sort(s));
+    return finish(s, physical_sort(s));
 }
 
 int fsim_density_begin(fsim_sim *s)
 {
     FSIM_TRY(check(s));
-    if (!s->sorted) FSIM_TRY(finish(s, launch_sort(s)));
-    return finish(s, launch_cellsum(s));
+    FSIM_TRY(finish(s, bin_particles(s)));
+    FSIM_TRY(finish(s, launch_cellsum(s)));
+    // the deposit is done with the index list; now, every sort_interval frames, put the storage
+    // itself into cell order for the pushes that follow
+    if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) FSIM_TRY(finish(s, launch_apply_perm(s)));
+    return FSIM_OK;
 }
 int fsim_density_end(fsim_sim *s)
 {

@@ -81,8 +81,14 @@ struct fsim_sim {
     uint32_t *starts = nullptr;   // [ncell_local + 2]
     uint32_t *cursor = nullptr;   // [ncell_local + 1]
     uint32_t *blocksums = nullptr;
-    bool sorted = false;          // particle storage is sorted by cell and starts[] is valid
-    int steps_since_sort = 0;
+    uint32_t *perm = nullptr;     // [cap] particle slots ordered by cell (index sort)
+    void *dcol[3] = {};           // [cap] sprite colour 0.001*(v_r, v_a, v_z) of each slot (deposit prepass)
+    bool keys_valid = false;      // key[] and the histogram in counts[] match the current positions
+    bool counts_dirty = false;    // counts[] holds a histogram that no scan has consumed yet
+    bool binned = false;          // starts[] (+ perm[] unless perm_identity) match the current positions
+    bool perm_identity = false;   // storage itself is sorted by cell: segment j is slot j
+    bool ever_sorted = false;
+    int steps_since_sort = 0;     // step() calls since the last physical sort
 
     // tables
     void *cellrec = nullptr;   // [ncell_local][12]
@@ -173,11 +179,44 @@ __device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double ffloor(double x) { return floor(x); }
 __device__ __forceinline__ float ffloor(float x) { return floorf(x); }
 
+// bit 31 of a sort key: the particle's sprite is clipped (not deposited)
+constexpr uint32_t KEY_CLIPPED = 0x80000000u;
+constexpr uint32_t KEY_MASK = 0x7fffffffu;
+
+// Vertex shader of programMoments01 (empic.js:994-1006) for a particle at (x,y,z) with velocity v:
+// colour 0.001*(v_r, v_a, v_z) (the alpha channel is the constant 0.001*1.0) and the sort key =
+// gather cell (clamped like the texture fetch), with KEY_CLIPPED when the sprite centre lies
+// outside the target (GLES2 point clipping), is NaN, or is not in a locally held row.
+// `r` = sqrt(x*x + y*y) is passed in because the push kernel already has it.
+template <typename Real>
+__device__ __forceinline__ uint32_t sprite_key_colour(Real x, Real y, Real z, Real r, Real vx, Real vy,
+                                                      Real vz, int nr, int nz, int row0, int rows,
+                                                      Real &c0, Real &c1, Real &c2)
+{
+    const Real dx = x / r, dy = y / r;
+    const Real vr = vx * dx + vy * dy;
+    const Real va = vy * dx - vx * dy;
+    c0 = (Real)FSIM_DEPOSIT_WEIGHT * vr;
+    c1 = (Real)FSIM_DEPOSIT_WEIGHT * va;
+    c2 = (Real)FSIM_DEPOSIT_WEIGHT * vz;
+    const int gj = tex_idx(z, nz);
+    int cj = gj - row0;
+    const bool local = cj >= 0 && cj < rows;
+    cj = cj < 0 ? 0 : (cj >= rows ? rows - 1 : cj);
+    uint32_t key = (uint32_t)tex_idx(r, nr) + (uint32_t)cj * (uint32_t)nr;
+    const Real xw = r * (Real)nr, yw = z * (Real)nz;
+    const bool inside = (xw >= (Real)0) && (xw < (Real)nr) && (yw >= (Real)0) && (yw < (Real)nz);
+    if (!inside || !local) key |= KEY_CLIPPED;
+    return key;
+}
+
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // kernels / host stages implemented in the other translation units
-int launch_push(fsim_sim *s);
-int launch_sort(fsim_sim *s);
+int launch_push(fsim_sim *s, bool with_hist);
+int launch_keys(fsim_sim *s);      // deposit prepass from the stored state: key, colour, histogram
+int launch_bin(fsim_sim *s);       // scan + index scatter -> starts[], perm[]
+int launch_apply_perm(fsim_sim *s);  // physical re-sort: storage <- storage[perm]
 int launch_cellsum(fsim_sim *s);
 int launch_conv(fsim_sim *s);
 int launch_precalc(fsim_sim *s);

@@ -19,30 +19,12 @@ namespace fsim {
 
 constexpr int THREAD_CELL_MAX = 64;  // larger cells go to the block-per-cell path
 
-// vertex shader of programMoments01, empic.js:994-1006.  Returns false when the sprite is
-// clipped (centre outside the target, or NaN) or does not belong to local cell `c`.
-template <typename Real>
-__device__ __forceinline__ bool sprite_colour(Real x, Real y, Real z, Real vx, Real vy, Real vz,
-                                              int nr, int nz, int row0, uint32_t c, Real (&col)[4])
-{
-    const Real r = fsqrt(x * x + y * y);
-    const Real dx = x / r, dy = y / r;
-    const Real vr = vx * dx + vy * dy;
-    const Real va = vy * dx - vx * dy;
-    col[0] = (Real)FSIM_DEPOSIT_WEIGHT * vr;
-    col[1] = (Real)FSIM_DEPOSIT_WEIGHT * va;
-    col[2] = (Real)FSIM_DEPOSIT_WEIGHT * vz;
-    col[3] = (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
-    const Real xw = r * (Real)nr, yw = z * (Real)nz;
-    if (!(xw >= (Real)0) || !(xw < (Real)nr)) return false;
-    if (!(yw >= (Real)0) || !(yw < (Real)nz)) return false;
-    return (uint32_t)((int)xw + ((int)yw - row0) * nr) == c;
-}
-
 template <typename Real>
 struct CellSumArgs {
-    const Real *x, *y, *z, *vx, *vy, *vz;
+    const Real *dcol[3];   // sprite colour of each slot (deposit prepass)
+    const uint32_t *key;   // KEY_CLIPPED marks sprites that are not deposited
     const uint32_t *id;
+    const uint32_t *perm;  // particle slots in cell order
     const uint32_t *starts;
     Real *S;          // [ncell][4]
     uint32_t *count;  // [ncell]
@@ -50,44 +32,105 @@ struct CellSumArgs {
     int64_t ncell;
     int nr, nz, row0;
     // scratch of the block-per-cell path (the idle half of the particle double buffer)
-    Real *scol[4];
     uint32_t *sid, *sidx;
 };
+
+// Register path for a cell with k <= KR particles: (id, slot) pairs are loaded once, ordered by id
+// with a compile-time bitonic network (padding = 0xffffffff sorts last), then the colours are
+// added in that order.  All loads of a wave are independent, so they overlap.
+template <typename Real, int KR>
+__device__ __forceinline__ void cell_small(const CellSumArgs<Real> &a, uint32_t s, uint32_t k, Real (&acc)[4],
+                                           uint32_t &cnt)
+{
+    uint32_t pp[KR], ii[KR];
+#pragma unroll
+    for (int j = 0; j < KR; ++j) pp[j] = (uint32_t)j < k ? a.perm[s + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < KR; ++j) ii[j] = (uint32_t)j < k ? a.id[pp[j]] : 0xffffffffu;
+#pragma unroll
+    for (int kk = 2; kk <= KR; kk <<= 1) {
+#pragma unroll
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+#pragma unroll
+            for (int i = 0; i < KR; ++i) {
+                const int l = i ^ jj;
+                if (l > i) {
+                    const bool up = (i & kk) == 0;
+                    const bool sw = up ? (ii[i] > ii[l]) : (ii[i] < ii[l]);
+                    const uint32_t ti = sw ? ii[l] : ii[i], tl = sw ? ii[i] : ii[l];
+                    const uint32_t qi = sw ? pp[l] : pp[i], ql = sw ? pp[i] : pp[l];
+                    ii[i] = ti; ii[l] = tl; pp[i] = qi; pp[l] = ql;
+                }
+            }
+        }
+    }
+    uint32_t kf[KR];
+    Real c0[KR], c1[KR], c2[KR];
+#pragma unroll
+    for (int j = 0; j < KR; ++j) {
+        const bool on = (uint32_t)j < k;
+        kf[j] = on ? a.key[pp[j]] : KEY_CLIPPED;
+        c0[j] = on ? a.dcol[0][pp[j]] : (Real)0;
+        c1[j] = on ? a.dcol[1][pp[j]] : (Real)0;
+        c2[j] = on ? a.dcol[2][pp[j]] : (Real)0;
+    }
+#pragma unroll
+    for (int j = 0; j < KR; ++j) {
+        if (!(kf[j] & KEY_CLIPPED)) {
+            acc[0] += c0[j]; acc[1] += c1[j]; acc[2] += c2[j];
+            acc[3] += (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
+            cnt++;
+        }
+    }
+}
 
 template <typename Real>
 __global__ void __launch_bounds__(128) cellsum_kernel(const CellSumArgs<Real> a)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.ncell) return;
-    const uint32_t s = a.starts[c], e = a.starts[c + 1];
-    const uint32_t k = e - s;
+    const bool live = c < a.ncell;
+    uint32_t s = 0, k = 0;
+    if (live) {
+        s = a.starts[c];
+        k = a.starts[c + 1] - s;
+    }
     Real acc[4] = {(Real)0, (Real)0, (Real)0, (Real)0};
     uint32_t cnt = 0;
-    if (k > THREAD_CELL_MAX) {
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);  // warp-uniform choice of the path
+    if (kmax <= 4) {
+        cell_small<Real, 4>(a, s, k, acc, cnt);
+    } else if (kmax <= 8) {
+        cell_small<Real, 8>(a, s, k, acc, cnt);
+    } else if (k <= 16) {
+        cell_small<Real, 16>(a, s, k, acc, cnt);
+    } else if (k > THREAD_CELL_MAX) {
         a.heavy_list[atomicAdd(a.heavy_n, 1u)] = (uint32_t)c;
         return;
-    }
-    unsigned long long done = 0ull;
-    for (uint32_t t = 0; t < k; ++t) {
-        // selection: the not-yet-used particle of this cell with the smallest id
-        // (ids are unique and < 0xffffffff)
-        uint32_t best = 0xffffffffu, bj = 0;
-        for (uint32_t j = 0; j < k; ++j) {
-            const uint32_t v = a.id[s + j];
-            if (!((done >> j) & 1ull) && v < best) {
-                best = v;
-                bj = j;
+    } else {
+        unsigned long long done = 0ull;
+        for (uint32_t t = 0; t < k; ++t) {
+            // selection: the not-yet-used particle of this cell with the smallest id
+            // (ids are unique and < 0xffffffff)
+            uint32_t best = 0xffffffffu, bj = 0;
+            size_t p = 0;
+            for (uint32_t j = 0; j < k; ++j) {
+                const size_t pj = a.perm[s + j];
+                const uint32_t v = a.id[pj];
+                if (!((done >> j) & 1ull) && v < best) {
+                    best = v;
+                    bj = j;
+                    p = pj;
+                }
+            }
+            done |= 1ull << bj;
+            if (!(a.key[p] & KEY_CLIPPED)) {
+                acc[0] += a.dcol[0][p]; acc[1] += a.dcol[1][p]; acc[2] += a.dcol[2][p];
+                acc[3] += (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
+                cnt++;
             }
         }
-        done |= 1ull << bj;
-        const size_t p = (size_t)s + bj;
-        Real col[4];
-        if (sprite_colour<Real>(a.x[p], a.y[p], a.z[p], a.vx[p], a.vy[p], a.vz[p], a.nr, a.nz, a.row0,
-                                (uint32_t)c, col)) {
-            acc[0] += col[0]; acc[1] += col[1]; acc[2] += col[2]; acc[3] += col[3];
-            cnt++;
-        }
     }
+    if (!live) return;
     Real *o = a.S + 4 * (size_t)c;
     o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
     a.count[c] = cnt;
@@ -105,13 +148,9 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
     const uint32_t k = e - s;
     uint32_t *sid = a.sid + s, *sidx = a.sidx + s;
     for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
-        const size_t p = (size_t)s + j;
-        Real col[4];
-        const bool ok = sprite_colour<Real>(a.x[p], a.y[p], a.z[p], a.vx[p], a.vy[p], a.vz[p], a.nr,
-                                            a.nz, a.row0, c, col);
-        a.scol[0][p] = col[0]; a.scol[1][p] = col[1]; a.scol[2][p] = col[2]; a.scol[3][p] = col[3];
+        const size_t p = a.perm[(size_t)s + j];
         sid[j] = a.id[p];
-        sidx[j] = j | (ok ? 0u : 0x80000000u);
+        sidx[j] = j | (a.key[p] & KEY_CLIPPED);
     }
     __syncthreads();
     uint32_t np2 = 1;
@@ -136,10 +175,10 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
         uint32_t cnt = 0;
         for (uint32_t t = 0; t < k; ++t) {
             const uint32_t j = sidx[t];
-            if (j & 0x80000000u) continue;
-            const size_t p = (size_t)s + j;
-            acc[0] += a.scol[0][p]; acc[1] += a.scol[1][p];
-            acc[2] += a.scol[2][p]; acc[3] += a.scol[3][p];
+            if (j & KEY_CLIPPED) continue;
+            const size_t p = a.perm[(size_t)s + j];
+            acc[0] += a.dcol[0][p]; acc[1] += a.dcol[1][p]; acc[2] += a.dcol[2][p];
+            acc[3] += (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
             cnt++;
         }
         Real *o = a.S + 4 * (size_t)c;
@@ -156,17 +195,16 @@ int launch_cellsum(fsim_sim *s)
         using Real = decltype(tag);
         const int cur = s->cur, alt = s->cur ^ 1;
         CellSumArgs<Real> a;
-        a.x = (const Real *)s->part[cur][AX]; a.y = (const Real *)s->part[cur][AY];
-        a.z = (const Real *)s->part[cur][AZ]; a.vx = (const Real *)s->part[cur][AVX];
-        a.vy = (const Real *)s->part[cur][AVY]; a.vz = (const Real *)s->part[cur][AVZ];
+        for (int q = 0; q < 3; ++q) a.dcol[q] = (const Real *)s->dcol[q];
+        a.key = s->key;
         a.id = s->pid[cur];
+        a.perm = s->perm;
         a.starts = s->starts;
         a.S = (Real *)s->cellsum;
         a.count = s->cellcount;
         a.heavy_list = s->heavy_list; a.heavy_n = s->heavy_n;
         a.ncell = s->ncell_local;
         a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0;
-        for (int k = 0; k < 4; ++k) a.scol[k] = (Real *)s->part[alt][k];
         a.sid = (uint32_t *)s->part[alt][4];
         a.sidx = (uint32_t *)s->part[alt][5];
         FSIM_CUDA(cudaMemsetAsync(s->heavy_n, 0, sizeof(uint32_t), s->stream));
@@ -185,15 +223,32 @@ int launch_cellsum(fsim_sim *s)
 }
 
 // ---- 11x11 stencil + normalise + running average -------------------------------------------
+// Tile: CT_I x CT_J output cells per block, one warp per output row.  The per-cell sums of the tile
+// and its 5-cell halo are staged in shared memory, one PLANE per channel (planes are padded so
+// that the 32 lanes of a warp -- 8 strips x 4 channels -- hit distinct banks).  A thread owns ONE
+// channel of a strip of 4 neighbouring cells: per stencil row it loads a 14-value window once and
+// slides it over the 4 outputs, so shared-memory traffic is ~1/2 of the thread-per-cell form and
+// the kernel is bound by the fp64 pipe (81 multiply + 81 add per cell and channel; the 40 taps
+// that are exactly zero are removed at compile time).  Cells outside the grid read as zero, which
+// adds exact zeros: identical to skipping them.
 constexpr int CT_I = 32, CT_J = 16;             // output tile
 constexpr int CH = FSIM_SHAPE_MID;              // halo = 5
 constexpr int CS_I = CT_I + 2 * CH, CS_J = CT_J + 2 * CH;
+constexpr int CPLANE = ((CS_I * CS_J + 30) / 32) * 32 + 1;  // == 1 (mod 32): conflict-free planes
+constexpr int CSTRIP = 4;
+constexpr int CWIN = CSTRIP + 2 * CH;           // 14
 
 __constant__ double c_shape_f64[FSIM_NSHAPE * FSIM_NSHAPE];
 __constant__ float c_shape_f32[FSIM_NSHAPE * FSIM_NSHAPE];
 template <typename Real> __device__ __forceinline__ Real shape_w(int k);
 template <> __device__ __forceinline__ double shape_w<double>(int k) { return c_shape_f64[k]; }
 template <> __device__ __forceinline__ float shape_w<float>(int k) { return c_shape_f32[k]; }
+
+// taps of the footprint that are not identically zero: cos^2(pi d / 10) with d <= 5 (empic.js:959)
+__host__ __device__ constexpr bool tap_nonzero(int ti, int tj)
+{
+    return (ti - CH) * (ti - CH) + (tj - CH) * (tj - CH) <= CH * CH;
+}
 
 template <typename Real>
 struct ConvArgs {
@@ -204,13 +259,13 @@ struct ConvArgs {
 };
 
 template <typename Real>
-__global__ void __launch_bounds__(CT_I * 8) conv_kernel(const ConvArgs<Real> a)
+__global__ void __launch_bounds__(CT_J * 32) conv_kernel(const ConvArgs<Real> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Real *sm = reinterpret_cast<Real *>(smem_raw);  // [CS_J][CS_I][4]
+    Real *sm = reinterpret_cast<Real *>(smem_raw);  // [4][CPLANE] with plane = [CS_J][CS_I]
     const int i0 = blockIdx.x * CT_I, jb = a.j0 + blockIdx.y * CT_J;
-    const int tid = threadIdx.y * CT_I + threadIdx.x;
-    for (int t = tid; t < CS_I * CS_J; t += CT_I * 8) {
+    const int tid = threadIdx.x;
+    for (int t = tid; t < CS_I * CS_J; t += CT_J * 32) {
         const int li = t % CS_I, lj = t / CS_I;
         const int gi = i0 + li - CH, gj = jb + lj - CH;
         Real v0 = (Real)0, v1 = (Real)0, v2 = (Real)0, v3 = (Real)0;
@@ -218,51 +273,47 @@ __global__ void __launch_bounds__(CT_I * 8) conv_kernel(const ConvArgs<Real> a)
             const Real *p = a.S + 4 * ((size_t)gi + (size_t)gj * a.nr);
             v0 = p[0]; v1 = p[1]; v2 = p[2]; v3 = p[3];
         }
-        Real *q = sm + 4 * t;
-        q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3;
+        sm[t] = v0; sm[CPLANE + t] = v1; sm[2 * CPLANE + t] = v2; sm[3 * CPLANE + t] = v3;
     }
     __syncthreads();
-    // validity of a source (it must exist in the GLOBAL grid rows held locally)
+
+    const int lane = tid & 31, lj = tid >> 5;   // warp = output row
+    const int c = lane & 3, strip = lane >> 2;  // channel, strip of 4 cells
+    const Real *plane = sm + c * CPLANE;
+    Real acc[CSTRIP];
 #pragma unroll
-    for (int rep = 0; rep < CT_J / 8; ++rep) {
-        const int lj = threadIdx.y + rep * 8, li = threadIdx.x;
-        const int gi = i0 + li, gj = jb + lj;
+    for (int o = 0; o < CSTRIP; ++o) acc[o] = (Real)0;
+#pragma unroll
+    for (int tj = 0; tj < FSIM_NSHAPE; ++tj) {
+        const Real *row = plane + (lj + 2 * CH - tj) * CS_I + strip * CSTRIP;
+        Real w[CWIN];
+#pragma unroll
+        for (int k = 0; k < CWIN; ++k) w[k] = row[k];
+#pragma unroll
+        for (int o = 0; o < CSTRIP; ++o) {
+#pragma unroll
+            for (int ti = 0; ti < FSIM_NSHAPE; ++ti)
+                if (tap_nonzero(ti, tj)) acc[o] = acc[o] + w[o + 2 * CH - ti] * shape_w<Real>(ti + FSIM_NSHAPE * tj);
+        }
+    }
+
+    const int gj = jb + lj;
+    const Real ratio = (Real)FSIM_EMA_RATIO;
+#pragma unroll
+    for (int o = 0; o < CSTRIP; ++o) {
+        const int gi = i0 + strip * CSTRIP + o;
+        const Real alpha = __shfl_sync(0xffffffffu, acc[o], lane | 3);  // channel 3 of the same cell
         if (gi >= a.nr || gj >= a.j1) continue;
-        Real acc0 = (Real)0, acc1 = (Real)0, acc2 = (Real)0, acc3 = (Real)0;
-        for (int tj = 0; tj < FSIM_NSHAPE; ++tj) {
-            const int sj = gj - tj + CH;  // source row (local)
-            if (sj < 0 || sj >= a.rows) continue;
-            const Real *row = sm + 4 * ((lj + 2 * CH - tj) * CS_I);
-            for (int ti = 0; ti < FSIM_NSHAPE; ++ti) {
-                const Real w = shape_w<Real>(ti + FSIM_NSHAPE * tj);
-                const int si = gi - ti + CH;
-                if (w == (Real)0 || si < 0 || si >= a.nr) continue;
-                const Real *q = row + 4 * (li + 2 * CH - ti);
-                acc0 = acc0 + q[0] * w; acc1 = acc1 + q[1] * w;
-                acc2 = acc2 + q[2] * w; acc3 = acc3 + q[3] * w;
-            }
-        }
-        const size_t c = (size_t)gi + (size_t)gj * a.nr;
-        if (a.mom) {
-            Real *m = a.mom + 4 * c;
-            m[0] = acc0; m[1] = acc1; m[2] = acc2; m[3] = acc3;
-        }
+        const size_t cell = (size_t)gi + (size_t)gj * a.nr;
+        if (a.mom) a.mom[4 * cell + c] = acc[o];
         // programNormalizeMoments01, empic.js:1055-1056
         const Real u = ((Real)gi + (Real)0.5) / (Real)a.nr;
-        Real M[4];
-        if (acc3 > (Real)0) {
-            M[0] = acc0 / acc3; M[1] = acc1 / acc3; M[2] = acc2 / acc3; M[3] = acc3;
-        } else {
-            M[0] = M[1] = M[2] = M[3] = (Real)0;
-        }
-        const Real ratio = (Real)FSIM_EMA_RATIO;
-        Real *av = a.avg + 4 * c;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const Real v = (Real)FSIM_NORM_SCALE * M[q] * (Real)FSIM_NORM_HALF / u;
-            if (a.norm) a.norm[4 * c + q] = v;
-            av[q] = ratio * v + ((Real)1.0 - ratio) * av[q];  // avg_frag, empic.js:277
-        }
+        Real M = (Real)0;
+        if (alpha > (Real)0) M = (c == 3) ? alpha : acc[o] / alpha;
+        const Real v = (Real)FSIM_NORM_SCALE * M * (Real)FSIM_NORM_HALF / u;
+        if (a.norm) a.norm[4 * cell + c] = v;
+        Real *av = a.avg + 4 * cell + c;
+        *av = ratio * v + ((Real)1.0 - ratio) * (*av);  // avg_frag, empic.js:277
     }
 }
 
@@ -285,9 +336,9 @@ int launch_conv(fsim_sim *s)
         a.mom = (Real *)s->mom; a.norm = (Real *)s->norm; a.avg = (Real *)s->avg;
         a.nr = s->nr; a.rows = s->rows;
         a.j0 = s->own0 - s->row0; a.j1 = a.j0 + s->own_rows;
-        dim3 block(CT_I, 8);
+        dim3 block(CT_J * 32);
         dim3 grid((s->nr + CT_I - 1) / CT_I, (s->own_rows + CT_J - 1) / CT_J);
-        const size_t smem = sizeof(Real) * 4 * CS_I * CS_J;
+        const size_t smem = sizeof(Real) * 4 * CPLANE;
         Bracket b(s, "conv");
         conv_kernel<Real><<<grid, block, smem, s->stream>>>(a);
         FSIM_CUDA(cudaGetLastError());

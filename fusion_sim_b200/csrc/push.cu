@@ -12,6 +12,8 @@
 // stores (ld.global.cs / st.global.cs keep the 126 MB L2 for the entropy and cell tables);
 // tables come through the read-only path.  Arithmetic is IEEE, left to right as the GLSL is
 // written, compiled with -fmad=false so it rounds exactly like the CPU oracle.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fsim {
@@ -24,7 +26,8 @@ struct PushArgs {
     const Real *__restrict__ cellrec;
     const uint8_t *__restrict__ sink;
     const Real *__restrict__ invcdf;
-    uint32_t *key;      // optional: gather cell of the NEW position (+ histogram)
+    uint32_t *key;      // optional deposit prepass: sort key, sprite colour, histogram
+    Real *dcol[3];
     uint32_t *counts;
     uint32_t *oob;
     int64_t n;
@@ -37,6 +40,7 @@ template <> struct Vec<double, 2> { using T = double2; };
 template <> struct Vec<float, 4> { using T = float4; };
 template <> struct Vec<double, 1> { using T = double; };
 template <> struct Vec<float, 1> { using T = float; };
+template <> struct Vec<float, 2> { using T = float2; };
 
 template <typename Real, int V>
 __device__ __forceinline__ void ld_stream(const Real *p, Real (&o)[V])
@@ -95,11 +99,12 @@ __device__ __forceinline__ void ld_ro2(const float *p, float &a, float &b)
     a = t.x; b = t.y;
 }
 
-template <typename Real, int V>
-__global__ void __launch_bounds__(256) push_kernel(const PushArgs<Real> a)
+template <typename Real, int V, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> a)
 {
+    // no early exit: the arrays are padded past n (common.cuh), the whole warp stays converged for
+    // the warp-aggregated histogram; side effects of slots >= n are masked.
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-    if (p0 >= a.n) return;
 
     Real x[V], y[V], z[V], vx[V], vy[V], vz[V], q0[V], q1[V], q2[V], q3[V];
     uint8_t al[V];
@@ -118,6 +123,8 @@ __global__ void __launch_bounds__(256) push_kernel(const PushArgs<Real> a)
 
     // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
     Real e[V][4], rec[V][12], dx[V], dy[V];
+    uint32_t newcell[V];
+    Real col[V][3];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int ie = tex_idx(q2[k], FSIM_N_ENTROPY) + FSIM_N_ENTROPY * tex_idx(q3[k], FSIM_N_ENTROPY);
@@ -177,6 +184,7 @@ __global__ void __launch_bounds__(256) push_kernel(const PushArgs<Real> a)
         bool keep = false;
         if (rn == rn && nzp == nzp)  // NaN position => absorbed (documented rule)
             keep = __ldg(a.sink + ((size_t)tex_idx(rn, a.nr) + (size_t)tex_idx(nzp, a.nz) * a.nr)) != 0;
+        Real rkey = rn;
         if (keep) {
             x[k] = nx; y[k] = ny; z[k] = nzp; al[k] = 1;
         } else {
@@ -184,7 +192,11 @@ __global__ void __launch_bounds__(256) push_kernel(const PushArgs<Real> a)
             Real sx, sz;
             ld_ro2(a.invcdf + 2 * (size_t)it, sx, sz);
             x[k] = sx; y[k] = (Real)0.0; z[k] = sz; al[k] = 0;
+            rkey = fsqrt(sx * sx + (Real)0.0 * (Real)0.0);
         }
+        if (a.key)  // deposit prepass on the NEW state (what density() will see)
+            newcell[k] = sprite_key_colour<Real>(x[k], y[k], z[k], rkey, vx[k], vy[k], vz[k], a.nr, a.nz,
+                                                 a.row0, a.rows, col[k][0], col[k][1], col[k][2]);
     }
 
     st_stream<Real, V>(a.a[AX] + p0, x);
@@ -200,21 +212,27 @@ __global__ void __launch_bounds__(256) push_kernel(const PushArgs<Real> a)
 #pragma unroll
     for (int k = 0; k < V; ++k) a.alive[p0 + k] = al[k];
 
-    if (a.key) {  // fused first pass of the counting sort: key + histogram of the NEW cell
+    if (a.key) {  // key, colour and the warp-aggregated histogram of the counting sort
+        const int lane = threadIdx.x & 31;
+        Real t[V];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) t[k] = col[k][q];
+            st_stream<Real, V>(a.dcol[q] + p0, t);
+        }
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            if (p0 + k >= a.n) break;
-            const Real r = fsqrt(x[k] * x[k] + y[k] * y[k]);
-            int cj = tex_idx(z[k], a.nz) - a.row0;
-            cj = cj < 0 ? 0 : (cj >= a.rows ? a.rows - 1 : cj);
-            const uint32_t c = (uint32_t)tex_idx(r, a.nr) + (uint32_t)cj * a.nr;
-            a.key[p0 + k] = c;
-            atomicAdd(a.counts + c, 1u);
+            const bool valid = p0 + k < a.n;
+            const uint32_t c = valid ? (newcell[k] & KEY_MASK) : 0xffffffffu;
+            if (valid) a.key[p0 + k] = newcell[k];
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            if (valid && (__ffs(peers) - 1) == lane) atomicAdd(a.counts + c, (uint32_t)__popc(peers));
         }
     }
 }
 
-template <typename Real, int V>
+template <typename Real, int V, int BLOCK, int MINB>
 static int push_impl(fsim_sim *s, bool with_hist)
 {
     PushArgs<Real> a;
@@ -225,27 +243,51 @@ static int push_impl(fsim_sim *s, bool with_hist)
     a.sink = s->sink;
     a.invcdf = (const Real *)s->invcdf;
     a.key = with_hist ? s->key : nullptr;
+    for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
     a.counts = s->counts;
     a.oob = s->oob;
     a.n = s->n;
     a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
     a.sf = (Real)s->step_factor;
-    const int block = 256;
     const int64_t nvec = (s->n + V - 1) / V;
     if (nvec == 0) return FSIM_OK;
     Bracket b(s, "push");
-    push_kernel<Real, V><<<grid_for(nvec, block), block, 0, s->stream>>>(a);
+    push_kernel<Real, V, BLOCK, MINB><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     FSIM_CUDA(cudaGetLastError());
     return FSIM_OK;
 }
 
-int launch_push(fsim_sim *s)
+// Tuning variants (vector width, block size, register cap); FSIM_PUSH_VARIANT selects one at run
+// time for measurement, the default is the one measured fastest on B200 (profiles/).
+static int push_variant()
 {
-    return dispatch(s, [&](auto tag) {
+    const char *e = getenv("FSIM_PUSH_VARIANT");  // read per launch: tools/tune.py sweeps it in-process
+    return e ? atoi(e) : 4;  // measured fastest on B200 for fp64 (profiles/r1_tuning.md)
+}
+
+int launch_push(fsim_sim *s, bool with_hist)
+{
+    if (with_hist && s->counts_dirty) {  // an unconsumed histogram: start from zero
+        FSIM_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (s->ncell_local + 1), s->stream));
+        s->counts_dirty = false;
+    }
+    int rc = dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
         constexpr int V = 16 / sizeof(Real);  // 128-bit loads and stores
-        return push_impl<Real, V>(s, false);
+        switch (push_variant()) {
+        case 1: return push_impl<Real, V, 128, 4>(s, with_hist);
+        case 2: return push_impl<Real, V, 256, 3>(s, with_hist);
+        case 3: return push_impl<Real, V / 2, 256, 3>(s, with_hist);
+        case 4: return push_impl<Real, V / 2, 256, 4>(s, with_hist);
+        case 5: return push_impl<Real, V / 2, 128, 6>(s, with_hist);
+        case 6: return push_impl<Real, V / 2, 512, 2>(s, with_hist);
+        default: return push_impl<Real, V, 256, 2>(s, with_hist);
+        }
     });
+    s->binned = false;
+    s->keys_valid = with_hist;
+    if (with_hist) s->counts_dirty = true;
+    return rc;
 }
 
 }  // namespace fsim

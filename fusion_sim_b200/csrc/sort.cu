@@ -6,36 +6,48 @@
 // by cell turns the gather into a streaming read of the cell table and gives every cell a
 // contiguous particle segment for the deterministic per-cell sums (deposit.cu).
 //
-// Three launches: (1) key + histogram, (2) exclusive scan of the per-cell counts,
-// (3) scatter of the 10 real arrays, the alive byte and the particle id.  The order INSIDE a
-// cell segment is not fixed by this sort (atomic cursors); determinism of the deposit comes
+// Every frame: (1) key + histogram (emitted by the second half-step's push, or by prepass_kernel),
+// (2) exclusive scan of the per-cell counts, (3) a 4-byte INDEX scatter: perm[] lists the
+// particle slots in cell order.  Every `sort_interval` frames the storage itself is permuted
+// (apply_perm_kernel) so that the push's cell-table gather stays a near-streaming read.  The
+// order INSIDE a cell segment is not fixed (atomic cursors); determinism of the deposit comes
 // from summing each segment in ascending particle-id order (deposit.cu), and the accessors
 // un-permute by id, so nothing observable depends on it.
 #include "common.cuh"
 
 namespace fsim {
 
+// Deposit prepass from the stored state (used when the push did not emit it: first density(),
+// after set()/half_step(), slab mode): sort key (+ clipped flag), sprite colour, histogram.
 template <typename Real>
-__global__ void __launch_bounds__(256)
-key_hist_kernel(const Real *__restrict__ x, const Real *__restrict__ y, const Real *__restrict__ z,
-                int64_t n, int nr, int nz, int row0, int rows, uint32_t *__restrict__ key,
-                uint32_t *__restrict__ counts)
+struct PrepassArgs {
+    const Real *x, *y, *z, *vx, *vy, *vz;
+    uint32_t *key, *counts;
+    Real *dcol[3];
+    int64_t n;
+    int nr, nz, row0, rows;
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256) prepass_kernel(const PrepassArgs<Real> a)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < n;
+    const bool valid = p < a.n;
     uint32_t c = 0xffffffffu;  // lanes past the end form their own (ignored) group
     if (valid) {
-        const Real xx = x[p], yy = y[p];
+        const Real xx = a.x[p], yy = a.y[p];
         const Real r = fsqrt(xx * xx + yy * yy);
-        int cj = tex_idx(z[p], nz) - row0;
-        cj = cj < 0 ? 0 : (cj >= rows ? rows - 1 : cj);
-        c = (uint32_t)tex_idx(r, nr) + (uint32_t)cj * (uint32_t)nr;
-        key[p] = c;
+        Real c0, c1, c2;
+        const uint32_t key = sprite_key_colour<Real>(xx, yy, a.z[p], r, a.vx[p], a.vy[p], a.vz[p], a.nr,
+                                                     a.nz, a.row0, a.rows, c0, c1, c2);
+        a.key[p] = key;
+        a.dcol[0][p] = c0; a.dcol[1][p] = c1; a.dcol[2][p] = c2;
+        c = key & KEY_MASK;
     }
     // warp-aggregated histogram: sorted input puts a handful of distinct cells in a warp
     const unsigned peers = __match_any_sync(0xffffffffu, c);
     if (valid && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-        atomicAdd(counts + c, (uint32_t)__popc(peers));
+        atomicAdd(a.counts + c, (uint32_t)__popc(peers));
 }
 
 // ---- exclusive scan over ncell counts: per-block sums, scan of block sums, final pass ----
@@ -131,86 +143,133 @@ scan_final_kernel(uint32_t *__restrict__ counts, int64_t m, const uint32_t *__re
     }
 }
 
+// physical re-sort: dst[j] = src[perm[j]] -- gathered reads (the storage is nearly ordered, so
+// they stay within a few lines), fully coalesced writes, no atomics.
 template <typename Real>
-struct ScatterArgs {
+struct PermuteArgs {
     const Real *src[NPART_ARRAYS];
     Real *dst[NPART_ARRAYS];
     const uint8_t *alive_src;
     uint8_t *alive_dst;
     const uint32_t *id_src;
     uint32_t *id_dst;
-    const uint32_t *key;
-    uint32_t *cursor;
+    const uint32_t *perm;
     int64_t n;
 };
 
 template <typename Real>
-__global__ void __launch_bounds__(256) scatter_kernel(const ScatterArgs<Real> a)
+__global__ void __launch_bounds__(256) apply_perm_kernel(const PermuteArgs<Real> a)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n) return;
+    const size_t p = a.perm[j];
+    Real v[NPART_ARRAYS];
+#pragma unroll
+    for (int k = 0; k < NPART_ARRAYS; ++k) v[k] = a.src[k][p];
+    const uint8_t al = a.alive_src[p];
+    const uint32_t id = a.id_src[p];
+#pragma unroll
+    for (int k = 0; k < NPART_ARRAYS; ++k) __stcs(a.dst[k] + j, v[k]);
+    a.alive_dst[j] = al;
+    a.id_dst[j] = id;
+}
+
+// index sort: perm[slot in cell order] = storage slot; nothing but 4 bytes per particle moves
+__global__ void __launch_bounds__(256)
+index_scatter_kernel(const uint32_t *__restrict__ key, uint32_t *__restrict__ cursor,
+                     uint32_t *__restrict__ perm, int64_t n)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < a.n;
-    const uint32_t c = valid ? a.key[p] : 0xffffffffu;
-    // one atomic per distinct cell per warp; lanes of the same cell take consecutive slots
+    const bool valid = p < n;
+    const uint32_t c = valid ? (key[p] & KEY_MASK) : 0xffffffffu;
     const unsigned peers = __match_any_sync(0xffffffffu, c);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if (valid && lane == leader) base = atomicAdd(a.cursor + c, (uint32_t)__popc(peers));
+    if (valid && lane == leader) base = atomicAdd(cursor + c, (uint32_t)__popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (!valid) return;
-    const size_t d = (size_t)base + (size_t)__popc(peers & ((1u << lane) - 1u));
-#pragma unroll
-    for (int k = 0; k < NPART_ARRAYS; ++k) a.dst[k][d] = __ldcs(a.src[k] + p);
-    a.alive_dst[d] = a.alive_src[p];
-    a.id_dst[d] = a.id_src[p];
+    if (valid) perm[(size_t)base + (size_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)p;
 }
 
-int launch_sort(fsim_sim *s)
+int launch_keys(fsim_sim *s)
 {
-    if (s->n == 0) {
-        FSIM_CUDA(cudaMemsetAsync(s->starts, 0, sizeof(uint32_t) * (s->ncell_local + 2), s->stream));
-        s->sorted = true;
-        return FSIM_OK;
+    if (s->counts_dirty) {
+        FSIM_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (s->ncell_local + 1), s->stream));
+        s->counts_dirty = false;
     }
+    if (s->n) {
+        int rc = dispatch(s, [&](auto tag) {
+            using Real = decltype(tag);
+            const int c = s->cur;
+            PrepassArgs<Real> a;
+            a.x = (const Real *)s->part[c][AX]; a.y = (const Real *)s->part[c][AY];
+            a.z = (const Real *)s->part[c][AZ]; a.vx = (const Real *)s->part[c][AVX];
+            a.vy = (const Real *)s->part[c][AVY]; a.vz = (const Real *)s->part[c][AVZ];
+            a.key = s->key; a.counts = s->counts;
+            for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
+            a.n = s->n; a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
+            Bracket b(s, "prepass");
+            prepass_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
+            FSIM_CUDA(cudaGetLastError());
+            return (int)FSIM_OK;
+        });
+        FSIM_TRY(rc);
+    }
+    s->keys_valid = true;
+    s->counts_dirty = true;
+    return FSIM_OK;
+}
+
+// scan of the histogram, then the 4-byte index scatter.  Requires keys_valid.
+int launch_bin(fsim_sim *s)
+{
     const int64_t m = s->ncell_local;
     const int ntiles = (int)((m + SCAN_TILE - 1) / SCAN_TILE);
-    int rc = dispatch(s, [&](auto tag) {
-        using Real = decltype(tag);
-        const int src = s->cur, dst = s->cur ^ 1;
-        {
-            Bracket b(s, "hist");
-            key_hist_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
-                (const Real *)s->part[src][AX], (const Real *)s->part[src][AY],
-                (const Real *)s->part[src][AZ], s->n, s->nr, s->nz, s->row0, s->rows, s->key, s->counts);
-            FSIM_CUDA(cudaGetLastError());
-        }
-        {
-            Bracket b(s, "scan");
-            scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, s->stream>>>(s->counts, m, s->blocksums);
-            scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, s->stream>>>(s->blocksums, ntiles);
-            scan_final_kernel<<<ntiles, SCAN_BLOCK, 0, s->stream>>>(s->counts, m, s->blocksums, s->starts,
-                                                                   s->cursor);
-            s->launches += 2;
-            FSIM_CUDA(cudaGetLastError());
-        }
-        {
-            ScatterArgs<Real> a;
+    {
+        Bracket b(s, "scan");
+        scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, s->stream>>>(s->counts, m, s->blocksums);
+        scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, s->stream>>>(s->blocksums, ntiles);
+        scan_final_kernel<<<ntiles, SCAN_BLOCK, 0, s->stream>>>(s->counts, m, s->blocksums, s->starts, s->cursor);
+        s->launches += 2;
+        FSIM_CUDA(cudaGetLastError());
+    }
+    s->counts_dirty = false;  // scan_final zeroed counts[]
+    if (s->n) {
+        Bracket b(s, "index_scatter");
+        index_scatter_kernel<<<grid_for(s->n, 256), 256, 0, s->stream>>>(s->key, s->cursor, s->perm, s->n);
+        FSIM_CUDA(cudaGetLastError());
+    }
+    s->binned = true;
+    return FSIM_OK;
+}
+
+// Physical re-sort of the particle storage into cell order.  Requires binned.  key[] / dcol[] are
+// per-slot and become stale, so the binning is invalidated (the next push re-emits them).
+int launch_apply_perm(fsim_sim *s)
+{
+    if (s->n) {
+        int rc = dispatch(s, [&](auto tag) {
+            using Real = decltype(tag);
+            const int src = s->cur, dst = s->cur ^ 1;
+            PermuteArgs<Real> a;
             for (int k = 0; k < NPART_ARRAYS; ++k) {
                 a.src[k] = (const Real *)s->part[src][k];
                 a.dst[k] = (Real *)s->part[dst][k];
             }
             a.alive_src = s->alive[src]; a.alive_dst = s->alive[dst];
             a.id_src = s->pid[src]; a.id_dst = s->pid[dst];
-            a.key = s->key; a.cursor = s->cursor; a.n = s->n;
-            Bracket b(s, "scatter");
-            scatter_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
+            a.perm = s->perm; a.n = s->n;
+            Bracket b(s, "permute");
+            apply_perm_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());
-        }
-        s->cur = dst;
-        return (int)FSIM_OK;
-    });
-    if (rc != FSIM_OK) return rc;
-    s->sorted = true;
+            s->cur = dst;
+            return (int)FSIM_OK;
+        });
+        FSIM_TRY(rc);
+    }
+    s->binned = false;
+    s->keys_valid = false;
+    s->ever_sorted = true;
     s->ids_identity = false;
     s->steps_since_sort = 0;
     return FSIM_OK;
