@@ -275,14 +275,19 @@ def run_ours(args):
     for _ in range(args.steps):
         frame()
     kern = {}
-    for nm in ("push", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_heavy", "conv"):
+    for nm in ("push", "push2", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_heavy", "conv"):
         ms, cnt = sim.timing_get(nm)
         if cnt:
             kern[nm] = {"ms_per_launch": ms / cnt, "launches_per_step": cnt / args.steps,
                         "ms_per_step": ms / args.steps}
     sim.timing(False)
     peak, peak_kind = measured_peak()
-    push_ms = kern["push"]["ms_per_launch"]
+    # dominant kernel: the fused step sweep (both half-steps of step() in one pass over HBM,
+    # push.cu NH=2).  Its algorithmic bytes are those of ONE sweep: particle state read + written
+    # once, tables once (SURVEY.md section 8d per-half-step figure).
+    pk = "push2" if "push2" in kern else "push"
+    halves = 2 if pk == "push2" else 1
+    push_ms = kern[pk]["ms_per_launch"]
     alg = push_algorithmic_bytes(n_local, ncell_local, args.precision)
     achieved = alg / (push_ms * 1e-3) / 1e9
     traffic = None
@@ -292,7 +297,9 @@ def run_ours(args):
             traffic = json.load(open(tp)).get(f"{args.workload}_{args.precision}")
         except Exception:
             traffic = None
-    roofline = {"kernel": "push_kernel (fused rand + gather/Boris + push/absorb/respawn half-step)",
+    roofline = {"kernel": "push_kernel<NH=%d> (rand + gather/Boris + push/absorb/respawn, %d half-step(s) per sweep"
+                          " + deposit prepass)" % (halves, halves),
+                "half_steps_per_launch": halves,
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_kind": peak_kind + " HBM copy bandwidth",
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": push_ms, "traffic": traffic,
@@ -340,7 +347,7 @@ def run_ours(args):
                        "parallelism": "slab%d" % world},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb,
-            "push_only_pushes_per_s": n_local * world / (push_ms * 1e-3),
+            "push_only_pushes_per_s": halves * n_local * world / (push_ms * 1e-3),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -691,7 +691,7 @@ static int physical_sort(fsim_sim *s)
 int fsim_half_step(fsim_sim *s)
 {
     FSIM_TRY(check(s));
-    return finish(s, launch_push(s, false));
+    return finish(s, launch_push(s, false, 1));
 }
 
 int fsim_step(fsim_sim *s)
@@ -700,8 +700,8 @@ int fsim_step(fsim_sim *s)
     // out.step, empic.js:1436-1469: B-buffers then A-buffers = two half-steps.  The second one also
     // emits the deposit prepass (sort key, sprite colour, histogram) of the new state for the
     // density() that follows.
-    FSIM_TRY(finish(s, launch_push(s, false)));
-    FSIM_TRY(finish(s, launch_push(s, !s->slab)));
+    // Both are done in ONE sweep over the particle storage (push.cu, NH = 2).
+    FSIM_TRY(finish(s, launch_push(s, !s->slab, 2)));
     s->steps_since_sort++;
     if (s->steps_since_sort >= 4 * sort_interval(s))  // push-only loops: keep the gather coherent
         FSIM_TRY(finish(s, physical_sort(s)));

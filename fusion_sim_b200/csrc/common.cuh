@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t sprite_key_colour(Real x, Real y, Real z, Re
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // kernels / host stages implemented in the other translation units
-int launch_push(fsim_sim *s, bool with_hist);
+int launch_push(fsim_sim *s, bool with_hist, int nhalf);  // nhalf half-steps in one sweep
 int launch_keys(fsim_sim *s);      // deposit prepass from the stored state: key, colour, histogram
 int launch_bin(fsim_sim *s);       // scan + index scatter -> starts[], perm[]
 int launch_apply_perm(fsim_sim *s);  // physical re-sort: storage <- storage[perm]

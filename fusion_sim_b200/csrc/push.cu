@@ -99,7 +99,11 @@ __device__ __forceinline__ void ld_ro2(const float *p, float &a, float &b)
     a = t.x; b = t.y;
 }
 
-template <typename Real, int V, int BLOCK, int MINB>
+// NH = number of leap-frog half-steps done per launch while the particle sits in registers.
+// out.step() is two half-steps with nothing in between that couples particles (static fields), so
+// NH = 2 performs the B-pass and the A-pass of empic.js:1438-1467 in one sweep over HBM: state
+// read once, written once.  Same operations in the same order, hence the same bits.
+template <typename Real, int V, int BLOCK, int MINB, int NH>
 __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> a)
 {
     // no early exit: the arrays are padded past n (common.cuh), the whole warp stays converged for
@@ -121,82 +125,84 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
 #pragma unroll
     for (int k = 0; k < V; ++k) al[k] = a.alive[p0 + k];
 
-    // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
-    Real e[V][4], rec[V][12], dx[V], dy[V];
-    uint32_t newcell[V];
-    Real col[V][3];
+    Real rcur[V];  // sqrt(x*x + y*y) of the current position (:755; reused by the next half-step)
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const int ie = tex_idx(q2[k], FSIM_N_ENTROPY) + FSIM_N_ENTROPY * tex_idx(q3[k], FSIM_N_ENTROPY);
-        ld_ro4(a.ent + 4 * (size_t)ie, e[k]);
-    }
+    for (int k = 0; k < V; ++k) rcur[k] = fsqrt(x[k] * x[k] + y[k] * y[k]);
+
+#pragma unroll 1
+    for (int hs = 0; hs < NH; ++hs) {
+        // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
+        Real e[V][4], rec[V][12], dx[V], dy[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const Real r = fsqrt(x[k] * x[k] + y[k] * y[k]);  // :755
-        dx[k] = x[k] / r;                                 // :756
-        dy[k] = y[k] / r;
-        const int ci = tex_idx(r, a.nr);
-        int cj = tex_idx(z[k], a.nz) - a.row0;
-        if (cj < 0 || cj >= a.rows) {  // slab mode: particle outside the local table
-            if (p0 + k < a.n) atomicAdd(a.oob, 1u);
-            cj = cj < 0 ? 0 : a.rows - 1;
+        for (int k = 0; k < V; ++k) {
+            const int ie = tex_idx(q2[k], FSIM_N_ENTROPY) + FSIM_N_ENTROPY * tex_idx(q3[k], FSIM_N_ENTROPY);
+            ld_ro4(a.ent + 4 * (size_t)ie, e[k]);
         }
-        ld_ro12(a.cellrec + FSIM_CELLREC * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
-    }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const Real r = rcur[k];
+            dx[k] = x[k] / r;  // :756
+            dy[k] = y[k] / r;
+            const int ci = tex_idx(r, a.nr);
+            int cj = tex_idx(z[k], a.nz) - a.row0;
+            if (cj < 0 || cj >= a.rows) {  // slab mode: particle outside the local table
+                if (p0 + k < a.n) atomicAdd(a.oob, 1u);
+                cj = cj < 0 ? 0 : a.rows - 1;
+            }
+            ld_ro12(a.cellrec + FSIM_CELLREC * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
+        }
 
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-        // ---- programStepRandA/B, empic.js:800-807 ----
-        const Real x0 = (Real)FSIM_RNG_KEEP * q2[k] + (Real)FSIM_RNG_MIX * e[k][2];
-        const Real x1 = (Real)FSIM_RNG_KEEP * q3[k] + (Real)FSIM_RNG_MIX * e[k][3];
-        const Real m0 = q0[k] + e[k][0];
-        const Real m1 = q1[k] + e[k][1];
-        const Real o0 = q0[k], o1 = q1[k], o2 = q2[k];  // shaders below read the OLD rand
-        q0[k] = (m0 > (Real)1.0) ? m0 - (Real)1.0 : m0;
-        q1[k] = (m1 > (Real)1.0) ? m1 - (Real)1.0 : m1;
-        q2[k] = (Real)4.0 * x0 * ((Real)1.0 - x0);
-        q3[k] = (Real)4.0 * x1 * ((Real)1.0 - x1);
+        for (int k = 0; k < V; ++k) {
+            // ---- programStepRandA/B, empic.js:800-807 ----
+            const Real x0 = (Real)FSIM_RNG_KEEP * q2[k] + (Real)FSIM_RNG_MIX * e[k][2];
+            const Real x1 = (Real)FSIM_RNG_KEEP * q3[k] + (Real)FSIM_RNG_MIX * e[k][3];
+            const Real m0 = q0[k] + e[k][0];
+            const Real m1 = q1[k] + e[k][1];
+            const Real o0 = q0[k], o1 = q1[k], o2 = q2[k];  // shaders below read the OLD rand
+            q0[k] = (m0 > (Real)1.0) ? m0 - (Real)1.0 : m0;
+            q1[k] = (m1 > (Real)1.0) ? m1 - (Real)1.0 : m1;
+            q2[k] = (Real)4.0 * x0 * ((Real)1.0 - x0);
+            q3[k] = (Real)4.0 * x1 * ((Real)1.0 - x1);
 
-        // ---- step_velocity_frag, empic.js:758-772 ----
-        const Real vr = vx[k] * dx[k] + vy[k] * dy[k];
-        const Real va = vy[k] * dx[k] - vx[k] * dy[k];
-        const Real *R = rec[k];
-        const Real c0 = (R[0] * vr + R[1] * va + R[2] * vz[k]) + R[9];
-        const Real c1 = (R[3] * vr + R[4] * va + R[5] * vz[k]) + R[10];
-        const Real c2 = (R[6] * vr + R[7] * va + R[8] * vz[k]) + R[11];
-        Real nvx, nvy, nvz;
-        if (al[k]) {
-            nvx = c0 * dx[k] - c1 * dy[k];
-            nvy = c0 * dy[k] + c1 * dx[k];
-            nvz = c2;
-        } else {  // just respawned: fresh random velocity (:772)
-            nvx = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o0 - (Real)1.0);
-            nvy = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o1 - (Real)1.0);
-            nvz = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o2 - (Real)1.0);
-        }
-        vx[k] = nvx; vy[k] = nvy; vz[k] = nvz;
+            // ---- step_velocity_frag, empic.js:758-772 ----
+            const Real vr = vx[k] * dx[k] + vy[k] * dy[k];
+            const Real va = vy[k] * dx[k] - vx[k] * dy[k];
+            const Real *R = rec[k];
+            const Real c0 = (R[0] * vr + R[1] * va + R[2] * vz[k]) + R[9];
+            const Real c1 = (R[3] * vr + R[4] * va + R[5] * vz[k]) + R[10];
+            const Real c2 = (R[6] * vr + R[7] * va + R[8] * vz[k]) + R[11];
+            Real nvx, nvy, nvz;
+            if (al[k]) {
+                nvx = c0 * dx[k] - c1 * dy[k];
+                nvy = c0 * dy[k] + c1 * dx[k];
+                nvz = c2;
+            } else {  // just respawned: fresh random velocity (:772)
+                nvx = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o0 - (Real)1.0);
+                nvy = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o1 - (Real)1.0);
+                nvz = (Real)FSIM_RESPAWN_SPEED * ((Real)2.0 * o2 - (Real)1.0);
+            }
+            vx[k] = nvx; vy[k] = nvy; vz[k] = nvz;
 
-        // ---- step_position_frag, empic.js:714-719 ----
-        const Real nx = x[k] + a.sf * nvx;
-        const Real ny = y[k] + a.sf * nvy;
-        const Real nzp = z[k] + a.sf * nvz;
-        const Real rn = fsqrt(nx * nx + ny * ny);
-        bool keep = false;
-        if (rn == rn && nzp == nzp)  // NaN position => absorbed (documented rule)
-            keep = __ldg(a.sink + ((size_t)tex_idx(rn, a.nr) + (size_t)tex_idx(nzp, a.nz) * a.nr)) != 0;
-        Real rkey = rn;
-        if (keep) {
-            x[k] = nx; y[k] = ny; z[k] = nzp; al[k] = 1;
-        } else {
-            const int it = tex_idx(o0, FSIM_N_INVCDF) + FSIM_N_INVCDF * tex_idx(o1, FSIM_N_INVCDF);
-            Real sx, sz;
-            ld_ro2(a.invcdf + 2 * (size_t)it, sx, sz);
-            x[k] = sx; y[k] = (Real)0.0; z[k] = sz; al[k] = 0;
-            rkey = fsqrt(sx * sx + (Real)0.0 * (Real)0.0);
+            // ---- step_position_frag, empic.js:714-719 ----
+            const Real nx = x[k] + a.sf * nvx;
+            const Real ny = y[k] + a.sf * nvy;
+            const Real nzp = z[k] + a.sf * nvz;
+            const Real rn = fsqrt(nx * nx + ny * ny);
+            bool keep = false;
+            if (rn == rn && nzp == nzp)  // NaN position => absorbed (documented rule)
+                keep = __ldg(a.sink + ((size_t)tex_idx(rn, a.nr) + (size_t)tex_idx(nzp, a.nz) * a.nr)) != 0;
+            if (keep) {
+                x[k] = nx; y[k] = ny; z[k] = nzp; al[k] = 1;
+                rcur[k] = rn;
+            } else {
+                const int it = tex_idx(o0, FSIM_N_INVCDF) + FSIM_N_INVCDF * tex_idx(o1, FSIM_N_INVCDF);
+                Real sx, sz;
+                ld_ro2(a.invcdf + 2 * (size_t)it, sx, sz);
+                x[k] = sx; y[k] = (Real)0.0; z[k] = sz; al[k] = 0;
+                rcur[k] = fsqrt(sx * sx + (Real)0.0 * (Real)0.0);
+            }
         }
-        if (a.key)  // deposit prepass on the NEW state (what density() will see)
-            newcell[k] = sprite_key_colour<Real>(x[k], y[k], z[k], rkey, vx[k], vy[k], vz[k], a.nr, a.nz,
-                                                 a.row0, a.rows, col[k][0], col[k][1], col[k][2]);
     }
 
     st_stream<Real, V>(a.a[AX] + p0, x);
@@ -212,15 +218,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
 #pragma unroll
     for (int k = 0; k < V; ++k) a.alive[p0 + k] = al[k];
 
-    if (a.key) {  // key, colour and the warp-aggregated histogram of the counting sort
+    if (a.key) {  // deposit prepass on the NEW state (what density() will see): sort key, sprite
+                  // colour and the warp-aggregated histogram of the counting sort
         const int lane = threadIdx.x & 31;
-        Real t[V];
+        uint32_t newcell[V];
+        Real col[3][V];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int k = 0; k < V; ++k)
+            newcell[k] = sprite_key_colour<Real>(x[k], y[k], z[k], rcur[k], vx[k], vy[k], vz[k], a.nr, a.nz,
+                                                 a.row0, a.rows, col[0][k], col[1][k], col[2][k]);
 #pragma unroll
-            for (int k = 0; k < V; ++k) t[k] = col[k][q];
-            st_stream<Real, V>(a.dcol[q] + p0, t);
-        }
+        for (int q = 0; q < 3; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const bool valid = p0 + k < a.n;
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
 }
 
 template <typename Real, int V, int BLOCK, int MINB>
-static int push_impl(fsim_sim *s, bool with_hist)
+static int push_impl(fsim_sim *s, bool with_hist, int nhalf)
 {
     PushArgs<Real> a;
     for (int k = 0; k < NPART_ARRAYS; ++k) a.a[k] = (Real *)s->part[s->cur][k];
@@ -251,8 +259,11 @@ static int push_impl(fsim_sim *s, bool with_hist)
     a.sf = (Real)s->step_factor;
     const int64_t nvec = (s->n + V - 1) / V;
     if (nvec == 0) return FSIM_OK;
-    Bracket b(s, "push");
-    push_kernel<Real, V, BLOCK, MINB><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+    Bracket b(s, nhalf == 2 ? "push2" : "push");
+    if (nhalf == 2)
+        push_kernel<Real, V, BLOCK, MINB, 2><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+    else
+        push_kernel<Real, V, BLOCK, MINB, 1><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     FSIM_CUDA(cudaGetLastError());
     return FSIM_OK;
 }
@@ -265,7 +276,7 @@ static int push_variant()
     return e ? atoi(e) : 4;  // measured fastest on B200 for fp64 (profiles/r1_tuning.md)
 }
 
-int launch_push(fsim_sim *s, bool with_hist)
+int launch_push(fsim_sim *s, bool with_hist, int nhalf)
 {
     if (with_hist && s->counts_dirty) {  // an unconsumed histogram: start from zero
         FSIM_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (s->ncell_local + 1), s->stream));
@@ -275,13 +286,13 @@ int launch_push(fsim_sim *s, bool with_hist)
         using Real = decltype(tag);
         constexpr int V = 16 / sizeof(Real);  // 128-bit loads and stores
         switch (push_variant()) {
-        case 1: return push_impl<Real, V, 128, 4>(s, with_hist);
-        case 2: return push_impl<Real, V, 256, 3>(s, with_hist);
-        case 3: return push_impl<Real, V / 2, 256, 3>(s, with_hist);
-        case 4: return push_impl<Real, V / 2, 256, 4>(s, with_hist);
-        case 5: return push_impl<Real, V / 2, 128, 6>(s, with_hist);
-        case 6: return push_impl<Real, V / 2, 512, 2>(s, with_hist);
-        default: return push_impl<Real, V, 256, 2>(s, with_hist);
+        case 1: return push_impl<Real, V, 128, 4>(s, with_hist, nhalf);
+        case 2: return push_impl<Real, V, 256, 3>(s, with_hist, nhalf);
+        case 3: return push_impl<Real, V / 2, 256, 3>(s, with_hist, nhalf);
+        case 4: return push_impl<Real, V / 2, 256, 4>(s, with_hist, nhalf);
+        case 5: return push_impl<Real, V / 2, 128, 6>(s, with_hist, nhalf);
+        case 6: return push_impl<Real, V / 2, 512, 2>(s, with_hist, nhalf);
+        default: return push_impl<Real, V, 256, 2>(s, with_hist, nhalf);
         }
     });
     s->binned = false;

@@ -17,7 +17,7 @@ sc = bench.build_scene(workload, 0, 1)
 spec = dict(sc["spec"], precision=precision)
 sim = makeCylindricalParticlePusher(spec)
 apply_scene(sim, sc)
-names = ("push", "scan", "permute", "index_scatter", "cellsum", "cellsum_heavy", "conv", "prepass")
+names = ("push", "push2", "scan", "permute", "index_scatter", "cellsum", "cellsum_heavy", "conv", "prepass")
 out = {}
 for v in variants:
     os.environ["FSIM_PUSH_VARIANT"] = str(v)
