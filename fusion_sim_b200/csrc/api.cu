@@ -358,6 +358,8 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_TRY(dalloc(&s->heavy_list, s->cap / 64 + 2));
     FSIM_TRY(dalloc(&s->heavy_n, 1));
     FSIM_TRY(dalloc(&s->oob, 1));
+    FSIM_TRY(dalloc(&s->mscratch, 2 * 64 + 8));
+    FSIM_TRY(dalloc(&s->hole_flag, s->cap));
 
     // host-computed constant tables (libm): deposit footprint and quadrature cosines
     double shape64[FSIM_NSHAPE * FSIM_NSHAPE], shape32[FSIM_NSHAPE * FSIM_NSHAPE];
@@ -398,7 +400,7 @@ static void free_all(fsim_sim *s)
     }
     void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->dcol[2], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
-                    s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr};
+                    s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag};
     for (void *p : ptrs) cudaFree(p);
     if (s->hstage) cudaFreeHost(s->hstage);
     for (auto &kv : s->timers)
@@ -415,8 +417,8 @@ static int particles_in3(fsim_sim *s, const double *host, int a0, double f0, dou
                          bool set_alive)
 {
     if (!host) return fail(FSIM_ERR_INVALID, "null array");
-    if (s->slab && !s->ids_identity)
-        return fail(FSIM_ERR_STATE, "set position/velocity after migration is not defined in slab mode");
+    // single GPU: element p of the host array is particle id p wherever it is stored;
+    // slab mode: element p is storage slot p (ids are global there, see fsim_set_ids)
     if (s->n == 0) return FSIM_OK;
     FSIM_TRY(stage_in(s, host, sizeof(double) * 3 * s->n));
     return dispatch(s, [&](auto tag) {
@@ -598,7 +600,6 @@ int fsim_set_rand(fsim_sim *s, const double *rnd)
 {
     FSIM_TRY(check(s));
     if (!rnd) return fail(FSIM_ERR_INVALID, "null array");
-    if (s->slab && !s->ids_identity) return fail(FSIM_ERR_STATE, "set rand after migration is not defined in slab mode");
     if (s->n == 0) return FSIM_OK;
     FSIM_TRY(finish(s, stage_in(s, rnd, sizeof(double) * 4 * s->n)));
     return finish(s, dispatch(s, [&](auto tag) {
@@ -619,6 +620,12 @@ int fsim_set_particle_count(fsim_sim *s, int64_t n)
     s->n = n;
     s->binned = false;
     s->keys_valid = false;
+    // slots get fresh ids id_base + slot (a re-initialisation; fsim_set_ids may override)
+    if (n) {
+        iota_ids_kernel<double><<<grid_for(n, 256), 256, 0, s->stream>>>(s->pid[s->cur], n, s->id_base);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+    }
     return FSIM_OK;
 }
 int fsim_set_ids(fsim_sim *s, const uint64_t *ids)
@@ -741,9 +748,14 @@ int fsim_render_rgba8(fsim_sim *s, uint8_t *rgba)
     if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
     const size_t bytes = 4 * (size_t)s->ncell_global;
     FSIM_TRY(finish(s, ensure_stage(s, bytes)));
-    if (s->slab) FSIM_CUDA(cudaMemsetAsync(s->stage, 0, bytes, s->stream));
     FSIM_TRY(finish(s, launch_render(s, (uint8_t *)s->stage)));
-    return finish(s, stage_out(s, rgba, bytes));
+    // canvas rows run top-down (row nz-1-j): the owned rows [own0, own0+own_rows) are one block;
+    // a slab rank fills only its block of the caller's full-size image.
+    const size_t off = 4 * (size_t)s->nr * (size_t)(s->nz - s->own0 - s->own_rows);
+    const size_t len = 4 * (size_t)s->nr * (size_t)s->own_rows;
+    FSIM_CUDA(cudaMemcpyAsync(rgba + off, (uint8_t *)s->stage + off, len, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
 }
 
 int fsim_sync(fsim_sim *s)

@@ -114,8 +114,11 @@ struct fsim_sim {
     size_t stage_bytes = 0;
     void *hstage = nullptr;
     size_t hstage_bytes = 0;
-    void *migr = nullptr;
+    void *migr = nullptr;          // packed migration records (send side)
     size_t migr_bytes = 0;
+    uint32_t *mscratch = nullptr;  // small counters of the migration kernels
+    uint8_t *hole_flag = nullptr;  // [cap] 1 = slot vacated by a leaver
+    uint32_t nholes_host = 0;
 
     // measurement
     bool timing = false;
@@ -186,12 +189,12 @@ constexpr uint32_t KEY_MASK = 0x7fffffffu;
 // Vertex shader of programMoments01 (empic.js:994-1006) for a particle at (x,y,z) with velocity v:
 // colour 0.001*(v_r, v_a, v_z) (the alpha channel is the constant 0.001*1.0) and the sort key =
 // gather cell (clamped like the texture fetch), with KEY_CLIPPED when the sprite centre lies
-// outside the target (GLES2 point clipping), is NaN, or is not in a locally held row.
+// outside the target (GLES2 point clipping), is NaN, or is not in a row this rank owns.
 // `r` = sqrt(x*x + y*y) is passed in because the push kernel already has it.
 template <typename Real>
 __device__ __forceinline__ uint32_t sprite_key_colour(Real x, Real y, Real z, Real r, Real vx, Real vy,
                                                       Real vz, int nr, int nz, int row0, int rows,
-                                                      Real &c0, Real &c1, Real &c2)
+                                                      int own_lo, int own_hi, Real &c0, Real &c1, Real &c2)
 {
     const Real dx = x / r, dy = y / r;
     const Real vr = vx * dx + vy * dy;
@@ -201,7 +204,7 @@ __device__ __forceinline__ uint32_t sprite_key_colour(Real x, Real y, Real z, Re
     c2 = (Real)FSIM_DEPOSIT_WEIGHT * vz;
     const int gj = tex_idx(z, nz);
     int cj = gj - row0;
-    const bool local = cj >= 0 && cj < rows;
+    const bool local = cj >= own_lo && cj < own_hi;  // deposited only by the rank that owns the row
     cj = cj < 0 ? 0 : (cj >= rows ? rows - 1 : cj);
     uint32_t key = (uint32_t)tex_idx(r, nr) + (uint32_t)cj * (uint32_t)nr;
     const Real xw = r * (Real)nr, yw = z * (Real)nz;

@@ -1,5 +1,169 @@
-// migrate.cu -- multi-GPU slab exchange.  Filled in below.
+// migrate.cu -- multi-GPU slab exchange: one process per GPU, the grid is
+// cut into slabs of rows along z (index i + j*nr, empic.js:1162, makes a slab contiguous).
+//
+//  * particle migration: a particle whose row floor(z*nz) is not owned by this rank (it drifted
+//    across the slab boundary, or it respawned anywhere: the source pdf is global, empic.js:717)
+//    is packed into a device buffer grouped by destination rank; the caller moves the groups with
+//    an all-to-all-v (NCCL through torch.distributed) and hands the arrivals to
+//    fsim_migrate_unpack, which fills the holes and compacts the storage.  Records carry the global
+//    particle id, so the id-ordered deposit stays bit-identical to a single-GPU run.
+//  * halo of the per-cell sums: 5 rows (footprint radius, empic.js:949-952) each side.
+//
+// Record layout: NPART_ARRAYS reals (x y z vx vy vz q0..q3), then u32 id, u32 alive.
+#include <vector>
+
 #include "common.cuh"
+
+namespace fsim {
+
+constexpr int MAX_RANKS = 64;
+
+struct RankBounds {
+    int n;
+    int self;
+    int lo[MAX_RANKS + 1];  // rank k owns rows [lo[k], lo[k+1])
+};
+
+template <typename Real>
+__device__ __forceinline__ int dest_rank(const RankBounds &rb, Real z, int nz)
+{
+    const int row = tex_idx(z, nz);  // NaN -> row 0: same rule as every texture fetch
+    int d = 0;
+    while (d + 1 < rb.n && row >= rb.lo[d + 1]) ++d;
+    return d;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+migrate_count_kernel(const Real *__restrict__ z, int64_t n, int nz, RankBounds rb, uint32_t *__restrict__ counts)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int d = dest_rank(rb, z[p], nz);
+    if (d != rb.self) atomicAdd(counts + d, 1u);
+}
+
+template <typename Real>
+struct PackArgs {
+    const Real *src[NPART_ARRAYS];
+    const uint8_t *alive;
+    const uint32_t *id;
+    unsigned char *buf;
+    uint32_t *cursor;   // [nranks] running offsets (records) into buf, initialised to the group starts
+    uint32_t *holes;    // slots vacated
+    uint32_t *nholes;
+    uint8_t *hole_flag;
+    int64_t n;
+    int nz;
+    RankBounds rb;
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256) migrate_pack_kernel(const PackArgs<Real> a)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n) return;
+    const int d = dest_rank(a.rb, a.src[AZ][p], a.nz);
+    if (d == a.rb.self) return;
+    const uint32_t slot = atomicAdd(a.cursor + d, 1u);
+    unsigned char *rec = a.buf + (size_t)slot * (NPART_ARRAYS * sizeof(Real) + 8);
+    Real *r = reinterpret_cast<Real *>(rec);
+#pragma unroll
+    for (int k = 0; k < NPART_ARRAYS; ++k) r[k] = a.src[k][p];
+    uint32_t *t = reinterpret_cast<uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
+    t[0] = a.id[p];
+    t[1] = a.alive[p];
+    a.holes[atomicAdd(a.nholes, 1u)] = (uint32_t)p;
+    a.hole_flag[p] = 1;
+}
+
+template <typename Real>
+struct UnpackArgs {
+    Real *dst[NPART_ARRAYS];
+    uint8_t *alive;
+    uint32_t *id;
+    const unsigned char *buf;
+    const uint32_t *holes;
+    uint8_t *hole_flag;
+    uint32_t nholes;
+    int64_t n_old;
+    int64_t nrecv;
+};
+
+// arrival i goes into hole i while holes last, then to the end of the storage
+template <typename Real>
+__global__ void __launch_bounds__(256) migrate_unpack_kernel(const UnpackArgs<Real> a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nrecv) return;
+    size_t slot;
+    if (i < (int64_t)a.nholes) {
+        slot = a.holes[i];
+        a.hole_flag[slot] = 0;
+    } else {
+        slot = (size_t)(a.n_old + (i - (int64_t)a.nholes));
+    }
+    const unsigned char *rec = a.buf + (size_t)i * (NPART_ARRAYS * sizeof(Real) + 8);
+    const Real *r = reinterpret_cast<const Real *>(rec);
+#pragma unroll
+    for (int k = 0; k < NPART_ARRAYS; ++k) a.dst[k][slot] = r[k];
+    const uint32_t *t = reinterpret_cast<const uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
+    a.id[slot] = t[0];
+    a.alive[slot] = (uint8_t)t[1];
+}
+
+// more leavers than arrivals: the storage shrinks to n_new; live particles in the tail
+// [n_new, n_old) move into the unfilled holes below n_new.
+__global__ void __launch_bounds__(256)
+compact_lists_kernel(const uint32_t *__restrict__ holes, uint32_t nholes, uint32_t first_unfilled,
+                     const uint8_t *__restrict__ hole_flag, int64_t n_new, int64_t n_old,
+                     uint32_t *__restrict__ targets, uint32_t *__restrict__ ntargets,
+                     uint32_t *__restrict__ sources, uint32_t *__restrict__ nsources)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nh = (int64_t)nholes - first_unfilled;
+    if (t < nh) {
+        const uint32_t slot = holes[first_unfilled + t];
+        if ((int64_t)slot < n_new) targets[atomicAdd(ntargets, 1u)] = slot;
+    }
+    const int64_t q = n_new + t;
+    if (q < n_old && !hole_flag[q]) sources[atomicAdd(nsources, 1u)] = (uint32_t)q;
+}
+
+template <typename Real>
+struct MoveArgs {
+    Real *a[NPART_ARRAYS];
+    uint8_t *alive;
+    uint32_t *id;
+    const uint32_t *targets, *sources;
+    const uint32_t *ntargets;
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256) compact_move_kernel(const MoveArgs<Real> m)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *m.ntargets) return;
+    const size_t d = m.targets[i], s = m.sources[i];
+#pragma unroll
+    for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k][d] = m.a[k][s];
+    m.alive[d] = m.alive[s];
+    m.id[d] = m.id[s];
+}
+
+static int ensure_migr(fsim_sim *s, size_t bytes)
+{
+    if (bytes <= s->migr_bytes) return FSIM_OK;
+    if (s->migr) FSIM_CUDA(cudaFree(s->migr));
+    s->migr = nullptr;
+    s->migr_bytes = 0;
+    bytes = bytes + bytes / 2 + 4096;
+    FSIM_CUDA(cudaMalloc(&s->migr, bytes));
+    s->migr_bytes = bytes;
+    return FSIM_OK;
+}
+
+}  // namespace fsim
 
 using namespace fsim;
 
@@ -7,20 +171,147 @@ extern "C" {
 
 int64_t fsim_migrate_record_bytes(const fsim_sim *s) { return s ? (int64_t)(NPART_ARRAYS * s->rs + 8) : -1; }
 
-int fsim_migrate_pack(fsim_sim *, const int64_t *, int32_t, int32_t, int64_t *, void **)
+int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, int32_t self, int64_t *send_counts,
+                      void **send_buf_dev)
 {
-    set_error("fsim_migrate_pack: not implemented yet");
-    return FSIM_ERR_UNSUPPORTED;
+    if (!s || !row_bounds || !send_counts || !send_buf_dev) {
+        set_error("fsim_migrate_pack: null argument");
+        return FSIM_ERR_INVALID;
+    }
+    if (nranks < 1 || nranks > MAX_RANKS || self < 0 || self >= nranks) {
+        set_error("fsim_migrate_pack: bad rank arguments");
+        return FSIM_ERR_INVALID;
+    }
+    FSIM_CUDA(cudaSetDevice(s->device));
+    RankBounds rb;
+    rb.n = nranks;
+    rb.self = self;
+    for (int k = 0; k <= nranks; ++k) rb.lo[k] = (int)row_bounds[k];
+    // scratch: counts[nranks] | cursor[nranks] | nholes | ntargets | nsources
+    uint32_t *scr = s->mscratch;
+    FSIM_CUDA(cudaMemsetAsync(scr, 0, sizeof(uint32_t) * (2 * MAX_RANKS + 4), s->stream));
+    uint32_t hc[MAX_RANKS] = {};
+    if (s->n) {
+        int rc = dispatch(s, [&](auto tag) {
+            using Real = decltype(tag);
+            migrate_count_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+                (const Real *)s->part[s->cur][AZ], s->n, s->nz, rb, scr);
+            FSIM_CUDA(cudaGetLastError());
+            s->launches++;
+            return (int)FSIM_OK;
+        });
+        FSIM_TRY(rc);
+        FSIM_CUDA(cudaMemcpyAsync(hc, scr, sizeof(uint32_t) * nranks, cudaMemcpyDeviceToHost, s->stream));
+        FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    uint32_t off[MAX_RANKS] = {};
+    int64_t total = 0;
+    for (int k = 0; k < nranks; ++k) {
+        send_counts[k] = hc[k];
+        off[k] = (uint32_t)total;
+        total += hc[k];
+    }
+    const size_t rb_bytes = NPART_ARRAYS * s->rs + 8;
+    FSIM_TRY(ensure_migr(s, (size_t)total * rb_bytes + 16));
+    // hole list lives in perm[] (free between a density() and the next binning)
+    s->nholes_host = (uint32_t)total;
+    s->binned = false;
+    s->keys_valid = false;
+    *send_buf_dev = s->migr;
+    if (total == 0) return FSIM_OK;
+    FSIM_CUDA(cudaMemcpyAsync(scr + MAX_RANKS, off, sizeof(uint32_t) * nranks, cudaMemcpyHostToDevice, s->stream));
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        PackArgs<Real> a;
+        for (int k = 0; k < NPART_ARRAYS; ++k) a.src[k] = (const Real *)s->part[s->cur][k];
+        a.alive = s->alive[s->cur];
+        a.id = s->pid[s->cur];
+        a.buf = (unsigned char *)s->migr;
+        a.cursor = scr + MAX_RANKS;
+        a.holes = s->perm;
+        a.nholes = scr + 2 * MAX_RANKS;
+        a.hole_flag = s->hole_flag;
+        a.n = s->n; a.nz = s->nz; a.rb = rb;
+        Bracket b(s, "migrate_pack");
+        migrate_pack_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
+        FSIM_CUDA(cudaGetLastError());
+        FSIM_CUDA(cudaStreamSynchronize(s->stream));
+        return (int)FSIM_OK;
+    });
 }
-int fsim_migrate_unpack(fsim_sim *, const void *, int64_t)
+
+int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
 {
-    set_error("fsim_migrate_unpack: not implemented yet");
-    return FSIM_ERR_UNSUPPORTED;
+    if (!s || nrecv < 0 || (nrecv > 0 && !recv_buf_dev)) {
+        set_error("fsim_migrate_unpack: bad argument");
+        return FSIM_ERR_INVALID;
+    }
+    FSIM_CUDA(cudaSetDevice(s->device));
+    const int64_t nholes = s->nholes_host;
+    const int64_t n_old = s->n;
+    const int64_t n_new = n_old - nholes + nrecv;
+    if (n_new > s->cap - 1024) {
+        set_error("fsim_migrate_unpack: arrivals exceed the particle capacity of this rank");
+        return FSIM_ERR_RANGE;
+    }
+    uint32_t *scr = s->mscratch;
+    int rc = dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        const int c = s->cur;
+        if (nrecv) {
+            UnpackArgs<Real> a;
+            for (int k = 0; k < NPART_ARRAYS; ++k) a.dst[k] = (Real *)s->part[c][k];
+            a.alive = s->alive[c]; a.id = s->pid[c];
+            a.buf = (const unsigned char *)recv_buf_dev;
+            a.holes = s->perm; a.hole_flag = s->hole_flag;
+            a.nholes = (uint32_t)nholes; a.n_old = n_old; a.nrecv = nrecv;
+            Bracket b(s, "migrate_unpack");
+            migrate_unpack_kernel<Real><<<grid_for(nrecv, 256), 256, 0, s->stream>>>(a);
+            FSIM_CUDA(cudaGetLastError());
+        }
+        if (nholes > nrecv) {  // shrink: move tail particles into the remaining holes
+            const int64_t span = std::max<int64_t>(nholes - nrecv, n_old - n_new);
+            uint32_t *targets = (uint32_t *)s->key, *sources = (uint32_t *)s->key + (s->cap / 2);
+            compact_lists_kernel<<<grid_for(span, 256), 256, 0, s->stream>>>(
+                s->perm, (uint32_t)nholes, (uint32_t)nrecv, s->hole_flag, n_new, n_old, targets,
+                scr + 2 * MAX_RANKS + 1, sources, scr + 2 * MAX_RANKS + 2);
+            MoveArgs<Real> m;
+            for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k] = (Real *)s->part[c][k];
+            m.alive = s->alive[c]; m.id = s->pid[c];
+            m.targets = targets; m.sources = sources; m.ntargets = scr + 2 * MAX_RANKS + 1;
+            compact_move_kernel<Real><<<grid_for(nholes - nrecv, 256), 256, 0, s->stream>>>(m);
+            FSIM_CUDA(cudaGetLastError());
+            s->launches += 2;
+        }
+        // clear the hole flags of everything that was vacated (cheap: the flag array is 1 B/slot)
+        if (nholes) FSIM_CUDA(cudaMemsetAsync(s->hole_flag, 0, (size_t)std::max(n_old, n_new), s->stream));
+        return (int)FSIM_OK;
+    });
+    FSIM_TRY(rc);
+    s->n = n_new;
+    s->nholes_host = 0;
+    s->ids_identity = false;
+    s->binned = false;
+    s->keys_valid = false;
+    return FSIM_OK;
 }
-int fsim_halo_ptrs(fsim_sim *, void **, void **, void **, void **, int64_t *)
+
+int fsim_halo_ptrs(fsim_sim *s, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, int64_t *bytes_each)
 {
-    set_error("fsim_halo_ptrs: not implemented yet");
-    return FSIM_ERR_UNSUPPORTED;
+    if (!s || !send_lo || !send_hi || !recv_lo || !recv_hi || !bytes_each) {
+        set_error("fsim_halo_ptrs: null argument");
+        return FSIM_ERR_INVALID;
+    }
+    const size_t row_bytes = (size_t)s->nr * 4 * s->rs;
+    const int H = FSIM_SHAPE_MID;
+    unsigned char *S = (unsigned char *)s->cellsum;
+    const int o0 = s->own0 - s->row0;  // first owned row, local index
+    *bytes_each = (int64_t)(H * row_bytes);
+    *send_lo = S + (size_t)o0 * row_bytes;
+    *send_hi = S + (size_t)(o0 + s->own_rows - H) * row_bytes;
+    *recv_lo = (o0 >= H) ? S + (size_t)(o0 - H) * row_bytes : nullptr;
+    *recv_hi = (o0 + s->own_rows + H <= s->rows) ? S + (size_t)(o0 + s->own_rows) * row_bytes : nullptr;
+    return FSIM_OK;
 }
 
 }  // extern "C"

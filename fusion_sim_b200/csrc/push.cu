@@ -31,7 +31,7 @@ struct PushArgs {
     uint32_t *counts;
     uint32_t *oob;
     int64_t n;
-    int nr, nz, row0, rows;
+    int nr, nz, row0, rows, own_lo, own_hi;
     Real sf;
 };
 
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
 #pragma unroll
         for (int k = 0; k < V; ++k)
             newcell[k] = sprite_key_colour<Real>(x[k], y[k], z[k], rcur[k], vx[k], vy[k], vz[k], a.nr, a.nz,
-                                                 a.row0, a.rows, col[0][k], col[1][k], col[2][k]);
+                                                 a.row0, a.rows, a.own_lo, a.own_hi, col[0][k], col[1][k], col[2][k]);
 #pragma unroll
         for (int q = 0; q < 3; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);
 #pragma unroll
@@ -256,6 +256,7 @@ static int push_impl(fsim_sim *s, bool with_hist, int nhalf)
     a.oob = s->oob;
     a.n = s->n;
     a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
+    a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
     a.sf = (Real)s->step_factor;
     const int64_t nvec = (s->n + V - 1) / V;
     if (nvec == 0) return FSIM_OK;

@@ -25,7 +25,7 @@ struct PrepassArgs {
     uint32_t *key, *counts;
     Real *dcol[3];
     int64_t n;
-    int nr, nz, row0, rows;
+    int nr, nz, row0, rows, own_lo, own_hi;
 };
 
 template <typename Real>
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) prepass_kernel(const PrepassArgs<Real> a)
         const Real r = fsqrt(xx * xx + yy * yy);
         Real c0, c1, c2;
         const uint32_t key = sprite_key_colour<Real>(xx, yy, a.z[p], r, a.vx[p], a.vy[p], a.vz[p], a.nr,
-                                                     a.nz, a.row0, a.rows, c0, c1, c2);
+                                                     a.nz, a.row0, a.rows, a.own_lo, a.own_hi, c0, c1, c2);
         a.key[p] = key;
         a.dcol[0][p] = c0; a.dcol[1][p] = c1; a.dcol[2][p] = c2;
         c = key & KEY_MASK;
@@ -208,6 +208,7 @@ int launch_keys(fsim_sim *s)
             a.key = s->key; a.counts = s->counts;
             for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
             a.n = s->n; a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
+            a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
             Bracket b(s, "prepass");
             prepass_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());

@@ -1,0 +1,185 @@
+"""Multi-GPU driver: slab decomposition of the grid along z, one process per GPU
+(SURVEY.md section 8e).  torch.distributed is the plumbing (NCCL over NVLink on GPUs, gloo in
+the CPU tests); the data path is libfusionsim.so.
+
+Per frame:
+  step()     every rank pushes its own particles (no communication: the gather is nearest-grid-
+             point, `halo_rows` rows of cell table beyond the slab cover the drift of a frame);
+  density()  1. particles whose row left the slab (drift, or respawn anywhere in the domain) are
+                packed by destination and moved with an all-to-all-v; records carry the global id;
+             2. sort + per-cell sums of the owned rows (id order => same bits as on one GPU);
+             3. the 5 boundary rows of per-cell sums go to each neighbour (send/recv);
+             4. 11x11 stencil + normalise + running average on the owned rows.
+
+The exchange functions work on any backend object with the small interface used below, so the
+host logic is tested on CPU (gloo, world_size 2) against the single-process oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HALO_DEPOSIT = 5  # footprint radius, empic.js:949-952
+
+
+def slab_bounds(nz: int, world: int):
+    """Rows [b[k], b[k+1]) belong to rank k."""
+    return [(k * nz) // world for k in range(world + 1)]
+
+
+def exchange_records(send: torch.Tensor, send_counts, record_bytes: int, group=None):
+    """All-to-all-v of packed particle records.  `send` is a uint8 tensor holding the records
+    grouped by destination rank, `send_counts[k]` records for rank k.  Returns (recv, nrecv)."""
+    world = dist.get_world_size(group)
+    dev = send.device
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    rc_l = [int(v) for v in rc.tolist()]
+    sc_l = [int(v) for v in send_counts]
+    recv = torch.empty(sum(rc_l) * record_bytes, dtype=torch.uint8, device=dev)
+    dist.all_to_all_single(recv, send[: sum(sc_l) * record_bytes],
+                           output_split_sizes=[c * record_bytes for c in rc_l],
+                           input_split_sizes=[c * record_bytes for c in sc_l], group=group)
+    assert world == len(sc_l)
+    return recv, sum(rc_l)
+
+
+def exchange_halo(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, group=None):
+    """Boundary rows of the per-cell sums: send_lo -> rank-1 (its recv_hi), send_hi -> rank+1."""
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, send_lo, rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_lo, rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, send_hi, rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_hi, rank + 1, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+class _DevPtr:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 3}
+
+
+def _dev_tensor(ptr: int, nbytes: int, device) -> torch.Tensor:
+    if nbytes == 0 or not ptr:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
+
+
+class SlabPusher:
+    """One rank of a slab-decomposed simulation; same member names as the single-GPU object."""
+
+    def __init__(self, spec: dict, scene: dict, rank: int, world: int, halo_rows: int = 16, slack: float = 0.25):
+        from . import _lib
+        from .pusher import CylindricalParticlePusher
+        from .scenes import apply_scene
+        self.rank, self.world = rank, world
+        self.nz, self.nr = int(spec["nz"]), int(spec["nr"])
+        self.bounds = slab_bounds(self.nz, world)
+        n_local = len(scene["position"])
+        lspec = dict(spec)
+        lspec.update(slab_row0=self.bounds[rank], slab_rows=self.bounds[rank + 1] - self.bounds[rank],
+                     halo_rows=halo_rows, nparticles_total=n_local,
+                     capacity=int(n_local * (1 + slack)) + 4096, id_base=rank * n_local)
+        self.device = torch.device("cuda", int(lspec.get("device", 0)))
+        self.sim = CylindricalParticlePusher(lspec)
+        apply_scene(self.sim, scene)
+        self._lib = _lib
+        self.record_bytes = int(_lib.lib().fsim_migrate_record_bytes(self.sim.handle))
+        self.ncell_local = self.sim.ncell_local
+        self._bounds_c = (C.c_int64 * (world + 1))(*self.bounds)
+        self.migrated = 0
+        self.t_migrate = self.t_halo = 0.0
+
+    # -- frame --------------------------------------------------------------------------------
+    def step(self):
+        self.sim.step()
+
+    def migrate(self):
+        L, h = self._lib.lib(), self.sim.handle
+        counts = (C.c_int64 * self.world)()
+        buf = C.c_void_p()
+        self._lib.check(L.fsim_migrate_pack(h, self._bounds_c, self.world, self.rank, counts, C.byref(buf)))
+        sc = list(counts)
+        send = _dev_tensor(buf.value or 0, sum(sc) * self.record_bytes, self.device)
+        recv, nrecv = exchange_records(send, sc, self.record_bytes)
+        torch.cuda.current_stream().synchronize()
+        self._lib.check(L.fsim_migrate_unpack(h, C.c_void_p(recv.data_ptr() if nrecv else 0), nrecv))
+        self.sim.sync()  # recv may be freed after this
+        self.migrated += sum(sc)
+
+    def density(self):
+        L, h = self._lib.lib(), self.sim.handle
+        self.migrate()
+        self._lib.check(L.fsim_density_begin(h))
+        ptrs = [C.c_void_p() for _ in range(4)]
+        nbytes = C.c_int64()
+        self._lib.check(L.fsim_halo_ptrs(h, *[C.byref(p) for p in ptrs], C.byref(nbytes)))
+        t = [_dev_tensor(p.value or 0, nbytes.value if p.value else 0, self.device) for p in ptrs]
+        self.sim.sync()
+        exchange_halo(t[0], t[1], t[2], t[3], self.rank, self.world)
+        torch.cuda.current_stream().synchronize()
+        self._lib.check(L.fsim_density_end(h))
+
+    # -- pass-throughs ----------------------------------------------------------------------------
+    def sync(self):
+        self.sim.sync()
+
+    def mark(self, slot):
+        self.sim.mark(slot)
+
+    def elapsed_ms(self, a, b):
+        return self.sim.elapsed_ms(a, b)
+
+    def timing(self, on):
+        self.sim.timing(on)
+
+    def timing_reset(self):
+        self.sim.timing_reset()
+
+    def timing_get(self, name):
+        return self.sim.timing_get(name)
+
+    def render(self, out):
+        return self.sim.render(out)
+
+    def set(self, value):
+        self.sim.set(value)
+
+    @property
+    def launch_count(self):
+        return self.sim.launch_count
+
+    @property
+    def n(self):
+        return self.sim.n
+
+    def gather_particles(self):
+        """(ids, position[N][4], velocity[N][3], rand[N][4]) of all ranks, sorted by id, on rank 0."""
+        ids = self.sim.getIds().astype(np.int64)
+        parts = [ids, self.sim.getPosition(), self.sim.getVelocity(), self.sim.getRand()]
+        out = [None] * self.world if self.rank == 0 else None
+        dist.gather_object(parts, out, dst=0)
+        if self.rank != 0:
+            return None
+        cat = [np.concatenate([o[k] for o in out]) for k in range(4)]
+        order = np.argsort(cat[0], kind="stable")
+        return tuple(c[order] for c in cat)
+
+    def gather_field(self, name):
+        """Owned rows of a cell field from every rank, assembled in global row order on rank 0."""
+        a = self.sim.getField(name)
+        row0 = max(0, self.bounds[self.rank] - int(self.sim.spec["halo_rows"]))
+        lo = (self.bounds[self.rank] - row0) * self.nr
+        hi = (self.bounds[self.rank + 1] - row0) * self.nr
+        out = [None] * self.world if self.rank == 0 else None
+        dist.gather_object(a[lo:hi], out, dst=0)
+        return np.concatenate(out) if self.rank == 0 else None

@@ -91,7 +91,7 @@ int fsim_set_source_pdf(fsim_sim *sim, const double *pdf, int64_t n0, int64_t n1
 int fsim_set_rand(fsim_sim *sim, const double *rnd);            /* [N][4] in [0,1]            */
 int fsim_set_entropy(fsim_sim *sim, const double *entropy);     /* [1024*1024][4] in [0,1]    */
 int fsim_set_inv_cdf(fsim_sim *sim, const double *table);       /* [512*512][2], texel i+j*512 */
-int fsim_set_particle_count(fsim_sim *sim, int64_t n);          /* multi-GPU: live count <= capacity */
+int fsim_set_particle_count(fsim_sim *sim, int64_t n);          /* multi-GPU: live count <= capacity; ids := id_base + slot */
 int fsim_set_ids(fsim_sim *sim, const uint64_t *ids);           /* multi-GPU: global particle ids */
 
 /* ---- static field builders, blended ONE,ONE into B ---------------------------------------- */
