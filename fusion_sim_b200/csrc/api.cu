@@ -560,6 +560,7 @@ int fsim_set_position(fsim_sim *s, const double *pos)
     FSIM_TRY(check(s));
     s->binned = false;
     s->keys_valid = false;
+    s->have_leavers = false;
     return finish(s, particles_in3(s, pos, AX, s->factor_r, s->factor_r, s->factor_z, true));
 }
 int fsim_set_velocity(fsim_sim *s, const double *vel)
@@ -620,6 +621,7 @@ int fsim_set_particle_count(fsim_sim *s, int64_t n)
     s->n = n;
     s->binned = false;
     s->keys_valid = false;
+    s->have_leavers = false;
     // slots get fresh ids id_base + slot (a re-initialisation; fsim_set_ids may override)
     if (n) {
         iota_ids_kernel<double><<<grid_for(n, 256), 256, 0, s->stream>>>(s->pid[s->cur], n, s->id_base);
@@ -708,7 +710,7 @@ int fsim_step(fsim_sim *s)
     // emits the deposit prepass (sort key, sprite colour, histogram) of the new state for the
     // density() that follows.
     // Both are done in ONE sweep over the particle storage (push.cu, NH = 2).
-    FSIM_TRY(finish(s, launch_push(s, !s->slab, 2)));
+    FSIM_TRY(finish(s, launch_push(s, true, 2)));
     s->steps_since_sort++;
     if (s->steps_since_sort >= 4 * sort_interval(s))  // push-only loops: keep the gather coherent
         FSIM_TRY(finish(s, physical_sort(s)));

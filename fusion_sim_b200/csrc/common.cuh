@@ -119,6 +119,7 @@ struct fsim_sim {
     uint32_t *mscratch = nullptr;  // small counters of the migration kernels
     uint8_t *hole_flag = nullptr;  // [cap] 1 = slot vacated by a leaver
     uint32_t nholes_host = 0;
+    bool have_leavers = false;     // perm[0..*nleavers) lists the slots whose row left the slab (emitted by the push)
 
     // measurement
     bool timing = false;

@@ -33,14 +33,26 @@ __device__ __forceinline__ int dest_rank(const RankBounds &rb, Real z, int nz)
     return d;
 }
 
+// fallback when the push did not emit the list: scan all particles for rows that are not owned
 template <typename Real>
 __global__ void __launch_bounds__(256)
-migrate_count_kernel(const Real *__restrict__ z, int64_t n, int nz, RankBounds rb, uint32_t *__restrict__ counts)
+find_leavers_kernel(const Real *__restrict__ z, int64_t n, int nz, int own0, int own_rows,
+                    uint32_t *__restrict__ list, uint32_t *__restrict__ nlist)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const int d = dest_rank(rb, z[p], nz);
-    if (d != rb.self) atomicAdd(counts + d, 1u);
+    const int gj = tex_idx(z[p], nz);
+    if (gj < own0 || gj >= own0 + own_rows) list[atomicAdd(nlist, 1u)] = (uint32_t)p;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256)
+migrate_count_kernel(const Real *__restrict__ z, const uint32_t *__restrict__ list, uint32_t nlist, int nz,
+                     RankBounds rb, uint32_t *__restrict__ counts)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlist) return;
+    atomicAdd(counts + dest_rank(rb, z[list[t]], nz), 1u);
 }
 
 template <typename Real>
@@ -49,11 +61,12 @@ struct PackArgs {
     const uint8_t *alive;
     const uint32_t *id;
     unsigned char *buf;
-    uint32_t *cursor;   // [nranks] running offsets (records) into buf, initialised to the group starts
-    uint32_t *holes;    // slots vacated
-    uint32_t *nholes;
+    uint32_t *cursor;        // [nranks] running offsets (records) into buf, initialised to the group starts
+    const uint32_t *list;    // slots that leave (they become the holes)
+    uint32_t nlist;
     uint8_t *hole_flag;
-    int64_t n;
+    const uint32_t *key;     // non-null: keep the sort histogram consistent
+    uint32_t *counts;
     int nz;
     RankBounds rb;
 };
@@ -61,20 +74,20 @@ struct PackArgs {
 template <typename Real>
 __global__ void __launch_bounds__(256) migrate_pack_kernel(const PackArgs<Real> a)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nlist) return;
+    const size_t p = a.list[t];
     const int d = dest_rank(a.rb, a.src[AZ][p], a.nz);
-    if (d == a.rb.self) return;
     const uint32_t slot = atomicAdd(a.cursor + d, 1u);
     unsigned char *rec = a.buf + (size_t)slot * (NPART_ARRAYS * sizeof(Real) + 8);
     Real *r = reinterpret_cast<Real *>(rec);
 #pragma unroll
     for (int k = 0; k < NPART_ARRAYS; ++k) r[k] = a.src[k][p];
-    uint32_t *t = reinterpret_cast<uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
-    t[0] = a.id[p];
-    t[1] = a.alive[p];
-    a.holes[atomicAdd(a.nholes, 1u)] = (uint32_t)p;
+    uint32_t *u = reinterpret_cast<uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
+    u[0] = a.id[p];
+    u[1] = a.alive[p];
     a.hole_flag[p] = 1;
+    if (a.key) atomicSub(a.counts + (a.key[p] & KEY_MASK), 1u);
 }
 
 template <typename Real>
@@ -88,6 +101,10 @@ struct UnpackArgs {
     uint32_t nholes;
     int64_t n_old;
     int64_t nrecv;
+    // non-null key: arrivals get their deposit prepass here (key, colour, histogram)
+    uint32_t *key, *counts;
+    Real *dcol[3];
+    int nr, nz, row0, rows, own_lo, own_hi;
 };
 
 // arrival i goes into hole i while holes last, then to the end of the storage
@@ -105,11 +122,24 @@ __global__ void __launch_bounds__(256) migrate_unpack_kernel(const UnpackArgs<Re
     }
     const unsigned char *rec = a.buf + (size_t)i * (NPART_ARRAYS * sizeof(Real) + 8);
     const Real *r = reinterpret_cast<const Real *>(rec);
+    Real v[NPART_ARRAYS];
 #pragma unroll
-    for (int k = 0; k < NPART_ARRAYS; ++k) a.dst[k][slot] = r[k];
-    const uint32_t *t = reinterpret_cast<const uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
-    a.id[slot] = t[0];
-    a.alive[slot] = (uint8_t)t[1];
+    for (int k = 0; k < NPART_ARRAYS; ++k) {
+        v[k] = r[k];
+        a.dst[k][slot] = v[k];
+    }
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
+    a.id[slot] = u[0];
+    a.alive[slot] = (uint8_t)u[1];
+    if (a.key) {
+        const Real rr = fsqrt(v[AX] * v[AX] + v[AY] * v[AY]);
+        Real c0, c1, c2;
+        const uint32_t key = sprite_key_colour<Real>(v[AX], v[AY], v[AZ], rr, v[AVX], v[AVY], v[AVZ], a.nr, a.nz,
+                                                     a.row0, a.rows, a.own_lo, a.own_hi, c0, c1, c2);
+        a.key[slot] = key;
+        a.dcol[0][slot] = c0; a.dcol[1][slot] = c1; a.dcol[2][slot] = c2;
+        atomicAdd(a.counts + (key & KEY_MASK), 1u);
+    }
 }
 
 // more leavers than arrivals: the storage shrinks to n_new; live particles in the tail
@@ -137,6 +167,8 @@ struct MoveArgs {
     uint32_t *id;
     const uint32_t *targets, *sources;
     const uint32_t *ntargets;
+    uint32_t *key;  // non-null: the per-slot prepass data moves along
+    Real *dcol[3];
 };
 
 template <typename Real>
@@ -149,6 +181,11 @@ __global__ void __launch_bounds__(256) compact_move_kernel(const MoveArgs<Real> 
     for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k][d] = m.a[k][s];
     m.alive[d] = m.alive[s];
     m.id[d] = m.id[s];
+    if (m.key) {
+        m.key[d] = m.key[s];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) m.dcol[q][d] = m.dcol[q][s];
+    }
 }
 
 static int ensure_migr(fsim_sim *s, size_t bytes)
@@ -182,60 +219,79 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
         set_error("fsim_migrate_pack: bad rank arguments");
         return FSIM_ERR_INVALID;
     }
+    if (row_bounds[self] != s->own0 || row_bounds[self + 1] != s->own0 + s->own_rows) {
+        set_error("fsim_migrate_pack: row_bounds[self] does not match the slab of this handle");
+        return FSIM_ERR_INVALID;
+    }
     FSIM_CUDA(cudaSetDevice(s->device));
     RankBounds rb;
     rb.n = nranks;
     rb.self = self;
     for (int k = 0; k <= nranks; ++k) rb.lo[k] = (int)row_bounds[k];
-    // scratch: counts[nranks] | cursor[nranks] | nholes | ntargets | nsources
+    // scratch: counts[MAX_RANKS] | cursor[MAX_RANKS] | nleavers | ntargets | nsources
     uint32_t *scr = s->mscratch;
-    FSIM_CUDA(cudaMemsetAsync(scr, 0, sizeof(uint32_t) * (2 * MAX_RANKS + 4), s->stream));
-    uint32_t hc[MAX_RANKS] = {};
-    if (s->n) {
-        int rc = dispatch(s, [&](auto tag) {
-            using Real = decltype(tag);
-            migrate_count_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
-                (const Real *)s->part[s->cur][AZ], s->n, s->nz, rb, scr);
-            FSIM_CUDA(cudaGetLastError());
-            s->launches++;
-            return (int)FSIM_OK;
-        });
-        FSIM_TRY(rc);
-        FSIM_CUDA(cudaMemcpyAsync(hc, scr, sizeof(uint32_t) * nranks, cudaMemcpyDeviceToHost, s->stream));
-        FSIM_CUDA(cudaStreamSynchronize(s->stream));
-    }
-    uint32_t off[MAX_RANKS] = {};
-    int64_t total = 0;
-    for (int k = 0; k < nranks; ++k) {
-        send_counts[k] = hc[k];
-        off[k] = (uint32_t)total;
-        total += hc[k];
-    }
-    const size_t rb_bytes = NPART_ARRAYS * s->rs + 8;
-    FSIM_TRY(ensure_migr(s, (size_t)total * rb_bytes + 16));
-    // hole list lives in perm[] (free between a density() and the next binning)
-    s->nholes_host = (uint32_t)total;
+    uint32_t *nlist_d = scr + 2 * MAX_RANKS;
+    FSIM_CUDA(cudaMemsetAsync(scr, 0, sizeof(uint32_t) * 2 * MAX_RANKS, s->stream));
+    FSIM_CUDA(cudaMemsetAsync(scr + 2 * MAX_RANKS + 1, 0, sizeof(uint32_t) * 2, s->stream));
+    for (int k = 0; k < nranks; ++k) send_counts[k] = 0;
+    *send_buf_dev = nullptr;
+    s->nholes_host = 0;
     s->binned = false;
-    s->keys_valid = false;
-    *send_buf_dev = s->migr;
-    if (total == 0) return FSIM_OK;
-    FSIM_CUDA(cudaMemcpyAsync(scr + MAX_RANKS, off, sizeof(uint32_t) * nranks, cudaMemcpyHostToDevice, s->stream));
+    if (s->n == 0) return FSIM_OK;
+    const bool keys = s->keys_valid;
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
+        const int c = s->cur;
+        if (!s->have_leavers) {  // the push did not emit the list: scan the positions
+            FSIM_CUDA(cudaMemsetAsync(nlist_d, 0, sizeof(uint32_t), s->stream));
+            find_leavers_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+                (const Real *)s->part[c][AZ], s->n, s->nz, s->own0, s->own_rows, s->perm, nlist_d);
+            FSIM_CUDA(cudaGetLastError());
+            s->launches++;
+        }
+        s->have_leavers = false;
+        uint32_t nlist = 0;
+        FSIM_CUDA(cudaMemcpyAsync(&nlist, nlist_d, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        FSIM_CUDA(cudaStreamSynchronize(s->stream));
+        if (nlist == 0) return (int)FSIM_OK;
+        if ((int64_t)nlist > s->cap / 2) {
+            set_error("fsim_migrate_pack: more than half of the particle slots leave the slab at once");
+            return (int)FSIM_ERR_RANGE;
+        }
+        migrate_count_kernel<Real><<<grid_for(nlist, 256), 256, 0, s->stream>>>(
+            (const Real *)s->part[c][AZ], s->perm, nlist, s->nz, rb, scr);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        uint32_t hc[MAX_RANKS] = {}, off[MAX_RANKS] = {};
+        FSIM_CUDA(cudaMemcpyAsync(hc, scr, sizeof(uint32_t) * nranks, cudaMemcpyDeviceToHost, s->stream));
+        FSIM_CUDA(cudaStreamSynchronize(s->stream));
+        int64_t total = 0;
+        for (int k = 0; k < nranks; ++k) {
+            send_counts[k] = hc[k];
+            off[k] = (uint32_t)total;
+            total += hc[k];
+        }
+        FSIM_TRY(ensure_migr(s, (size_t)total * (NPART_ARRAYS * sizeof(Real) + 8) + 16));
+        FSIM_CUDA(cudaMemcpyAsync(scr + MAX_RANKS, off, sizeof(uint32_t) * nranks, cudaMemcpyHostToDevice, s->stream));
         PackArgs<Real> a;
-        for (int k = 0; k < NPART_ARRAYS; ++k) a.src[k] = (const Real *)s->part[s->cur][k];
-        a.alive = s->alive[s->cur];
-        a.id = s->pid[s->cur];
+        for (int k = 0; k < NPART_ARRAYS; ++k) a.src[k] = (const Real *)s->part[c][k];
+        a.alive = s->alive[c];
+        a.id = s->pid[c];
         a.buf = (unsigned char *)s->migr;
         a.cursor = scr + MAX_RANKS;
-        a.holes = s->perm;
-        a.nholes = scr + 2 * MAX_RANKS;
+        a.list = s->perm; a.nlist = nlist;
         a.hole_flag = s->hole_flag;
-        a.n = s->n; a.nz = s->nz; a.rb = rb;
-        Bracket b(s, "migrate_pack");
-        migrate_pack_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
-        FSIM_CUDA(cudaGetLastError());
+        a.key = keys ? s->key : nullptr;
+        a.counts = s->counts;
+        a.nz = s->nz; a.rb = rb;
+        {
+            Bracket b(s, "migrate_pack");
+            migrate_pack_kernel<Real><<<grid_for(nlist, 256), 256, 0, s->stream>>>(a);
+            FSIM_CUDA(cudaGetLastError());
+        }
         FSIM_CUDA(cudaStreamSynchronize(s->stream));
+        s->nholes_host = nlist;
+        *send_buf_dev = s->migr;
         return (int)FSIM_OK;
     });
 }
@@ -265,13 +321,19 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
             a.buf = (const unsigned char *)recv_buf_dev;
             a.holes = s->perm; a.hole_flag = s->hole_flag;
             a.nholes = (uint32_t)nholes; a.n_old = n_old; a.nrecv = nrecv;
+            a.key = s->keys_valid ? s->key : nullptr;
+            a.counts = s->counts;
+            for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
+            a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
+            a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
             Bracket b(s, "migrate_unpack");
             migrate_unpack_kernel<Real><<<grid_for(nrecv, 256), 256, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());
         }
         if (nholes > nrecv) {  // shrink: move tail particles into the remaining holes
             const int64_t span = std::max<int64_t>(nholes - nrecv, n_old - n_new);
-            uint32_t *targets = (uint32_t *)s->key, *sources = (uint32_t *)s->key + (s->cap / 2);
+            // target/source lists: the tail of perm[] beyond the hole list (both are tiny)
+            uint32_t *targets = s->perm + s->cap / 2, *sources = s->perm + s->cap / 2 + s->cap / 4;
             compact_lists_kernel<<<grid_for(span, 256), 256, 0, s->stream>>>(
                 s->perm, (uint32_t)nholes, (uint32_t)nrecv, s->hole_flag, n_new, n_old, targets,
                 scr + 2 * MAX_RANKS + 1, sources, scr + 2 * MAX_RANKS + 2);
@@ -279,6 +341,8 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
             for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k] = (Real *)s->part[c][k];
             m.alive = s->alive[c]; m.id = s->pid[c];
             m.targets = targets; m.sources = sources; m.ntargets = scr + 2 * MAX_RANKS + 1;
+            m.key = s->keys_valid ? s->key : nullptr;
+            for (int q = 0; q < 3; ++q) m.dcol[q] = (Real *)s->dcol[q];
             compact_move_kernel<Real><<<grid_for(nholes - nrecv, 256), 256, 0, s->stream>>>(m);
             FSIM_CUDA(cudaGetLastError());
             s->launches += 2;
@@ -291,8 +355,7 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
     s->n = n_new;
     s->nholes_host = 0;
     s->ids_identity = false;
-    s->binned = false;
-    s->keys_valid = false;
+    s->binned = false;  // keys_valid is kept: the kernels above maintained key[], dcol[] and counts[]
     return FSIM_OK;
 }
 

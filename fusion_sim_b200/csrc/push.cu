@@ -30,6 +30,8 @@ struct PushArgs {
     Real *dcol[3];
     uint32_t *counts;
     uint32_t *oob;
+    uint32_t *leavers, *nleavers;  // slab mode: slots whose new row is not owned (migration list)
+    int own0, own_rows;
     int64_t n;
     int nr, nz, row0, rows, own_lo, own_hi;
     Real sf;
@@ -234,6 +236,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
             const bool valid = p0 + k < a.n;
             const uint32_t c = valid ? (newcell[k] & KEY_MASK) : 0xffffffffu;
             if (valid) a.key[p0 + k] = newcell[k];
+            if (valid && a.leavers) {
+                const int gj = tex_idx(z[k], a.nz);
+                if (gj < a.own0 || gj >= a.own0 + a.own_rows) a.leavers[atomicAdd(a.nleavers, 1u)] = (uint32_t)(p0 + k);
+            }
             const unsigned peers = __match_any_sync(0xffffffffu, c);
             if (valid && (__ffs(peers) - 1) == lane) atomicAdd(a.counts + c, (uint32_t)__popc(peers));
         }
@@ -254,6 +260,9 @@ static int push_impl(fsim_sim *s, bool with_hist, int nhalf)
     for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
     a.counts = s->counts;
     a.oob = s->oob;
+    a.leavers = (with_hist && s->slab) ? s->perm : nullptr;
+    a.nleavers = s->mscratch + 2 * 64;
+    a.own0 = s->own0; a.own_rows = s->own_rows;
     a.n = s->n;
     a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
     a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
@@ -283,6 +292,7 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf)
         FSIM_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (s->ncell_local + 1), s->stream));
         s->counts_dirty = false;
     }
+    if (with_hist && s->slab) FSIM_CUDA(cudaMemsetAsync(s->mscratch + 2 * 64, 0, sizeof(uint32_t), s->stream));
     int rc = dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
         constexpr int V = 16 / sizeof(Real);  // 128-bit loads and stores
@@ -298,6 +308,7 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf)
     });
     s->binned = false;
     s->keys_valid = with_hist;
+    s->have_leavers = with_hist && s->slab;
     if (with_hist) s->counts_dirty = true;
     return rc;
 }

@@ -270,6 +270,7 @@ int launch_apply_perm(fsim_sim *s)
     }
     s->binned = false;
     s->keys_valid = false;
+    s->have_leavers = false;
     s->ever_sorted = true;
     s->ids_identity = false;
     s->steps_since_sort = 0;
