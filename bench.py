@@ -305,6 +305,7 @@ def run_ours(args):
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_kind": peak_kind + " HBM copy bandwidth",
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": push_ms, "traffic": traffic,
+                "achieved_per_push_formula": halves * alg / (push_ms * 1e-3) / 1e9,
                 "frac_of_nominal_8000": achieved / 8000.0, "kernels_ms_per_step": kern}
 
     # ---- end to end through the public host API with host buffers ----

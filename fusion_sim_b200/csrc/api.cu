@@ -727,7 +727,10 @@ int fsim_density_begin(fsim_sim *s)
 {
     FSIM_TRY(check(s));
     FSIM_TRY(finish(s, bin_particles(s)));
-    FSIM_TRY(finish(s, launch_cellsum(s)));
+    if (s->spec.flags & FSIM_FLAG_ATOMIC_DEPOSIT)
+        FSIM_TRY(finish(s, launch_cellsum_atomic(s)));  // measured alternative, not bit-reproducible
+    else
+        FSIM_TRY(finish(s, launch_cellsum(s)));
     // the deposit is done with the index list; now, every sort_interval frames, put the storage
     // itself into cell order for the pushes that follow
     if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) FSIM_TRY(finish(s, launch_apply_perm(s)));

@@ -222,6 +222,7 @@ int launch_keys(fsim_sim *s);      // deposit prepass from the stored state: key
 int launch_bin(fsim_sim *s);       // scan + index scatter -> starts[], perm[]
 int launch_apply_perm(fsim_sim *s);  // physical re-sort: storage <- storage[perm]
 int launch_cellsum(fsim_sim *s);
+int launch_cellsum_atomic(fsim_sim *s);
 int launch_conv(fsim_sim *s);
 int launch_precalc(fsim_sim *s);
 int launch_add_loop(fsim_sim *s, double R, double Z, double I);

@@ -189,6 +189,42 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
   }
 }
 
+// Measured alternative (FSIM_FLAG_ATOMIC_DEPOSIT): particle-parallel global atomics on the per-cell
+// sums.  No sort needed, but the floating-point sum order is the arrival order of the atomics, so
+// the result is NOT bit-reproducible; the id-ordered path above is the default.
+template <typename Real>
+__global__ void __launch_bounds__(256)
+cellsum_atomic_kernel(const uint32_t *__restrict__ key, const Real *__restrict__ c0, const Real *__restrict__ c1,
+                      const Real *__restrict__ c2, int64_t n, Real *__restrict__ S, uint32_t *__restrict__ count)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t k = key[p];
+    if (k & KEY_CLIPPED) return;
+    Real *o = S + 4 * (size_t)k;
+    atomicAdd(o + 0, c0[p]);
+    atomicAdd(o + 1, c1[p]);
+    atomicAdd(o + 2, c2[p]);
+    atomicAdd(o + 3, (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0);
+    atomicAdd(count + k, 1u);
+}
+
+int launch_cellsum_atomic(fsim_sim *s)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        FSIM_CUDA(cudaMemsetAsync(s->cellsum, 0, sizeof(Real) * 4 * s->ncell_local, s->stream));
+        FSIM_CUDA(cudaMemsetAsync(s->cellcount, 0, sizeof(uint32_t) * s->ncell_local, s->stream));
+        if (s->n == 0) return (int)FSIM_OK;
+        Bracket b(s, "cellsum_atomic");
+        cellsum_atomic_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+            s->key, (const Real *)s->dcol[0], (const Real *)s->dcol[1], (const Real *)s->dcol[2], s->n,
+            (Real *)s->cellsum, s->cellcount);
+        FSIM_CUDA(cudaGetLastError());
+        return (int)FSIM_OK;
+    });
+}
+
 int launch_cellsum(fsim_sim *s)
 {
     return dispatch(s, [&](auto tag) {

@@ -122,6 +122,22 @@ def test_crowded_cells(precision):
         compare_grid(g, o, ["cell_sums", "moments01_avg"], f"crowded frame {frame}")
 
 
+def test_atomic_deposit_alternative_within_tolerance():
+    """FSIM_FLAG_ATOMIC_DEPOSIT: same terms, arrival-order sums -> 1e-12 relative, counts exact."""
+    sc = small_scene(n=20000, speed=0.02, blob=(0.5, 0.8))
+    sc["spec"]["flags"] = 4
+    g, o = make_pair(sc)
+    g.step(); o.step()
+    g.density(); o.density()
+    assert_same(g.getField("cell_count"), o.getField("cell_count"), "counts")
+    a, b = g.getField("cell_sums"), o.getField("cell_sums")
+    scale = np.abs(b).max()
+    assert np.nanmax(np.abs(a - b)) <= 1e-12 * scale
+    m, n = g.getField("moments01_avg"), o.getField("moments01_avg")
+    ok = ~np.isnan(n)
+    assert np.abs(m[ok] - n[ok]).max() <= 1e-12 * np.abs(n[ok]).max()
+
+
 def test_sort_is_invisible():
     sc = small_scene(n=5000, speed=0.05, blob=(0.5, 0.8))
     g, o = make_pair(sc)
