@@ -63,11 +63,15 @@ __device__ __forceinline__ void st_stream(Real *p, const Real (&o)[V])
 }
 
 // 4 reals of one entropy texel / 12 reals of one cell record through the read-only path
+// 256-bit read-only load (sm_100: LDG.E.256): one request, and for a gather one L1 wavefront per
+// lane, where two 128-bit loads take two.  p must be 32-byte aligned.
+__device__ __forceinline__ void ld_ro256(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 __device__ __forceinline__ void ld_ro4(const double *p, double (&o)[4])
 {
-    double2 a = __ldg(reinterpret_cast<const double2 *>(p));
-    double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    ld_ro256(p, o[0], o[1], o[2], o[3]);
 }
 __device__ __forceinline__ void ld_ro4(const float *p, float (&o)[4])
 {
@@ -77,10 +81,7 @@ __device__ __forceinline__ void ld_ro4(const float *p, float (&o)[4])
 __device__ __forceinline__ void ld_ro12(const double *p, double (&o)[12])
 {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        double2 a = __ldg(reinterpret_cast<const double2 *>(p) + k);
-        o[2 * k] = a.x; o[2 * k + 1] = a.y;
-    }
+    for (int k = 0; k < 3; ++k) ld_ro256(p + 4 * k, o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
 }
 __device__ __forceinline__ void ld_ro12(const float *p, float (&o)[12])
 {
