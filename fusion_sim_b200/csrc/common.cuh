@@ -214,6 +214,21 @@ __device__ __forceinline__ uint32_t sprite_key_colour(Real x, Real y, Real z, Re
     return key;
 }
 
+// Warp-level aggregation over RUNS of equal keys in consecutive lanes (the storage is nearly in cell
+// order, so equal keys sit next to each other).  Returns the lane that leads this lane's run, the
+// run length and this lane's rank in it -- from one shuffle and one ballot, no MATCH.ANY.
+// Equal keys in non-adjacent lanes simply form separate runs (one atomic each): still correct.
+__device__ __forceinline__ void warp_runs(uint32_t key, int lane, int &leader, uint32_t &len, uint32_t &rank)
+{
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    leader = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+    const unsigned after = heads & ~(0xffffffffu >> (31 - lane));  // heads strictly above this lane
+    const int next = after ? (__ffs((int)after) - 1) : 32;
+    len = (uint32_t)(next - leader);
+    rank = (uint32_t)(lane - leader);
+}
+
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // kernels / host stages implemented in the other translation units

@@ -241,8 +241,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
                 const int gj = tex_idx(z[k], a.nz);
                 if (gj < a.own0 || gj >= a.own0 + a.own_rows) a.leavers[atomicAdd(a.nleavers, 1u)] = (uint32_t)(p0 + k);
             }
-            const unsigned peers = __match_any_sync(0xffffffffu, c);
-            if (valid && (__ffs(peers) - 1) == lane) atomicAdd(a.counts + c, (uint32_t)__popc(peers));
+            int leader;
+            uint32_t len, rank;
+            warp_runs(c, lane, leader, len, rank);
+            if (valid && rank == 0) atomicAdd(a.counts + c, len);
         }
     }
 }

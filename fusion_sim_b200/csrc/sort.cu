@@ -44,10 +44,11 @@ __global__ void __launch_bounds__(256) prepass_kernel(const PrepassArgs<Real> a)
         a.dcol[0][p] = c0; a.dcol[1][p] = c1; a.dcol[2][p] = c2;
         c = key & KEY_MASK;
     }
-    // warp-aggregated histogram: sorted input puts a handful of distinct cells in a warp
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    if (valid && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-        atomicAdd(a.counts + c, (uint32_t)__popc(peers));
+    // warp-aggregated histogram: one atomic per run of equal keys
+    int leader;
+    uint32_t len, rank;
+    warp_runs(c, (int)(threadIdx.x & 31), leader, len, rank);
+    if (valid && rank == 0) atomicAdd(a.counts + c, len);
 }
 
 // ---- exclusive scan over ncell counts: per-block sums, scan of block sums, final pass ----
@@ -83,14 +84,28 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
     return base + inc - v;
 }
 
+// 8 consecutive counts per thread as two 128-bit loads (the arrays are padded to a multiple of 8)
+__device__ __forceinline__ void load8(const uint32_t *p, int64_t base, int64_t m, uint32_t (&v)[SCAN_ITEMS])
+{
+    if (base + SCAN_ITEMS <= m) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(p + base);
+        const uint4 b = *reinterpret_cast<const uint4 *>(p + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < m) ? p[base + k] : 0u;
+    }
+}
+
 __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_tile_sums_kernel(const uint32_t *__restrict__ counts, int64_t m, uint32_t *__restrict__ tile_sums)
 {
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    load8(counts, base, m, v);
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k)
-        if (base + k < m) s += counts[base + k];
+    for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
     uint32_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
@@ -124,23 +139,36 @@ scan_final_kernel(uint32_t *__restrict__ counts, int64_t m, const uint32_t *__re
 {
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
+    load8(counts, base, m, v);
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (base + k < m) ? counts[base + k] : 0;
-        s += v[k];
-    }
+    for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
     uint32_t run = tile_offsets[blockIdx.x] + block_exclusive_scan(s, nullptr);
+    uint32_t o[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < m) {
-            starts[base + k] = run;
-            cursor[base + k] = run;
-            counts[base + k] = 0;
-        }
+        o[k] = run;
         run += v[k];
-        if (base + k == m - 1) starts[m] = run;
     }
+    if (base + SCAN_ITEMS <= m) {
+        const uint4 a = make_uint4(o[0], o[1], o[2], o[3]), b = make_uint4(o[4], o[5], o[6], o[7]);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(starts + base) = a;
+        *reinterpret_cast<uint4 *>(starts + base + 4) = b;
+        *reinterpret_cast<uint4 *>(cursor + base) = a;
+        *reinterpret_cast<uint4 *>(cursor + base + 4) = b;
+        *reinterpret_cast<uint4 *>(counts + base) = z;
+        *reinterpret_cast<uint4 *>(counts + base + 4) = z;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (base + k < m) {
+                starts[base + k] = o[k];
+                cursor[base + k] = o[k];
+                counts[base + k] = 0;
+            }
+    }
+    if (base <= m - 1 && m - 1 < base + SCAN_ITEMS) starts[m] = run;  // total (run after the last item)
 }
 
 // physical re-sort: dst[j] = src[perm[j]] -- gathered reads (the storage is nearly ordered, so
@@ -174,23 +202,39 @@ __global__ void __launch_bounds__(256) apply_perm_kernel(const PermuteArgs<Real>
     a.id_dst[j] = id;
 }
 
-// index sort: perm[slot in cell order] = storage slot; nothing but 4 bytes per particle moves
+// index sort: perm[slot in cell order] = storage slot; nothing but 4 bytes per particle moves.
+// One cursor atomic per run of equal keys in a warp; the lanes of a run take consecutive slots.
+constexpr int IDX_ITEMS = 4;  // 32-particle chunks per warp: their atomics' round trips overlap
+
 __global__ void __launch_bounds__(256)
 index_scatter_kernel(const uint32_t *__restrict__ key, uint32_t *__restrict__ cursor,
                      uint32_t *__restrict__ perm, int64_t n)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < n;
-    const uint32_t c = valid ? (key[p] & KEY_MASK) : 0xffffffffu;
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (valid && lane == leader) base = atomicAdd(cursor + c, (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) perm[(size_t)base + (size_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)p;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t p0 = warp * (32 * IDX_ITEMS) + lane;
+    uint32_t c[IDX_ITEMS], base[IDX_ITEMS], rank[IDX_ITEMS];
+    int leader[IDX_ITEMS];
+#pragma unroll
+    for (int k = 0; k < IDX_ITEMS; ++k) {
+        const int64_t p = p0 + 32 * k;
+        c[k] = (p < n) ? (key[p] & KEY_MASK) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < IDX_ITEMS; ++k) {
+        uint32_t len;
+        warp_runs(c[k], lane, leader[k], len, rank[k]);
+        base[k] = 0;
+        if (c[k] != 0xffffffffu && rank[k] == 0) base[k] = atomicAdd(cursor + c[k], len);
+    }
+#pragma unroll
+    for (int k = 0; k < IDX_ITEMS; ++k) {
+        const uint32_t b = __shfl_sync(0xffffffffu, base[k], leader[k]);
+        if (c[k] != 0xffffffffu) perm[(size_t)b + rank[k]] = (uint32_t)(p0 + 32 * k);
+    }
 }
 
+// key[] + colour + histogram from the stored state
 int launch_keys(fsim_sim *s)
 {
     if (s->counts_dirty) {
@@ -237,7 +281,8 @@ int launch_bin(fsim_sim *s)
     s->counts_dirty = false;  // scan_final zeroed counts[]
     if (s->n) {
         Bracket b(s, "index_scatter");
-        index_scatter_kernel<<<grid_for(s->n, 256), 256, 0, s->stream>>>(s->key, s->cursor, s->perm, s->n);
+        index_scatter_kernel<<<grid_for((s->n + IDX_ITEMS - 1) / IDX_ITEMS, 256), 256, 0, s->stream>>>(s->key, s->cursor,
+                                                                                                      s->perm, s->n);
         FSIM_CUDA(cudaGetLastError());
     }
     s->binned = true;
