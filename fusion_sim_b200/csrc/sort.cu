@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) apply_perm_kernel(const PermuteArgs<Real>
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.n) return;
-    const size_t p = a.perm[j];
+    const size_t p = a.perm[j] & KEY_MASK;
     Real v[NPART_ARRAYS];
 #pragma unroll
     for (int k = 0; k < NPART_ARRAYS; ++k) v[k] = a.src[k][p];
@@ -215,10 +215,13 @@ index_scatter_kernel(const uint32_t *__restrict__ key, uint32_t *__restrict__ cu
     const int64_t p0 = warp * (32 * IDX_ITEMS) + lane;
     uint32_t c[IDX_ITEMS], base[IDX_ITEMS], rank[IDX_ITEMS];
     int leader[IDX_ITEMS];
+    uint32_t flag[IDX_ITEMS];  // the clipped bit travels in bit 31 of the perm entry
 #pragma unroll
     for (int k = 0; k < IDX_ITEMS; ++k) {
         const int64_t p = p0 + 32 * k;
-        c[k] = (p < n) ? (key[p] & KEY_MASK) : 0xffffffffu;
+        const uint32_t kk = (p < n) ? key[p] : 0xffffffffu;
+        c[k] = (p < n) ? (kk & KEY_MASK) : 0xffffffffu;
+        flag[k] = kk & KEY_CLIPPED;
     }
 #pragma unroll
     for (int k = 0; k < IDX_ITEMS; ++k) {
@@ -230,7 +233,7 @@ index_scatter_kernel(const uint32_t *__restrict__ key, uint32_t *__restrict__ cu
 #pragma unroll
     for (int k = 0; k < IDX_ITEMS; ++k) {
         const uint32_t b = __shfl_sync(0xffffffffu, base[k], leader[k]);
-        if (c[k] != 0xffffffffu) perm[(size_t)b + rank[k]] = (uint32_t)(p0 + 32 * k);
+        if (c[k] != 0xffffffffu) perm[(size_t)b + rank[k]] = (uint32_t)(p0 + 32 * k) | flag[k];
     }
 }
 

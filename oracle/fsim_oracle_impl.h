@@ -370,11 +370,13 @@ void ORC(orc_cell_sums_mt)(int64_t n, const REAL *pos, const REAL *vel, int64_t 
     }
 }
 
-/* CANONICAL form, step 2: moments01 = S (*) shape, gather form of the sprite
- * scatter: pixel (i,j) receives S[i-ti+5, j-tj+5] * shape[ti,tj]; sources
- * outside the grid do not exist (sprites are clipped at the target edge).
- * Taps are visited tj-major, ti-minor; taps whose weight is exactly 0 (the 40
- * corner texels with d > 5) are skipped.                                     */
+/* CANONICAL form, step 2: moments01 = S (*) shape, gather form of the sprite scatter: pixel (i,j)
+ * receives S[i+di, j+dj] * shape[5+di, 5+dj] for every offset with a non-zero weight (the 40 corner
+ * texels with d > 5 are exactly 0 and are skipped); sources outside the grid do not exist (sprites
+ * are clipped at the target edge).  The footprint is mirror-symmetric, shape[5+di,5+dj] =
+ * shape[5-di,5+dj] = shape[5+di,5-dj] = shape[5-di,5-dj] bit for bit, so the (up to four) mirror
+ * sources of a weight are added first and weighted once.  Fixed order: dj = 0..5 outer, di = 0..5
+ * inner; inside a class (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj), duplicates (di or dj = 0) once. */
 void ORC(orc_convolve)(int64_t nr, int64_t nz, const REAL *S, const REAL *shape,
                        REAL *mom, int nthreads)
 {
@@ -383,18 +385,25 @@ void ORC(orc_convolve)(int64_t nr, int64_t nz, const REAL *S, const REAL *shape,
     for (j = 0; j < nz; ++j)
         for (int64_t i = 0; i < nr; ++i) {
             REAL acc[4] = {RC(0.0), RC(0.0), RC(0.0), RC(0.0)};
-            for (int tj = 0; tj < FSIM_NSHAPE; ++tj) {
-                int64_t sj = j - tj + FSIM_SHAPE_MID;
-                if (sj < 0 || sj >= nz) continue;
-                for (int ti = 0; ti < FSIM_NSHAPE; ++ti) {
-                    REAL w = shape[ti + FSIM_NSHAPE * tj];
-                    int64_t si = i - ti + FSIM_SHAPE_MID;
-                    if (w == RC(0.0) || si < 0 || si >= nr) continue;
-                    const REAL *s = S + 4 * (si + sj * nr);
-                    acc[0] = acc[0] + s[0] * w; acc[1] = acc[1] + s[1] * w;
-                    acc[2] = acc[2] + s[2] * w; acc[3] = acc[3] + s[3] * w;
+            for (int dj = 0; dj <= FSIM_SHAPE_MID; ++dj)
+                for (int di = 0; di <= FSIM_SHAPE_MID; ++di) {
+                    REAL w = shape[(FSIM_SHAPE_MID + di) + FSIM_NSHAPE * (FSIM_SHAPE_MID + dj)];
+                    if (w == RC(0.0)) continue;
+                    REAL sum[4] = {RC(0.0), RC(0.0), RC(0.0), RC(0.0)};
+                    for (int sj = -1; sj <= 1; sj += 2) {
+                        if (dj == 0 && sj > 0) continue;
+                        for (int si = -1; si <= 1; si += 2) {
+                            if (di == 0 && si > 0) continue;
+                            int64_t ii = i + si * di, jj = j + sj * dj;
+                            if (ii < 0 || ii >= nr || jj < 0 || jj >= nz) continue;
+                            const REAL *s = S + 4 * (ii + jj * nr);
+                            sum[0] = sum[0] + s[0]; sum[1] = sum[1] + s[1];
+                            sum[2] = sum[2] + s[2]; sum[3] = sum[3] + s[3];
+                        }
+                    }
+                    acc[0] = acc[0] + sum[0] * w; acc[1] = acc[1] + sum[1] * w;
+                    acc[2] = acc[2] + sum[2] * w; acc[3] = acc[3] + sum[3] * w;
                 }
-            }
             REAL *m = mom + 4 * (i + j * nr);
             m[0] = acc[0]; m[1] = acc[1]; m[2] = acc[2]; m[3] = acc[3];
         }

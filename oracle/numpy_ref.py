@@ -146,21 +146,31 @@ def cell_sums(pos, vel, nr, nz):
 
 
 def convolve(S, shape, nr, nz):
-    """moments01 = S (*) shape, gather form, taps tj-major / ti-minor, zero taps skipped."""
-    S2 = S.reshape(nz, nr, 4)
-    out = np.zeros_like(S2)
-    for tj in range(11):
-        for ti in range(11):
-            w = shape[ti + 11 * tj]
+    """moments01 = S (*) shape with the mirror sources of each weight added first (the footprint is
+    mirror-symmetric): classes dj = 0..5 outer, di = 0..5 inner; inside a class the sources
+    (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj); zero weights skipped; sources outside the grid are
+    absent (padding with exact zeros is the same arithmetic)."""
+    S2 = np.zeros((nz + 10, nr + 10, 4), S.dtype)
+    S2[5:5 + nz, 5:5 + nr] = S.reshape(nz, nr, 4)
+    out = np.zeros((nz, nr, 4), S.dtype)
+
+    def src(di, dj):
+        return S2[5 + dj:5 + dj + nz, 5 + di:5 + di + nr]
+
+    for dj in range(6):
+        for di in range(6):
+            w = shape[(5 + di) + 11 * (5 + dj)]
             if w == 0:
                 continue
-            # out[j, i] += S[j - tj + 5, i - ti + 5] * w where the source exists
-            dj, di = 5 - tj, 5 - ti
-            j0, j1 = max(0, -dj), min(nz, nz - dj)
-            i0, i1 = max(0, -di), min(nr, nr - di)
-            if j0 >= j1 or i0 >= i1:
-                continue
-            out[j0:j1, i0:i1] = out[j0:j1, i0:i1] + S2[j0 + dj:j1 + dj, i0 + di:i1 + di] * w
+            tot = np.zeros((nz, nr, 4), S.dtype)
+            for sj in (-1, 1):
+                if dj == 0 and sj > 0:
+                    continue
+                for si in (-1, 1):
+                    if di == 0 and si > 0:
+                        continue
+                    tot = tot + src(si * di, sj * dj)
+            out = out + tot * w
     return out.reshape(nr * nz, 4)
 
 
