@@ -342,7 +342,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_TRY(dalloc(&s->starts, s->ncell_local + 2));
     FSIM_TRY(dalloc(&s->cursor, s->ncell_local + 1));
     FSIM_TRY(dalloc(&s->blocksums, s->ncell_local / 2048 + 2));
-    FSIM_TRY(dalloc_bytes(&s->cellrec, s->rs * FSIM_CELLREC * s->ncell_local));
+    FSIM_TRY(dalloc_bytes(&s->cellrec, s->rs * RECSTRIDE * s->ncell_local));
     FSIM_TRY(dalloc_bytes(&s->E, s->rs * 3 * s->ncell_local));
     FSIM_TRY(dalloc_bytes(&s->B, s->rs * 3 * s->ncell_local));
     FSIM_TRY(dalloc(&s->sink, s->ncell_global));
@@ -858,7 +858,9 @@ int fsim_get_field(fsim_sim *s, const char *name, double *out)
     if (n == "B") return finish(s, table_out(s, s->B, out, 3 * nc));
     if (n == "R1" || n == "R2" || n == "R3" || n == "A") {
         std::vector<double> rec((size_t)(FSIM_CELLREC * nc));
-        FSIM_TRY(finish(s, table_out(s, s->cellrec, rec.data(), FSIM_CELLREC * nc)));
+        FSIM_TRY(finish(s, ensure_stage(s, sizeof(double) * FSIM_CELLREC * nc)));
+        FSIM_TRY(finish(s, launch_expand_records(s, (double *)s->stage)));
+        FSIM_TRY(finish(s, stage_out(s, rec.data(), sizeof(double) * FSIM_CELLREC * nc)));
         const int off = n == "R1" ? 0 : n == "R2" ? 3 : n == "R3" ? 6 : 9;
         for (int64_t c = 0; c < nc; ++c)
             for (int k = 0; k < 3; ++k) out[3 * c + k] = rec[FSIM_CELLREC * c + off + k];

@@ -21,6 +21,14 @@
 namespace fsim {
 
 constexpr int NPART_ARRAYS = 10;  // x y z vx vy vz q0 q1 q2 q3
+// Device cell record: 8 reals = 64 bytes in fp64 (two 256-bit loads, half a cache line):
+//   Bx By Bz f one_m Ax Ay Az,   f = 2/(1+h^2|B|^2), one_m = 1 - h^2|B|^2 f   (empic.js:521-524)
+// The nine Boris entries R1..R3 of programPre1/2/3 are products of these (no sqrt, no divide);
+// the push rebuilds them per particle with the reference's own expressions (boris_rows below) --
+// ~33 cheap fp64 operations instead of gathering 96 bytes: the gather, not the fp64 pipe, is what
+// limits the step kernel on B200.  Same expressions, same order => same bits as a stored table.
+constexpr int RECSTRIDE = 8;
+enum { REC_BX = 0, REC_BY, REC_BZ, REC_F, REC_ONEM, REC_AX, REC_AY, REC_AZ };
 enum { AX = 0, AY, AZ, AVX, AVY, AVZ, AQ0, AQ1, AQ2, AQ3 };
 
 void set_error(const std::string &msg);
@@ -183,6 +191,22 @@ __device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double ffloor(double x) { return floor(x); }
 __device__ __forceinline__ float ffloor(float x) { return floorf(x); }
 
+// programPre1/2/3 (empic.js:524-527, :563-566, :603-606) from a cell record: R[0..8] row-major.
+template <typename Real>
+__device__ __forceinline__ void boris_rows(const Real *rec, Real h, Real k13, Real k31, Real (&R)[9])
+{
+    const Real Bx = rec[REC_BX], By = rec[REC_BY], Bz = rec[REC_BZ], f = rec[REC_F], one_m = rec[REC_ONEM];
+    R[0] = one_m + f * h * h * Bx * Bx;
+    R[1] = f * h * (Bz + h * Bx * By);
+    R[2] = (f * h * (-By + h * Bx * Bz)) * k13;
+    R[3] = f * h * (-Bz + h * By * Bx);
+    R[4] = one_m + f * h * h * By * By;
+    R[5] = (f * h * (Bx + h * By * Bz)) * k13;
+    R[6] = (f * h * (By + h * Bz * Bx)) * k31;
+    R[7] = (f * h * (-Bx + h * Bz * By)) * k31;
+    R[8] = one_m + f * h * h * Bz * Bz;
+}
+
 // bit 31 of a sort key: the particle's sprite is clipped (not deposited)
 constexpr uint32_t KEY_CLIPPED = 0x80000000u;
 constexpr uint32_t KEY_MASK = 0x7fffffffu;
@@ -240,6 +264,7 @@ int launch_cellsum(fsim_sim *s);
 int launch_cellsum_atomic(fsim_sim *s);
 int launch_conv(fsim_sim *s);
 int launch_precalc(fsim_sim *s);
+int launch_expand_records(fsim_sim *s, double *dev_out);  // [cells][12] R1 R2 R3 A as doubles
 int launch_add_loop(fsim_sim *s, double R, double Z, double I);
 int launch_add_uniform(fsim_sim *s, int kind, double val);
 int launch_render(fsim_sim *s, uint8_t *dev_rgba);

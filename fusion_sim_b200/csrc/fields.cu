@@ -1,7 +1,7 @@
 // fields.cu -- per-cell maps: precalc() and the static-field builders (sm_100a).
 //
 // precalc  : programPre1/2/3 + programPreA (empic.js:506-659, out.precalc :1413-1434) fused into
-//            one pass: (E,B) -> the 12-real cell record R1.xyz R2.xyz R3.xyz A.xyz.
+//            one pass: (E,B) -> the 8-real cell record (B, f, 1 - h^2|B|^2 f, A), see common.cuh.
 // add_loop : out.addCurrentLoop (empic.js:1352-1363).  The reference renders two Biot-Savart
 //            tables (programCurrentLoopShape :308-326, u_R = 0.5 and 0.1) and samples them NEAREST
 //            at a scaled coordinate (programCurrentLoop :367-377).  The sampled texel value is a
@@ -31,7 +31,7 @@ int upload_costab(const double *c)
 template <typename Real>
 __global__ void __launch_bounds__(256)
 precalc_kernel(const Real *__restrict__ E, const Real *__restrict__ B, Real *__restrict__ rec,
-               int64_t ncell, Real h, Real k13, Real k31, Real kr, Real kz, int corrected)
+               int64_t ncell, Real h, Real kr, Real kz, int corrected)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
@@ -41,19 +41,11 @@ precalc_kernel(const Real *__restrict__ E, const Real *__restrict__ B, Real *__r
     const Real hB2 = h * h * Bmag * Bmag;
     const Real f = (Real)2.0 / ((Real)1.0 + hB2);
     const Real one_m = (Real)1.0 - hB2 * f;
-    Real *o = rec + FSIM_CELLREC * c;
-    // programPre1, empic.js:524-527
-    o[0] = one_m + f * h * h * Bx * Bx;
-    o[1] = f * h * (Bz + h * Bx * By);
-    o[2] = (f * h * (-By + h * Bx * Bz)) * k13;
-    // programPre2, empic.js:563-566
-    o[3] = f * h * (-Bz + h * By * Bx);
-    o[4] = one_m + f * h * h * By * By;
-    o[5] = (f * h * (Bx + h * By * Bz)) * k13;
-    // programPre3, empic.js:603-606
-    o[6] = (f * h * (By + h * Bz * Bx)) * k31;
-    o[7] = (f * h * (-Bx + h * Bz * By)) * k31;
-    o[8] = one_m + f * h * h * Bz * Bz;
+    Real *o = rec + RECSTRIDE * c;
+    // what programPre1/2/3 need of B (empic.js:520-522); the nine entries are rebuilt by boris_rows()
+    o[REC_BX] = Bx; o[REC_BY] = By; o[REC_BZ] = Bz;
+    o[REC_F] = f;
+    o[REC_ONEM] = one_m;
     // programPreA, empic.js:645-647
     const Real cx = Ey * Bz - Ez * By;
     const Real cy = Ez * Bx - Ex * Bz;
@@ -72,9 +64,38 @@ precalc_kernel(const Real *__restrict__ E, const Real *__restrict__ B, Real *__r
         ay = (t1 * Ey + t2 * (cy + hd)) / (Real)FSIM_C_LIGHT;
         az = (t1 * Ez + t2 * (cz + hd)) / (Real)FSIM_C_LIGHT;
     }
-    o[9] = ax * kr;
-    o[10] = ay * kr;
-    o[11] = az * kz;
+    o[REC_AX] = ax * kr;
+    o[REC_AY] = ay * kr;
+    o[REC_AZ] = az * kz;
+}
+
+// accessor support: expand the records to the reference's four textures R1 R2 R3 A (12 reals)
+template <typename Real>
+__global__ void __launch_bounds__(256)
+expand_records_kernel(const Real *__restrict__ rec, double *__restrict__ out, int64_t ncell, Real h, Real k13,
+                      Real k31)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    Real R[9];
+    boris_rows<Real>(rec + RECSTRIDE * c, h, k13, k31, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[FSIM_CELLREC * c + k] = (double)R[k];
+    out[FSIM_CELLREC * c + 9] = (double)rec[RECSTRIDE * c + REC_AX];
+    out[FSIM_CELLREC * c + 10] = (double)rec[RECSTRIDE * c + REC_AY];
+    out[FSIM_CELLREC * c + 11] = (double)rec[RECSTRIDE * c + REC_AZ];
+}
+
+int launch_expand_records(fsim_sim *s, double *dev_out)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        expand_records_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
+            (const Real *)s->cellrec, dev_out, s->ncell_local, (Real)s->h, (Real)s->k13, (Real)s->k31);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
 }
 
 int launch_precalc(fsim_sim *s)
@@ -84,7 +105,7 @@ int launch_precalc(fsim_sim *s)
         Bracket b(s, "precalc");
         precalc_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
             (const Real *)s->E, (const Real *)s->B, (Real *)s->cellrec, s->ncell_local, (Real)s->h,
-            (Real)s->k13, (Real)s->k31, (Real)s->kr, (Real)s->kz,
+            (Real)s->kr, (Real)s->kz,
             (s->spec.flags & FSIM_FLAG_CORRECTED_PREA) ? 1 : 0);
         FSIM_CUDA(cudaGetLastError());
         return (int)FSIM_OK;

@@ -34,7 +34,7 @@ struct PushArgs {
     int own0, own_rows;
     int64_t n;
     int nr, nz, row0, rows, own_lo, own_hi;
-    Real sf;
+    Real sf, h, k13, k31;
 };
 
 template <typename Real, int V> struct Vec;
@@ -78,15 +78,16 @@ __device__ __forceinline__ void ld_ro4(const float *p, float (&o)[4])
     float4 a = __ldg(reinterpret_cast<const float4 *>(p));
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
 }
-__device__ __forceinline__ void ld_ro12(const double *p, double (&o)[12])
+// the 8-real cell record (common.cuh): two 256-bit loads in fp64, two 128-bit loads in fp32
+__device__ __forceinline__ void ld_rec(const double *p, double (&o)[RECSTRIDE])
 {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) ld_ro256(p + 4 * k, o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    ld_ro256(p, o[0], o[1], o[2], o[3]);
+    ld_ro256(p + 4, o[4], o[5], o[6], o[7]);
 }
-__device__ __forceinline__ void ld_ro12(const float *p, float (&o)[12])
+__device__ __forceinline__ void ld_rec(const float *p, float (&o)[RECSTRIDE])
 {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 2; ++k) {
         float4 a = __ldg(reinterpret_cast<const float4 *>(p) + k);
         o[4 * k] = a.x; o[4 * k + 1] = a.y; o[4 * k + 2] = a.z; o[4 * k + 3] = a.w;
     }
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
 #pragma unroll 1
     for (int hs = 0; hs < NH; ++hs) {
         // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
-        Real e[V][4], rec[V][12], dx[V], dy[V];
+        Real e[V][4], rec[V][RECSTRIDE], dx[V], dy[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int ie = tex_idx(q2[k], FSIM_N_ENTROPY) + FSIM_N_ENTROPY * tex_idx(q3[k], FSIM_N_ENTROPY);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
                 if (p0 + k < a.n) atomicAdd(a.oob, 1u);
                 cj = cj < 0 ? 0 : a.rows - 1;
             }
-            ld_ro12(a.cellrec + FSIM_CELLREC * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
+            ld_rec(a.cellrec + RECSTRIDE * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
         }
 
 #pragma unroll
@@ -171,10 +172,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
             // ---- step_velocity_frag, empic.js:758-772 ----
             const Real vr = vx[k] * dx[k] + vy[k] * dy[k];
             const Real va = vy[k] * dx[k] - vx[k] * dy[k];
-            const Real *R = rec[k];
-            const Real c0 = (R[0] * vr + R[1] * va + R[2] * vz[k]) + R[9];
-            const Real c1 = (R[3] * vr + R[4] * va + R[5] * vz[k]) + R[10];
-            const Real c2 = (R[6] * vr + R[7] * va + R[8] * vz[k]) + R[11];
+            Real R[9];  // rows of the Boris matrix, rebuilt from the record (programPre1/2/3)
+            boris_rows<Real>(rec[k], a.h, a.k13, a.k31, R);
+            const Real c0 = (R[0] * vr + R[1] * va + R[2] * vz[k]) + rec[k][REC_AX];
+            const Real c1 = (R[3] * vr + R[4] * va + R[5] * vz[k]) + rec[k][REC_AY];
+            const Real c2 = (R[6] * vr + R[7] * va + R[8] * vz[k]) + rec[k][REC_AZ];
             Real nvx, nvy, nvz;
             if (al[k]) {
                 nvx = c0 * dx[k] - c1 * dy[k];
@@ -270,6 +272,7 @@ static int push_impl(fsim_sim *s, bool with_hist, int nhalf)
     a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
     a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
     a.sf = (Real)s->step_factor;
+    a.h = (Real)s->h; a.k13 = (Real)s->k13; a.k31 = (Real)s->k31;
     const int64_t nvec = (s->n + V - 1) / V;
     if (nvec == 0) return FSIM_OK;
     Bracket b(s, nhalf == 2 ? "push2" : "push");
