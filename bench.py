@@ -102,10 +102,12 @@ def measured_peak():
 
 
 def push_algorithmic_bytes(n, ncell, precision):
-    """bytes one half-step launch must move (per GPU)."""
-    if precision == "f64":
-        return 162.0 * n + 97.0 * ncell + 37.7e6
-    return 82.0 * n + 49.0 * ncell + 18.9e6
+    """Bytes one sweep of the step kernel must move (per GPU): SURVEY.md section 8d with this
+    build's cell record (8 reals + 1 sink byte per cell instead of the survey's 12 + 1):
+    particle state read + written once (10 reals + 1 flag byte each way), the cell table, the
+    entropy table (4 reals x 1024^2) and the inverse-cdf table (2 reals x 512^2) once."""
+    rs = 8 if precision == "f64" else 4
+    return (2 * (10 * rs + 1)) * float(n) + (8 * rs + 1) * float(ncell) + rs * (4 * 1024 * 1024 + 2 * 512 * 512)
 
 
 def build_scene(workload, rank, world, seed=2026):
@@ -226,8 +228,11 @@ def run_ours(args):
         apply_scene(sim, sc)
     nr, nz = int(spec["nr"]), int(spec["nz"])
     ncell_local = sim.ncell_local
-    _keep3 = torch.empty((nz, nr, 4), dtype=torch.uint8, pin_memory=(world == 1))
-    canvas = _keep3.numpy()
+    # two host images for the e2e leg: frame k's read-back overlaps frame k+1 (slab ranks fill
+    # only their rows of the full-size image, so only those pages are touched)
+    _keep3 = [torch.empty((nz, nr, 4), dtype=torch.uint8, pin_memory=(world == 1)) for _ in range(2)]
+    canvases = [t.numpy() for t in _keep3]
+    canvas = canvases[0]
 
     def frame():
         sim.step()
@@ -321,17 +326,18 @@ def run_ours(args):
     sim.mark(2)
     check(lib().fsim_set_particle_count(base.handle, n_local))
     base.set({"position": pos_h, "velocity": vel_h})
-    for _ in range(args.steps):
+    for k in range(args.steps):
         frame()
-        sim.render(canvas)
+        sim.render_async(canvases[k & 1])
     sim.mark(3)
     ms_e2e = sim.elapsed_ms(2, 3)
-    sim.sync()
+    sim.sync()  # also waits for the last canvas copy
     ms_e2e = reduce_max(max(ms_e2e, (time.perf_counter() - t0) * 1e3))
     e2e = {"value": 2.0 * n_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h, "ms_total": ms_e2e,
            "what": "per rank: set(position,velocity) from pinned host arrays once + per frame step(), density(), "
-                   "canvas read-back (own rows) to pinned host memory; upload amortised over the K frames"}
+                   "canvas read-back (own rows) to pinned host memory on a copy stream, overlapping the next frame; upload "
+                   "amortised over the K frames; wall clock to the last byte on the host"}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -62,6 +62,7 @@ _SIGS = {
     "fsim_half_step": (C.c_int, [_P]),
     "fsim_density": (C.c_int, [_P]),
     "fsim_render_rgba8": (C.c_int, [_P, _P]),
+    "fsim_render_rgba8_async": (C.c_int, [_P, _P]),
     "fsim_sort": (C.c_int, [_P]),
     "fsim_sync": (C.c_int, [_P]),
     "fsim_particle_count": (C.c_int64, [_P]),

@@ -410,6 +410,12 @@ static void free_all(fsim_sim *s)
         }
     for (auto &m : s->marks)
         if (m) cudaEventDestroy(m);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(s->canvas_dev[k]);
+        if (s->render_done[k]) cudaEventDestroy(s->render_done[k]);
+        if (s->copy_done[k]) cudaEventDestroy(s->copy_done[k]);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
 }
 
@@ -763,10 +769,40 @@ int fsim_render_rgba8(fsim_sim *s, uint8_t *rgba)
     return FSIM_OK;
 }
 
+int fsim_render_rgba8_async(fsim_sim *s, uint8_t *rgba)
+{
+    FSIM_TRY(check(s));
+    if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
+    const size_t bytes = 4 * (size_t)s->ncell_global;
+    if (!s->copy_stream) {
+        FSIM_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            FSIM_CUDA(cudaMalloc((void **)&s->canvas_dev[k], bytes));
+            FSIM_CUDA(cudaEventCreateWithFlags(&s->render_done[k], cudaEventDisableTiming));
+            FSIM_CUDA(cudaEventCreateWithFlags(&s->copy_done[k], cudaEventDisableTiming));
+        }
+    }
+    const int k = (s->canvas_slot ^= 1);
+    if (s->copy_pending[k]) FSIM_CUDA(cudaEventSynchronize(s->copy_done[k]));  // image k is free again
+    FSIM_TRY(finish(s, launch_render(s, s->canvas_dev[k])));
+    FSIM_CUDA(cudaEventRecord(s->render_done[k], s->stream));
+    FSIM_CUDA(cudaStreamWaitEvent(s->copy_stream, s->render_done[k], 0));
+    const size_t off = 4 * (size_t)s->nr * (size_t)(s->nz - s->own0 - s->own_rows);
+    const size_t len = 4 * (size_t)s->nr * (size_t)s->own_rows;
+    FSIM_CUDA(cudaMemcpyAsync(rgba + off, s->canvas_dev[k] + off, len, cudaMemcpyDeviceToHost, s->copy_stream));
+    FSIM_CUDA(cudaEventRecord(s->copy_done[k], s->copy_stream));
+    s->copy_pending[k] = true;
+    return FSIM_OK;
+}
+
 int fsim_sync(fsim_sim *s)
 {
     FSIM_TRY(check(s));
     FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->copy_stream) {
+        FSIM_CUDA(cudaStreamSynchronize(s->copy_stream));
+        s->copy_pending[0] = s->copy_pending[1] = false;
+    }
     uint32_t oob = 0;
     FSIM_CUDA(cudaMemcpy(&oob, s->oob, sizeof oob, cudaMemcpyDeviceToHost));
     if (oob) {

@@ -134,6 +134,13 @@ struct fsim_sim {
     std::map<std::string, fsim::KernelTimer> timers;
     int64_t launches = 0;
     cudaEvent_t marks[16] = {};
+
+    // asynchronous canvas read-back (fsim_render_rgba8_async): two device images, copy stream
+    cudaStream_t copy_stream = nullptr;
+    uint8_t *canvas_dev[2] = {};
+    cudaEvent_t render_done[2] = {}, copy_done[2] = {};
+    bool copy_pending[2] = {false, false};
+    int canvas_slot = 0;
 };
 
 namespace fsim {

@@ -151,6 +151,9 @@ class SlabPusher:
     def render(self, out):
         return self.sim.render(out)
 
+    def render_async(self, out):
+        return self.sim.render_async(out)
+
     def set(self, value):
         self.sim.set(value)
 

@@ -157,6 +157,11 @@ class CylindricalParticlePusher:
         check(lib().fsim_render_rgba8(self._h, ptr(out)))
         return out
 
+    def render_async(self, out: np.ndarray) -> np.ndarray:
+        """Same image, copied to `out` (pinned memory) on a second stream; complete after sync()."""
+        check(lib().fsim_render_rgba8_async(self._h, ptr(out)))
+        return out
+
     @property
     def canvas(self) -> np.ndarray:
         """RGBA8 image [nz][nr][4], top row first: what `drawImage(simulation.canvas)` shows."""

@@ -107,6 +107,10 @@ int fsim_step(fsim_sim *sim);      /* out.step    :1436-1469: TWO leap-frog half
 int fsim_half_step(fsim_sim *sim); /* extension: one half-step (rand, velocity, position)      */
 int fsim_density(fsim_sim *sim);   /* out.density :1471-1495: deposit, normalise, running avg  */
 int fsim_render_rgba8(fsim_sim *sim, uint8_t *rgba); /* out.canvas :60 after :1497-1504; [nz][nr][4], top row first */
+/* extension: same image, but the device->host copy runs on a second stream and overlaps the next
+ * frame; `rgba` (pinned memory for a truly asynchronous copy) is complete after the next fsim_sync()
+ * or after two further fsim_render_rgba8_async() calls (two device buffers alternate).           */
+int fsim_render_rgba8_async(fsim_sim *sim, uint8_t *rgba);
 int fsim_sort(fsim_sim *sim);      /* extension: re-sort particle storage by cell now          */
 int fsim_sync(fsim_sim *sim);      /* wait for the handle's stream                             */
 

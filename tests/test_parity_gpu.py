@@ -171,6 +171,21 @@ def test_c1_demo_scene_frames():
     assert_same(g.canvas, o.canvas, "C1 canvas")
 
 
+def test_async_canvas_matches_sync():
+    sc = small_scene(n=3000, speed=0.02, blob=(0.5, 0.8))
+    g, o = make_pair(sc)
+    imgs = [np.zeros((g.nz, g.nr, 4), np.uint8) for _ in range(3)]
+    want = []
+    for k in range(3):
+        g.step(); o.step()
+        g.density(); o.density()
+        g.render_async(imgs[k])
+        want.append(o.canvas)
+    g.sync()
+    for k in range(3):
+        assert_same(imgs[k], want[k], f"async canvas {k}")
+
+
 def test_errors_are_thrown():
     from fusion_sim_b200 import Error, makeCylindricalParticlePusher
     sc = small_scene(n=64)
