@@ -567,6 +567,7 @@ int fsim_set_position(fsim_sim *s, const double *pos)
     s->binned = false;
     s->keys_valid = false;
     s->have_leavers = false;
+    s->steps_since_sort = 1 << 20;  // the storage order says nothing about the new positions: re-sort at the next density()
     return finish(s, particles_in3(s, pos, AX, s->factor_r, s->factor_r, s->factor_z, true));
 }
 int fsim_set_velocity(fsim_sim *s, const double *vel)
