@@ -233,3 +233,60 @@ def test_full_size_properties():
     assert_same(counts, np.bincount(cells, minlength=nr * nz).astype(np.uint32), "C3 per-cell counts")
     sums = g.getField("cell_sums")
     np.testing.assert_allclose(sums[:, 3].sum(), 0.001 * inside.sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_edge_shapes(precision):
+    """Empty particle set, a single particle, a one-column grid and a non-square particle count."""
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene
+    from oracle.oracle import OraclePusher
+    # no particles at all: every call must still work
+    sc = small_scene(precision=precision, n=16)
+    spec0 = dict(sc["spec"], nparticles=0)
+    spec0.pop("nparticles_total", None)
+    g = makeCylindricalParticlePusher(spec0)
+    g.set({"sink_mask": sc["sink_mask"], "source_pdf": sc["source_pdf"]})
+    g.addCurrentLoop(0.8, 2.0, -1e7)
+    g.precalc()
+    g.step(); g.density(); g.sort(); g.sync()
+    assert g.getPosition().shape == (0, 4) and int(g.getField("cell_count").sum()) == 0
+    assert g.canvas.shape == (g.nz, g.nr, 4)
+    # one particle; odd counts; tiny grids
+    for n, nr, nz in ((1, 8, 8), (7, 1, 16), (33, 16, 1), (1000, 5, 7)):
+        sc = small_scene(precision=precision, n=n, nr=nr, nz=nz, speed=0.05, blob=(0.7, 0.9))
+        g, o = make_pair(sc)
+        for _ in range(3):
+            g.step(); o.step()
+            g.density(); o.density()
+        compare_particles(g, o, f"n={n} grid {nr}x{nz}")
+        assert_same(g.getField("cell_count"), o.getField("cell_count"), "counts")
+        compare_grid(g, o, ["moments01_avg"], f"n={n} grid {nr}x{nz}")
+        assert_same(g.canvas, o.canvas, "canvas")
+
+
+def test_long_run_c1_energy_and_population():
+    """Config C1 for 200 frames (400 half-steps): bounded energy drift of the particles that were
+    never respawned (Boris rotation, E = 0), RNG state in range, particle count conserved."""
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene, c1_scene
+    sc = c1_scene(7)
+    g = makeCylindricalParticlePusher(sc["spec"])
+    apply_scene(g, sc)
+    fac = np.array([1.0, 1.0, 0.5])
+    e0 = ((g.getVelocity() / fac) ** 2).sum(1)
+    never = np.ones(g.n, bool)
+    for k in range(200):
+        g.step(); g.density()
+        if k % 20 == 19:
+            never &= g.getPosition()[:, 3] == 1
+    g.sync()
+    e1 = ((g.getVelocity() / fac) ** 2).sum(1)
+    # a respawned particle gets |v| <= 0.001*sqrt(3) again; the untouched ones keep their energy
+    drift = np.abs(e1[never] / e0[never] - 1)
+    assert never.sum() > 1000
+    assert drift.max() < 1e-11, drift.max()  # 400 rotations x ~1e-16
+    q = g.getRand()
+    assert q.min() >= 0 and q.max() <= 1 and g.n == 160000
+    ids = np.sort(g.getIds())
+    assert_same(ids, np.arange(160000, dtype=np.uint64), "ids after 200 frames")
