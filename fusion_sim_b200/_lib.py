@@ -86,6 +86,17 @@ _SIGS = {
     "fsim_migrate_unpack": (C.c_int, [_P, _P, C.c_int64]),
     "fsim_halo_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                  C.POINTER(C.c_int64)]),
+    "fsim_jacobi_create": (C.c_int, [C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(_P)]),
+    "fsim_jacobi_destroy": (C.c_int, [_P]),
+    "fsim_jacobi_vec_length": (C.c_int64, [_P]),
+    "fsim_jacobi_set_matrix": (C.c_int, [_P, _P]),
+    "fsim_jacobi_set_b": (C.c_int, [_P, _P]),
+    "fsim_jacobi_init_vector": (C.c_int, [_P, _P]),
+    "fsim_jacobi_solve": (C.c_int, [_P, C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_int32), _P]),
+    "fsim_jacobi_get_result": (C.c_int, [_P, _P]),
+    "fsim_jacobi_launch_count": (C.c_int64, [_P]),
+    "fsim_jacobi_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fsim_density_begin": (C.c_int, [_P]),
     "fsim_density_end": (C.c_int, [_P]),
 }

@@ -154,6 +154,25 @@ int fsim_halo_ptrs(fsim_sim *sim, void **send_lo, void **send_hi, void **recv_lo
 int fsim_density_begin(fsim_sim *sim); /* sort + per-cell sums (before the halo exchange)        */
 int fsim_density_end(fsim_sim *sim);   /* convolution + normalise + running average              */
 
+/* ---- dense weighted-Jacobi solver: matrix_webgl.makeSORIterative (matrix_webgl.js:35-711) ------------
+ * "next" row N3 of SURVEY.md section 8f.  vec_length L = 4 (2^n_power)^2; A is [L][L] row-major.
+ * FSIM_JACOBI_LITERAL reproduces two defects of the reference (row gather of programResult
+ * :408-411, never-reset statistics :628-634); without it the solver does what was evidently meant. */
+#define FSIM_JACOBI_LITERAL 1u
+typedef struct fsim_jacobi fsim_jacobi;
+int fsim_jacobi_create(int32_t n_power, double relaxation, int32_t precision, int32_t device, uint32_t flags,
+                       fsim_jacobi **out);                                   /* makeSORIterative :35 */
+int fsim_jacobi_destroy(fsim_jacobi *j);
+int64_t fsim_jacobi_vec_length(const fsim_jacobi *j);                        /* out.vec_length :52  */
+int fsim_jacobi_set_matrix(fsim_jacobi *j, const double *A);                 /* out.set_matrix :455 */
+int fsim_jacobi_set_b(fsim_jacobi *j, const double *b);                      /* out.set_b :482      */
+int fsim_jacobi_init_vector(fsim_jacobi *j, const double *x);                /* out.init_vector :503 */
+int fsim_jacobi_solve(fsim_jacobi *j, double tolerance, int32_t substep, int32_t max_iterations,
+                      double *correlation, double *diff, int32_t *iterations, double *result); /* out.solve :576 */
+int fsim_jacobi_get_result(fsim_jacobi *j, double *x);                       /* out.x_result_tex :703 */
+int64_t fsim_jacobi_launch_count(const fsim_jacobi *j);
+int fsim_jacobi_timing(fsim_jacobi *j, double *mv_ms, int64_t *mv_launches); /* device time of the mat-vec kernel */
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,18 @@ static inline float orc_floor_f32(float x) { return floorf(x); }
 #undef REAL
 #undef SFX
 
+/* dense weighted-Jacobi solver of matrix_webgl.js ("next" row N3 of SURVEY.md section 8f) */
+#define REAL double
+#define SFX f64
+#include "fsim_oracle_jacobi_impl.h"
+#undef REAL
+#undef SFX
+#define REAL float
+#define SFX f32
+#include "fsim_oracle_jacobi_impl.h"
+#undef REAL
+#undef SFX
+
 /* N(num) = num.toFixed(20) (empic.js:23-25) parsed back by the GLSL compiler. */
 double orc_tofixed20(double x)
 {

@@ -26,7 +26,7 @@ N_INVCDF = 512
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfsim_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("fsim_oracle.c", "fsim_oracle_impl.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fsim_oracle.c", "fsim_oracle_impl.h", "fsim_oracle_jacobi_impl.h", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "fsim_constants.h"))
     stale = (not os.path.exists(so)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
