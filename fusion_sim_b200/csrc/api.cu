@@ -402,7 +402,6 @@ static void free_all(fsim_sim *s)
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
                     s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag};
     for (void *p : ptrs) cudaFree(p);
-    if (s->hstage) cudaFreeHost(s->hstage);
     for (auto &kv : s->timers)
         for (auto &pe : kv.second.pending) {
             cudaEventDestroy(pe.first);

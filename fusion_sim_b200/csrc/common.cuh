@@ -93,8 +93,7 @@ struct fsim_sim {
     void *dcol[3] = {};           // [cap] sprite colour 0.001*(v_r, v_a, v_z) of each slot (deposit prepass)
     bool keys_valid = false;      // key[] and the histogram in counts[] match the current positions
     bool counts_dirty = false;    // counts[] holds a histogram that no scan has consumed yet
-    bool binned = false;          // starts[] (+ perm[] unless perm_identity) match the current positions
-    bool perm_identity = false;   // storage itself is sorted by cell: segment j is slot j
+    bool binned = false;          // starts[] and perm[] match the current positions
     bool ever_sorted = false;
     int steps_since_sort = 0;     // step() calls since the last physical sort
 
@@ -104,8 +103,6 @@ struct fsim_sim {
     uint8_t *sink = nullptr;   // [ncell_global]
     void *entropy = nullptr;   // [1024*1024][4]
     void *invcdf = nullptr;    // [512*512][2]
-    void *costab = nullptr;    // [1000]
-    void *shape = nullptr;     // [121]
     bool have_precalc = false;
 
     // deposit
@@ -120,8 +117,6 @@ struct fsim_sim {
     // staging
     void *stage = nullptr;
     size_t stage_bytes = 0;
-    void *hstage = nullptr;
-    size_t hstage_bytes = 0;
     void *migr = nullptr;          // packed migration records (send side)
     size_t migr_bytes = 0;
     uint32_t *mscratch = nullptr;  // small counters of the migration kernels
