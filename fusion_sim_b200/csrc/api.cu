@@ -161,6 +161,18 @@ __global__ void convert_out_kernel(const Real *__restrict__ in, double *__restri
     if (k < n) out[k] = (double)in[k];
 }
 
+// planar grid field (common.cuh) -> [cell][4] doubles, cell = i + j*nr
+template <typename Real>
+__global__ void planar_out_kernel(const Real *__restrict__ in, double *__restrict__ out, int nr, int rows,
+                                  int pitch, int64_t plane)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (int64_t)nr * rows) return;
+    const size_t o = (size_t)(c / nr) * pitch + (size_t)(c % nr);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out[4 * c + q] = (double)in[q * plane + o];
+}
+
 // value.sink_mask [nr][nz] -> 1 byte per global cell i + j*nr; the shader tests .r > 0.5 (:719)
 __global__ void sink_in_kernel(const double *__restrict__ in, uint8_t *__restrict__ out, int nr, int nz)
 {
@@ -314,6 +326,8 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
         s->own0 = 0; s->own_rows = s->nz; s->row0 = 0; s->rows = s->nz;
     }
     s->ncell_local = (int64_t)s->nr * s->rows;
+    s->pitch = (s->nr + 3) / 4 * 4;
+    s->plane = (int64_t)s->pitch * s->rows;
 
     // physical quantities, empic.js:44-46, :852 and the toFixed(20) literals of :527,:606,:647
     s->h = sp->particle_charge * sp->dt / (2 * sp->particle_mass);
@@ -348,12 +362,13 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_TRY(dalloc(&s->sink, s->ncell_global));
     FSIM_TRY(dalloc_bytes(&s->entropy, s->rs * 4 * FSIM_N_ENTROPY * FSIM_N_ENTROPY));
     FSIM_TRY(dalloc_bytes(&s->invcdf, s->rs * 2 * FSIM_N_INVCDF * FSIM_N_INVCDF));
-    FSIM_TRY(dalloc_bytes(&s->cellsum, s->rs * 4 * s->ncell_local));
+    FSIM_TRY(dalloc_bytes(&s->cellsum, s->rs * 4 * s->plane));
+    FSIM_TRY(make_sums_tensor_map(s));
     FSIM_TRY(dalloc(&s->cellcount, s->ncell_local));
-    FSIM_TRY(dalloc_bytes(&s->avg, s->rs * 4 * s->ncell_local));
+    FSIM_TRY(dalloc_bytes(&s->avg, s->rs * 4 * s->plane));
     if (sp->flags & FSIM_FLAG_KEEP_MOMENTS) {
-        FSIM_TRY(dalloc_bytes(&s->mom, s->rs * 4 * s->ncell_local));
-        FSIM_TRY(dalloc_bytes(&s->norm, s->rs * 4 * s->ncell_local));
+        FSIM_TRY(dalloc_bytes(&s->mom, s->rs * 4 * s->plane));
+        FSIM_TRY(dalloc_bytes(&s->norm, s->rs * 4 * s->plane));
     }
     FSIM_TRY(dalloc(&s->heavy_list, s->cap / 64 + 2));
     FSIM_TRY(dalloc(&s->heavy_n, 1));
@@ -400,7 +415,7 @@ static void free_all(fsim_sim *s)
     }
     void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->dcol[2], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
-                    s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag};
+                    s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf};
     for (void *p : ptrs) cudaFree(p);
     for (auto &kv : s->timers)
         for (auto &pe : kv.second.pending) {
@@ -480,6 +495,23 @@ static int table_out(fsim_sim *s, const void *src, double *host, int64_t count)
     });
     FSIM_TRY(rc);
     return stage_out(s, host, sizeof(double) * count);
+}
+
+static int planar_out(fsim_sim *s, const void *src, double *host)
+{
+    if (!host) return fail(FSIM_ERR_INVALID, "null array");
+    const int64_t nc = s->ncell_local;
+    FSIM_TRY(ensure_stage(s, sizeof(double) * 4 * nc));
+    int rc = dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        planar_out_kernel<Real><<<grid_for(nc, 256), 256, 0, s->stream>>>((const Real *)src, (double *)s->stage,
+                                                                         s->nr, s->rows, s->pitch, s->plane);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+    FSIM_TRY(rc);
+    return stage_out(s, host, sizeof(double) * 4 * nc);
 }
 
 static int collect_timers(fsim_sim *s)
@@ -740,11 +772,13 @@ int fsim_density_begin(fsim_sim *s)
     // the deposit is done with the index list; now, every sort_interval frames, put the storage
     // itself into cell order for the pushes that follow
     if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) FSIM_TRY(finish(s, launch_apply_perm(s)));
+    if (s->slab) FSIM_TRY(finish(s, launch_halo_pack(s)));  // own boundary rows -> send buffers
     return FSIM_OK;
 }
 int fsim_density_end(fsim_sim *s)
 {
     FSIM_TRY(check(s));
+    if (s->slab) FSIM_TRY(finish(s, launch_halo_unpack(s)));  // neighbours' boundary rows -> halo rows of the sums
     return finish(s, launch_conv(s));
 }
 int fsim_density(fsim_sim *s)
@@ -902,11 +936,11 @@ int fsim_get_field(fsim_sim *s, const char *name, double *out)
             for (int k = 0; k < 3; ++k) out[3 * c + k] = rec[FSIM_CELLREC * c + off + k];
         return FSIM_OK;
     }
-    if (n == "cell_sums") return finish(s, table_out(s, s->cellsum, out, 4 * nc));
-    if (n == "moments01_avg") return finish(s, table_out(s, s->avg, out, 4 * nc));
+    if (n == "cell_sums") return finish(s, planar_out(s, s->cellsum, out));
+    if (n == "moments01_avg") return finish(s, planar_out(s, s->avg, out));
     if (n == "moments01" || n == "moments01_norm") {
         if (!s->mom) return fail(FSIM_ERR_STATE, "moments01/moments01_norm are kept only with FSIM_FLAG_KEEP_MOMENTS");
-        return finish(s, table_out(s, n == "moments01" ? s->mom : s->norm, out, 4 * nc));
+        return finish(s, planar_out(s, n == "moments01" ? s->mom : s->norm, out));
     }
     if (n == "inv_cdf") return finish(s, table_out(s, s->invcdf, out, 2ll * FSIM_N_INVCDF * FSIM_N_INVCDF));
     if (n == "entropy") return finish(s, table_out(s, s->entropy, out, 4ll * FSIM_N_ENTROPY * FSIM_N_ENTROPY));

@@ -68,6 +68,11 @@ struct fsim_sim {
     int row0 = 0, rows = 0;   // local table rows (owned + halo, clipped to the grid)
     int own0 = 0, own_rows = 0;  // owned rows (== whole grid on one GPU)
     int64_t ncell_local = 0, ncell_global = 0;
+    // planar grid fields (per-cell sums, running average, moments): channel q of local cell (i, j) at
+    // base[q*plane + j*pitch + i]; the row pitch is padded to 16 bytes for the TMA tensor map
+    int pitch = 0;
+    int64_t plane = 0;
+    alignas(64) unsigned char tm_sums[128] = {};  // CUtensorMap of the per-cell sums (deposit.cu)
     bool slab = false;
 
     // physical constants (host doubles, empic.js:44-46, :852)
@@ -122,6 +127,7 @@ struct fsim_sim {
     uint32_t *mscratch = nullptr;  // small counters of the migration kernels
     uint8_t *hole_flag = nullptr;  // [cap] 1 = slot vacated by a leaver
     uint32_t nholes_host = 0;
+    void *halo_buf = nullptr;      // slab mode: [send_lo | send_hi | recv_lo | recv_hi], each 4 x 5 x nr reals
     bool have_leavers = false;     // perm[0..*nleavers) lists the slots whose row left the slab (emitted by the push)
 
     // measurement
@@ -265,6 +271,9 @@ int launch_apply_perm(fsim_sim *s);  // physical re-sort: storage <- storage[per
 int launch_cellsum(fsim_sim *s);
 int launch_cellsum_atomic(fsim_sim *s);
 int launch_conv(fsim_sim *s);
+int make_sums_tensor_map(fsim_sim *s);
+int launch_halo_pack(fsim_sim *s);
+int launch_halo_unpack(fsim_sim *s);
 int launch_precalc(fsim_sim *s);
 int launch_expand_records(fsim_sim *s, double *dev_out);  // [cells][12] R1 R2 R3 A as doubles
 int launch_add_loop(fsim_sim *s, double R, double Z, double I);

@@ -13,6 +13,8 @@
 //   conv    : 11x11 stencil on shared-memory tiles fused with programNormalizeMoments01
 //             (empic.js:1053-1056), programAvgMoments (avg_frag :274-277, ratio :1083) and the
 //             avgA -> avgB copy (:1490-1495).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace fsim {
@@ -26,8 +28,10 @@ struct CellSumArgs {
     const uint32_t *id;
     const uint32_t *perm;  // particle slots in cell order
     const uint32_t *starts;
-    Real *S;          // [ncell][4]
+    Real *S;          // planar: channel q of cell (i,j) at S[q*plane + j*pitch + i]
     uint32_t *count;  // [ncell]
+    int pitch;
+    int64_t plane;
     uint32_t *heavy_list, *heavy_n;
     int64_t ncell;
     int nr, nz, row0;
@@ -130,8 +134,8 @@ __global__ void __launch_bounds__(128) cellsum_kernel(const CellSumArgs<Real> a)
         }
     }
     if (!live) return;
-    Real *o = a.S + 4 * (size_t)c;
-    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+    Real *o = a.S + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr);
+    o[0] = acc[0]; o[a.plane] = acc[1]; o[2 * a.plane] = acc[2]; o[3 * a.plane] = acc[3];
     a.count[c] = cnt;
 }
 
@@ -180,8 +184,8 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
             acc[3] += (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
             cnt++;
         }
-        Real *o = a.S + 4 * (size_t)c;
-        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+        Real *o = a.S + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr);
+        o[0] = acc[0]; o[a.plane] = acc[1]; o[2 * a.plane] = acc[2]; o[3 * a.plane] = acc[3];
         a.count[c] = cnt;
     }
     __syncthreads();
@@ -194,17 +198,18 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
 template <typename Real>
 __global__ void __launch_bounds__(256)
 cellsum_atomic_kernel(const uint32_t *__restrict__ key, const Real *__restrict__ c0, const Real *__restrict__ c1,
-                      const Real *__restrict__ c2, int64_t n, Real *__restrict__ S, uint32_t *__restrict__ count)
+                      const Real *__restrict__ c2, int64_t n, Real *__restrict__ S, uint32_t *__restrict__ count,
+                      int nr, int pitch, int64_t plane)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t k = key[p];
     if (k & KEY_CLIPPED) return;
-    Real *o = S + 4 * (size_t)k;
-    atomicAdd(o + 0, c0[p]);
-    atomicAdd(o + 1, c1[p]);
-    atomicAdd(o + 2, c2[p]);
-    atomicAdd(o + 3, (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0);
+    Real *o = S + (size_t)(k / nr) * pitch + (size_t)(k % nr);
+    atomicAdd(o, c0[p]);
+    atomicAdd(o + plane, c1[p]);
+    atomicAdd(o + 2 * plane, c2[p]);
+    atomicAdd(o + 3 * plane, (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0);
     atomicAdd(count + k, 1u);
 }
 
@@ -212,13 +217,13 @@ int launch_cellsum_atomic(fsim_sim *s)
 {
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
-        FSIM_CUDA(cudaMemsetAsync(s->cellsum, 0, sizeof(Real) * 4 * s->ncell_local, s->stream));
+        FSIM_CUDA(cudaMemsetAsync(s->cellsum, 0, sizeof(Real) * 4 * s->plane, s->stream));
         FSIM_CUDA(cudaMemsetAsync(s->cellcount, 0, sizeof(uint32_t) * s->ncell_local, s->stream));
         if (s->n == 0) return (int)FSIM_OK;
         Bracket b(s, "cellsum_atomic");
         cellsum_atomic_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
             s->key, (const Real *)s->dcol[0], (const Real *)s->dcol[1], (const Real *)s->dcol[2], s->n,
-            (Real *)s->cellsum, s->cellcount);
+            (Real *)s->cellsum, s->cellcount, s->nr, s->pitch, s->plane);
         FSIM_CUDA(cudaGetLastError());
         return (int)FSIM_OK;
     });
@@ -237,6 +242,7 @@ int launch_cellsum(fsim_sim *s)
         a.starts = s->starts;
         a.S = (Real *)s->cellsum;
         a.count = s->cellcount;
+        a.pitch = s->pitch; a.plane = s->plane;
         a.heavy_list = s->heavy_list; a.heavy_n = s->heavy_n;
         a.ncell = s->ncell_local;
         a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0;
@@ -258,19 +264,30 @@ int launch_cellsum(fsim_sim *s)
 }
 
 // ---- 11x11 stencil + normalise + running average -------------------------------------------
-// Tile: CT_I x CT_J output cells per block, one warp per output row.  The per-cell sums of the tile
-// and its 5-cell halo are staged in shared memory, one PLANE per channel (planes are padded so
-// that the 32 lanes of a warp -- 8 strips x 4 channels -- hit distinct banks).  A thread owns ONE
-// channel of a strip of 4 neighbouring cells: per stencil row pair it loads two 14-value windows
-// once and slides them over the 4 outputs, so shared-memory traffic is ~1/2 of the
-// thread-per-cell form and the kernel is bound by the fp64 pipe (the 40 taps that are exactly
-// zero are removed at compile time; mirror taps share one multiply).  Cells outside the grid read
-// as zero, which adds exact zeros: identical to skipping them.
+// Tile: CT_I x CT_J output cells per block.  The per-cell sums are stored planar (one plane per
+// channel, row pitch padded to 16 bytes), so ONE 3-D TMA box load (cp.async.bulk.tensor, mbarrier
+// completion) brings the tile and its 5-cell halo of all four channels into shared memory;
+// coordinates outside the tensor -- the grid edge -- are zero-filled by the TMA unit, which is
+// exactly "sprites are clipped at the target edge": adding exact zeros equals skipping the source.
+// A warp owns one channel of a 32-column x 4-row strip; a lane owns one column: per column offset
+// di it loads two vertical 14-value windows (columns -di and +di; consecutive lanes read
+// consecutive words, so no bank conflicts for any plane stride) and slides them over its 4
+// outputs.  The footprint is mirror-symmetric, so the up to four mirror sources of a weight are
+// added first and weighted once: classes di = 0..5 outer, dj = 0..5 inner, sources (-di,-dj),
+// (+di,-dj), (-di,+dj), (+di,+dj) -- the canonical order of the oracle; the 40 taps that are
+// exactly zero are removed at compile time.  107 fp64 operations per cell and channel: the kernel
+// is bound by the fp64 pipe.
 constexpr int CT_I = 32, CT_J = 16;             // output tile
 constexpr int CH = FSIM_SHAPE_MID;              // halo = 5
-constexpr int CS_I = CT_I + 2 * CH, CS_J = CT_J + 2 * CH;
-constexpr int CPLANE = ((CS_I * CS_J + 30) / 32) * 32 + 1;  // == 1 (mod 32): conflict-free planes
-constexpr int CSTRIP = 4;
+constexpr int CS_J = CT_J + 2 * CH;             // 26 rows
+// TMA needs the box START (innermost coordinate x element size) 16-byte aligned, and the box width
+// a multiple of 16 bytes: the box therefore begins CXOFF >= 5 cells left of the tile, CXOFF a
+// multiple of 2 reals (fp64) / 4 reals (fp32), and is CBOXW >= CXOFF + 32 + 5 wide.  (A start at
+// -5 cells is an "illegal instruction" fault: measured, tools/scratch/tma_test2.cu.)
+template <typename Real> struct ConvBox;
+template <> struct ConvBox<double> { static constexpr int XOFF = 6, W = 44; };
+template <> struct ConvBox<float> { static constexpr int XOFF = 8, W = 48; };
+constexpr int CSTRIP = 4;                       // output rows per thread
 constexpr int CWIN = CSTRIP + 2 * CH;           // 14
 
 __constant__ double c_shape_f64[FSIM_NSHAPE * FSIM_NSHAPE];
@@ -285,86 +302,137 @@ __host__ __device__ constexpr bool tap_nonzero(int ti, int tj)
     return (ti - CH) * (ti - CH) + (tj - CH) * (tj - CH) <= CH * CH;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 template <typename Real>
 struct ConvArgs {
-    const Real *S;
-    Real *mom, *norm, *avg;
-    int nr, rows;        // local table: nr x rows
-    int j0, j1;          // output rows [j0, j1) (owned rows, local index)
+    Real *mom, *norm, *avg;   // planar like S
+    int nr, pitch;
+    int64_t plane;
+    int j0, j1;               // output rows [j0, j1) (owned rows, local index)
 };
 
 template <typename Real>
-__global__ void __launch_bounds__(CT_J * 32) conv_kernel(const ConvArgs<Real> a)
+__global__ void __launch_bounds__(CT_J * 32)
+conv_kernel(const __grid_constant__ CUtensorMap tmS, const ConvArgs<Real> a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Real *sm = reinterpret_cast<Real *>(smem_raw);  // [4][CPLANE] with plane = [CS_J][CS_I]
+    constexpr int CBOXW = ConvBox<Real>::W, CXOFF = ConvBox<Real>::XOFF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Real *sm = reinterpret_cast<Real *>(smem_raw);  // [4][CS_J][CBOXW], written by the TMA unit
+    __shared__ __align__(8) unsigned long long bar;
     const int i0 = blockIdx.x * CT_I, jb = a.j0 + blockIdx.y * CT_J;
     const int tid = threadIdx.x;
-    for (int t = tid; t < CS_I * CS_J; t += CT_J * 32) {
-        const int li = t % CS_I, lj = t / CS_I;
-        const int gi = i0 + li - CH, gj = jb + lj - CH;
-        Real v0 = (Real)0, v1 = (Real)0, v2 = (Real)0, v3 = (Real)0;
-        if (gi >= 0 && gi < a.nr && gj >= 0 && gj < a.rows) {
-            const Real *p = a.S + 4 * ((size_t)gi + (size_t)gj * a.nr);
-            v0 = p[0]; v1 = p[1]; v2 = p[2]; v3 = p[3];
-        }
-        sm[t] = v0; sm[CPLANE + t] = v1; sm[2 * CPLANE + t] = v2; sm[3 * CPLANE + t] = v3;
+    constexpr uint32_t kBytes = 4u * CS_J * CBOXW * sizeof(Real);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(kBytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(sm)), "l"(reinterpret_cast<unsigned long long>(&tmS)), "r"(i0 - CXOFF), "r"(jb - CH), "r"(0),
+            "r"(smem_u32(&bar))
+            : "memory");
+    }
+    {
+        uint32_t done = 0;
+        for (uint32_t spin = 0; !done; ++spin) {
+            if (spin > (1u << 24)) __trap();  // a TMA that never completes must not hang the GPU
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done)
+                : "r"(smem_u32(&bar)), "r"(0u)
+                : "memory");
+        }
+    }
 
-    const int lane = tid & 31, lj = tid >> 5;   // warp = output row
-    const int c = lane & 3, strip = lane >> 2;  // channel, strip of 4 cells
-    const Real *plane = sm + c * CPLANE + strip * CSTRIP;
+    const int lane = tid & 31, w = tid >> 5;
+    const int c = w & 3, strip = w >> 2;  // channel; strip of CSTRIP output rows
+    const Real *col = sm + c * (CS_J * CBOXW) + (strip * CSTRIP) * CBOXW + lane + CXOFF;
     Real acc[CSTRIP];
 #pragma unroll
     for (int o = 0; o < CSTRIP; ++o) acc[o] = (Real)0;
-    // The footprint is mirror-symmetric (shape[5+di][5+dj] == shape[5-di][5+dj] == ...), so the up
-    // to four mirror sources of a weight are added first and weighted once: classes dj = 0..5
-    // outer, di = 0..5 inner, sources (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj) -- the canonical
-    // order of the oracle.  107 instead of 162 fp64 operations per cell and channel.
 #pragma unroll
-    for (int dj = 0; dj <= CH; ++dj) {
+    for (int di = 0; di <= CH; ++di) {
         Real wm[CWIN], wp[CWIN];
-        const Real *rm = plane + (lj + CH - dj) * CS_I, *rp = plane + (lj + CH + dj) * CS_I;
 #pragma unroll
         for (int k = 0; k < CWIN; ++k) {
-            wm[k] = rm[k];
-            wp[k] = dj ? rp[k] : (Real)0;
+            wm[k] = col[k * CBOXW - di];
+            wp[k] = di ? col[k * CBOXW + di] : (Real)0;
         }
 #pragma unroll
         for (int o = 0; o < CSTRIP; ++o) {
 #pragma unroll
-            for (int di = 0; di <= CH; ++di) {
+            for (int dj = 0; dj <= CH; ++dj) {
                 if (!tap_nonzero(CH + di, CH + dj)) continue;
-                Real sum = wm[o + CH - di];
-                if (di) sum = sum + wm[o + CH + di];
+                Real sum = wm[o + CH - dj];
+                if (di) sum = sum + wp[o + CH - dj];
                 if (dj) {
-                    sum = sum + wp[o + CH - di];
-                    if (di) sum = sum + wp[o + CH + di];
+                    sum = sum + wm[o + CH + dj];
+                    if (di) sum = sum + wp[o + CH + dj];
                 }
                 acc[o] = acc[o] + sum * shape_w<Real>((CH + di) + FSIM_NSHAPE * (CH + dj));
             }
         }
     }
 
-    const int gj = jb + lj;
+    // the four channels of a cell sit in four warps: exchange through shared memory (the tile is dead)
+    __syncthreads();
+    Real *ex = sm;  // [4][CT_J][CT_I]
+#pragma unroll
+    for (int o = 0; o < CSTRIP; ++o) ex[(c * CT_J + strip * CSTRIP + o) * CT_I + lane] = acc[o];
+    __syncthreads();
     const Real ratio = (Real)FSIM_EMA_RATIO;
+    const int gi = i0 + lane;
 #pragma unroll
     for (int o = 0; o < CSTRIP; ++o) {
-        const int gi = i0 + strip * CSTRIP + o;
-        const Real alpha = __shfl_sync(0xffffffffu, acc[o], lane | 3);  // channel 3 of the same cell
+        const int row = strip * CSTRIP + o, gj = jb + row;
         if (gi >= a.nr || gj >= a.j1) continue;
-        const size_t cell = (size_t)gi + (size_t)gj * a.nr;
-        if (a.mom) a.mom[4 * cell + c] = acc[o];
+        const Real alpha = ex[(3 * CT_J + row) * CT_I + lane];
+        const size_t idx = (size_t)c * a.plane + (size_t)gj * a.pitch + gi;
+        if (a.mom) a.mom[idx] = acc[o];
         // programNormalizeMoments01, empic.js:1055-1056
         const Real u = ((Real)gi + (Real)0.5) / (Real)a.nr;
         Real M = (Real)0;
         if (alpha > (Real)0) M = (c == 3) ? alpha : acc[o] / alpha;
         const Real v = (Real)FSIM_NORM_SCALE * M * (Real)FSIM_NORM_HALF / u;
-        if (a.norm) a.norm[4 * cell + c] = v;
-        Real *av = a.avg + 4 * cell + c;
-        *av = ratio * v + ((Real)1.0 - ratio) * (*av);  // avg_frag, empic.js:277
+        if (a.norm) a.norm[idx] = v;
+        a.avg[idx] = ratio * v + ((Real)1.0 - ratio) * a.avg[idx];  // avg_frag, empic.js:277
     }
+}
+
+// Tensor map of the planar per-cell sums: dims (i, j, channel), box (CBOXW, CS_J, 4), zero fill.
+// cuTensorMapEncodeTiled is taken from the driver through the runtime (no link against libcuda).
+int make_sums_tensor_map(fsim_sim *s)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    FSIM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return FSIM_ERR_CUDA;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)s->nr, (cuuint64_t)s->rows, 4};
+    const cuuint64_t gstride[2] = {(cuuint64_t)s->pitch * s->rs, (cuuint64_t)s->plane * s->rs};
+    const cuuint32_t box[3] = {(cuuint32_t)(s->prec == FSIM_F64 ? ConvBox<double>::W : ConvBox<float>::W), CS_J, 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    static_assert(sizeof(CUtensorMap) == sizeof(s->tm_sums), "tensor map storage");
+    const CUresult r = ((EncodeFn)fn)(reinterpret_cast<CUtensorMap *>(s->tm_sums),
+                                      s->prec == FSIM_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                      3, s->cellsum, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return FSIM_ERR_CUDA;
+    }
+    return FSIM_OK;
 }
 
 // shape64: footprint in double; shape32: the Float32Array variant (empic.js:950-971)
@@ -382,15 +450,14 @@ int launch_conv(fsim_sim *s)
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
         ConvArgs<Real> a;
-        a.S = (const Real *)s->cellsum;
         a.mom = (Real *)s->mom; a.norm = (Real *)s->norm; a.avg = (Real *)s->avg;
-        a.nr = s->nr; a.rows = s->rows;
+        a.nr = s->nr; a.pitch = s->pitch; a.plane = s->plane;
         a.j0 = s->own0 - s->row0; a.j1 = a.j0 + s->own_rows;
         dim3 block(CT_J * 32);
         dim3 grid((s->nr + CT_I - 1) / CT_I, (s->own_rows + CT_J - 1) / CT_J);
-        const size_t smem = sizeof(Real) * 4 * CPLANE;
+        const size_t smem = sizeof(Real) * 4 * CS_J * ConvBox<Real>::W;
         Bracket b(s, "conv");
-        conv_kernel<Real><<<grid, block, smem, s->stream>>>(a);
+        conv_kernel<Real><<<grid, block, smem, s->stream>>>(*reinterpret_cast<const CUtensorMap *>(s->tm_sums), a);
         FSIM_CUDA(cudaGetLastError());
         return (int)FSIM_OK;
     });

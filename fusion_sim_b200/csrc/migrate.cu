@@ -365,16 +365,75 @@ int fsim_halo_ptrs(fsim_sim *s, void **send_lo, void **send_hi, void **recv_lo, 
         set_error("fsim_halo_ptrs: null argument");
         return FSIM_ERR_INVALID;
     }
-    const size_t row_bytes = (size_t)s->nr * 4 * s->rs;
-    const int H = FSIM_SHAPE_MID;
-    unsigned char *S = (unsigned char *)s->cellsum;
+    FSIM_CUDA(cudaSetDevice(s->device));
+    const size_t each = (size_t)4 * FSIM_SHAPE_MID * s->nr * s->rs;
+    if (!s->halo_buf) {
+        FSIM_CUDA(cudaMalloc(&s->halo_buf, 4 * each));
+        FSIM_CUDA(cudaMemset(s->halo_buf, 0, 4 * each));
+    }
+    unsigned char *b = (unsigned char *)s->halo_buf;
     const int o0 = s->own0 - s->row0;  // first owned row, local index
-    *bytes_each = (int64_t)(H * row_bytes);
-    *send_lo = S + (size_t)o0 * row_bytes;
-    *send_hi = S + (size_t)(o0 + s->own_rows - H) * row_bytes;
-    *recv_lo = (o0 >= H) ? S + (size_t)(o0 - H) * row_bytes : nullptr;
-    *recv_hi = (o0 + s->own_rows + H <= s->rows) ? S + (size_t)(o0 + s->own_rows) * row_bytes : nullptr;
+    *bytes_each = (int64_t)each;
+    *send_lo = b;
+    *send_hi = b + each;
+    *recv_lo = (o0 >= FSIM_SHAPE_MID) ? b + 2 * each : nullptr;                           // a lower neighbour exists
+    *recv_hi = (o0 + s->own_rows + FSIM_SHAPE_MID <= s->rows) ? b + 3 * each : nullptr;   // an upper neighbour exists
     return FSIM_OK;
 }
 
 }  // extern "C"
+
+namespace fsim {
+
+// boundary rows of the planar per-cell sums <-> contiguous exchange buffers [channel][5 rows][nr]
+template <typename Real>
+__global__ void __launch_bounds__(256)
+halo_copy_kernel(Real *__restrict__ S, Real *__restrict__ buf, int nr, int pitch, int64_t plane, int row_first,
+                 int to_buffer)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)FSIM_SHAPE_MID * nr;
+    if (t >= 4 * per) return;
+    const int q = (int)(t / per), r = (int)((t % per) / nr), i = (int)(t % nr);
+    Real *cell = S + q * plane + (size_t)(row_first + r) * pitch + i;
+    if (to_buffer) buf[t] = *cell;
+    else *cell = buf[t];
+}
+
+static int halo_copy(fsim_sim *s, int which, int row_first, int to_buffer)
+{
+    const size_t each = (size_t)4 * FSIM_SHAPE_MID * s->nr * s->rs;
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        const int64_t n = 4ll * FSIM_SHAPE_MID * s->nr;
+        halo_copy_kernel<Real><<<grid_for(n, 256), 256, 0, s->stream>>>(
+            (Real *)s->cellsum, (Real *)((unsigned char *)s->halo_buf + which * each), s->nr, s->pitch, s->plane,
+            row_first, to_buffer);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    });
+}
+
+int launch_halo_pack(fsim_sim *s)
+{
+    void *p[4];
+    int64_t n;
+    FSIM_TRY(fsim_halo_ptrs(s, &p[0], &p[1], &p[2], &p[3], &n));
+    const int o0 = s->own0 - s->row0;
+    FSIM_TRY(halo_copy(s, 0, o0, 1));                                   // first 5 owned rows -> send_lo
+    return halo_copy(s, 1, o0 + s->own_rows - FSIM_SHAPE_MID, 1);       // last 5 owned rows  -> send_hi
+}
+
+int launch_halo_unpack(fsim_sim *s)
+{
+    void *p[4];
+    int64_t n;
+    FSIM_TRY(fsim_halo_ptrs(s, &p[0], &p[1], &p[2], &p[3], &n));
+    const int o0 = s->own0 - s->row0;
+    if (p[2]) FSIM_TRY(halo_copy(s, 2, o0 - FSIM_SHAPE_MID, 0));        // recv_lo -> 5 rows below the slab
+    if (p[3]) FSIM_TRY(halo_copy(s, 3, o0 + s->own_rows, 0));           // recv_hi -> 5 rows above the slab
+    return FSIM_OK;
+}
+
+}  // namespace fsim

@@ -23,8 +23,8 @@ __device__ __forceinline__ Real quant8(Real v)
 
 template <typename Real>
 __global__ void __launch_bounds__(256)
-render_kernel(const Real *__restrict__ B, const Real *__restrict__ avg, uint8_t *__restrict__ rgba,
-              int nr, int nz, int row0, int own0, int own_rows)
+render_kernel(const Real *__restrict__ B, const Real *__restrict__ avg_alpha, int pitch,
+              uint8_t *__restrict__ rgba, int nr, int nz, int row0, int own0, int own_rows)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)nr * own_rows) return;
@@ -40,7 +40,7 @@ render_kernel(const Real *__restrict__ B, const Real *__restrict__ avg, uint8_t 
     c1[1] = mag * dx;
     c1[2] = mag * ((mx < (Real)0) ? -mx : mx);
     c1[3] = (Real)1.0;
-    const Real a = avg[4 * c + 3];
+    const Real a = avg_alpha[(size_t)(j - row0) * pitch + i];  // alpha plane of the running average
     const Real sc = (Real)FSIM_RENDER_DENSITY * a;
     const Real src[4] = {sc, sc, sc, (Real)FSIM_RENDER_DENSITY * (Real)1.0};
     const Real sa = clamp01(src[3]);
@@ -61,8 +61,8 @@ int launch_render(fsim_sim *s, uint8_t *dev_rgba)
         using Real = decltype(tag);
         Bracket b(s, "render");
         render_kernel<Real><<<grid_for((int64_t)s->nr * s->own_rows, 256), 256, 0, s->stream>>>(
-            (const Real *)s->B, (const Real *)s->avg, dev_rgba, s->nr, s->nz, s->row0, s->own0,
-            s->own_rows);
+            (const Real *)s->B, (const Real *)s->avg + 3 * s->plane, s->pitch, dev_rgba, s->nr, s->nz, s->row0,
+            s->own0, s->own_rows);
         FSIM_CUDA(cudaGetLastError());
         return (int)FSIM_OK;
     });

@@ -375,7 +375,7 @@ void ORC(orc_cell_sums_mt)(int64_t n, const REAL *pos, const REAL *vel, int64_t 
  * texels with d > 5 are exactly 0 and are skipped); sources outside the grid do not exist (sprites
  * are clipped at the target edge).  The footprint is mirror-symmetric, shape[5+di,5+dj] =
  * shape[5-di,5+dj] = shape[5+di,5-dj] = shape[5-di,5-dj] bit for bit, so the (up to four) mirror
- * sources of a weight are added first and weighted once.  Fixed order: dj = 0..5 outer, di = 0..5
+ * sources of a weight are added first and weighted once.  Fixed order: di = 0..5 outer, dj = 0..5
  * inner; inside a class (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj), duplicates (di or dj = 0) once. */
 void ORC(orc_convolve)(int64_t nr, int64_t nz, const REAL *S, const REAL *shape,
                        REAL *mom, int nthreads)
@@ -385,8 +385,8 @@ void ORC(orc_convolve)(int64_t nr, int64_t nz, const REAL *S, const REAL *shape,
     for (j = 0; j < nz; ++j)
         for (int64_t i = 0; i < nr; ++i) {
             REAL acc[4] = {RC(0.0), RC(0.0), RC(0.0), RC(0.0)};
-            for (int dj = 0; dj <= FSIM_SHAPE_MID; ++dj)
-                for (int di = 0; di <= FSIM_SHAPE_MID; ++di) {
+            for (int di = 0; di <= FSIM_SHAPE_MID; ++di)
+                for (int dj = 0; dj <= FSIM_SHAPE_MID; ++dj) {
                     REAL w = shape[(FSIM_SHAPE_MID + di) + FSIM_NSHAPE * (FSIM_SHAPE_MID + dj)];
                     if (w == RC(0.0)) continue;
                     REAL sum[4] = {RC(0.0), RC(0.0), RC(0.0), RC(0.0)};

@@ -147,7 +147,7 @@ def cell_sums(pos, vel, nr, nz):
 
 def convolve(S, shape, nr, nz):
     """moments01 = S (*) shape with the mirror sources of each weight added first (the footprint is
-    mirror-symmetric): classes dj = 0..5 outer, di = 0..5 inner; inside a class the sources
+    mirror-symmetric): classes di = 0..5 outer, dj = 0..5 inner; inside a class the sources
     (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj); zero weights skipped; sources outside the grid are
     absent (padding with exact zeros is the same arithmetic)."""
     S2 = np.zeros((nz + 10, nr + 10, 4), S.dtype)
@@ -157,8 +157,8 @@ def convolve(S, shape, nr, nz):
     def src(di, dj):
         return S2[5 + dj:5 + dj + nz, 5 + di:5 + di + nr]
 
-    for dj in range(6):
-        for di in range(6):
+    for di in range(6):
+        for dj in range(6):
             w = shape[(5 + di) + 11 * (5 + dj)]
             if w == 0:
                 continue
