@@ -160,7 +160,8 @@ def cpu_baseline(workload, precision, steps, target_s=12.0, threads=None):
     o = OraclePusher(sc["spec"], nthreads=threads)
     rng = np.random.Generator(np.random.PCG64(5))
     sc["rand"] = rng.random((o.n, 4))
-    sc["entropy"] = rng.random((1024 * 1024, 4))
+    from fusion_sim_b200.scenes import entropy_table
+    sc["entropy"] = entropy_table(rng)
     apply_scene(o, sc)
 
     def frame():

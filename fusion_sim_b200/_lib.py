@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfusionsim.so")
+# FSIM_LIB_PATH: A/B measurement of another build of the same library (tools/ab_build.sh); never a fallback
+LIB_PATH = os.environ.get("FSIM_LIB_PATH") or os.path.join(_HERE, "csrc", "libfusionsim.so")
 
 FSIM_F64, FSIM_F32 = 0, 1
 FLAG_CORRECTED_PREA, FLAG_KEEP_MOMENTS, FLAG_ATOMIC_DEPOSIT = 1, 2, 4
@@ -97,6 +98,7 @@ _SIGS = {
     "fsim_jacobi_get_result": (C.c_int, [_P, _P]),
     "fsim_jacobi_launch_count": (C.c_int64, [_P]),
     "fsim_jacobi_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "fsim_solve_fields": (C.c_int, [_P, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_density_begin": (C.c_int, [_P]),
     "fsim_density_end": (C.c_int, [_P]),
 }

@@ -417,6 +417,7 @@ static void free_all(fsim_sim *s)
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
                     s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf};
     for (void *p : ptrs) cudaFree(p);
+    cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef);
     for (auto &kv : s->timers)
         for (auto &pe : kv.second.pending) {
             cudaEventDestroy(pe.first);
@@ -716,6 +717,27 @@ int fsim_precalc(fsim_sim *s)
     return FSIM_OK;
 }
 
+// EXTENSION: charge density from the deposited moments -> weighted-Jacobi sweeps on
+// the potential (warm start) -> E = -grad(phi) -> precalc().  Specification:
+// include/fusionsim.h (fsim_solve_fields).
+int fsim_solve_fields(fsim_sim *s, double macro_weight, int32_t sweeps, double omega, int32_t source)
+{
+    FSIM_TRY(check(s));
+    if (s->slab) return fail(FSIM_ERR_UNSUPPORTED, "solveFields: not available in slab (multi-GPU) mode yet");
+    if (sweeps < 0 || !(omega > 0.0 && omega < 2.0)) return fail(FSIM_ERR_INVALID, ".sweeps/.omega <- out of range");
+    if (source != 0 && source != 1) return fail(FSIM_ERR_INVALID, ".source <- 0 (running average) or 1 (instantaneous)");
+    if (source == 1 && !s->norm)
+        return fail(FSIM_ERR_STATE, "solveFields: the instantaneous density needs FSIM_FLAG_KEEP_MOMENTS");
+    FSIM_TRY(finish(s, ensure_fieldsolve(s)));
+    const double dr = s->spec.radius / (double)s->nr, dz = s->spec.height / (double)s->nz;
+    const double rho_scale = s->spec.particle_charge * macro_weight / (FSIM_PI * s->spec.radius * dr * dz * FSIM_EPS0);
+    const char *dens = (const char *)(source ? s->norm : s->avg) + s->rs * 3 * (size_t)s->plane;  // channel a
+    FSIM_TRY(finish(s, launch_field_solve(s, dens, rho_scale, sweeps, omega)));
+    FSIM_TRY(finish(s, launch_precalc(s)));
+    s->have_precalc = true;
+    return FSIM_OK;
+}
+
 // Physical re-sort of the particle storage every `sort_interval` frames (default 8): between
 // re-sorts density() bins through a 4-byte index list and the push tolerates the slowly decaying
 // order (particles move a fraction of a cell per half-step).
@@ -941,6 +963,12 @@ int fsim_get_field(fsim_sim *s, const char *name, double *out)
     if (n == "moments01" || n == "moments01_norm") {
         if (!s->mom) return fail(FSIM_ERR_STATE, "moments01/moments01_norm are kept only with FSIM_FLAG_KEEP_MOMENTS");
         return finish(s, planar_out(s, n == "moments01" ? s->mom : s->norm, out));
+    }
+    if (n == "phi" || n == "rho_src") {
+        if (!s->phi[0]) return fail(FSIM_ERR_STATE, "phi/rho_src exist after the first solveFields()");
+        FSIM_TRY(finish(s, ensure_stage(s, sizeof(double) * nc)));
+        FSIM_TRY(finish(s, launch_plane_out(s, n == "phi" ? s->phi[s->phi_cur] : s->rho_src, (double *)s->stage)));
+        return finish(s, stage_out(s, out, sizeof(double) * nc));
     }
     if (n == "inv_cdf") return finish(s, table_out(s, s->invcdf, out, 2ll * FSIM_N_INVCDF * FSIM_N_INVCDF));
     if (n == "entropy") return finish(s, table_out(s, s->entropy, out, 4ll * FSIM_N_ENTROPY * FSIM_N_ENTROPY));

@@ -119,6 +119,14 @@ struct fsim_sim {
     uint32_t *heavy_n = nullptr;
     uint32_t *oob = nullptr;     // particles whose gather row fell outside the local table
 
+    // EXTENSION: self-consistent field solve (fieldsolve.cu), allocated at the first fsim_solve_fields()
+    void *phi[2] = {};           // potential, planar [rows][pitch], ping-pong
+    int phi_cur = 0;
+    void *rho_src = nullptr;     // rho/eps0, planar
+    void *relax_coef = nullptr;  // [nr][4] Jacobi coefficients cE cW cZ cB
+    alignas(64) unsigned char tm_phi[2][128] = {};  // CUtensorMaps of phi[0], phi[1], rho_src
+    alignas(64) unsigned char tm_src[128] = {};
+
     // staging
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -279,5 +287,8 @@ int launch_expand_records(fsim_sim *s, double *dev_out);  // [cells][12] R1 R2 R
 int launch_add_loop(fsim_sim *s, double R, double Z, double I);
 int launch_add_uniform(fsim_sim *s, int kind, double val);
 int launch_render(fsim_sim *s, uint8_t *dev_rgba);
+int ensure_fieldsolve(fsim_sim *s);
+int launch_field_solve(fsim_sim *s, const void *dens_a, double rho_scale, int sweeps, double omega);
+int launch_plane_out(fsim_sim *s, const void *plane, double *dev_out);
 
 }  // namespace fsim

@@ -103,33 +103,24 @@ __device__ __forceinline__ void ld_ro2(const float *p, float &a, float &b)
     a = t.x; b = t.y;
 }
 
-// NH = number of leap-frog half-steps done per launch while the particle sits in registers.
+// The particle state a thread carries: V consecutive slots of every array.
+template <typename Real, int V>
+struct Slots {
+    Real x[V], y[V], z[V], vx[V], vy[V], vz[V], q0[V], q1[V], q2[V], q3[V];
+    Real rcur[V];  // sqrt(x*x + y*y) of the current position (:755; reused by the next half-step)
+    uint8_t al[V];
+};
+
+// NH leap-frog half-steps of the V particles in `t`, entirely in registers.
 // out.step() is two half-steps with nothing in between that couples particles (static fields), so
 // NH = 2 performs the B-pass and the A-pass of empic.js:1438-1467 in one sweep over HBM: state
 // read once, written once.  Same operations in the same order, hence the same bits.
-template <typename Real, int V, int BLOCK, int MINB, int NH>
-__global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> a)
+template <typename Real, int V, int NH>
+__device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p0, Slots<Real, V> &t)
 {
-    // no early exit: the arrays are padded past n (common.cuh), the whole warp stays converged for
-    // the warp-aggregated histogram; side effects of slots >= n are masked.
-    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-
-    Real x[V], y[V], z[V], vx[V], vy[V], vz[V], q0[V], q1[V], q2[V], q3[V];
-    uint8_t al[V];
-    ld_stream<Real, V>(a.a[AQ2] + p0, q2);
-    ld_stream<Real, V>(a.a[AQ3] + p0, q3);
-    ld_stream<Real, V>(a.a[AX] + p0, x);
-    ld_stream<Real, V>(a.a[AY] + p0, y);
-    ld_stream<Real, V>(a.a[AZ] + p0, z);
-    ld_stream<Real, V>(a.a[AQ0] + p0, q0);
-    ld_stream<Real, V>(a.a[AQ1] + p0, q1);
-    ld_stream<Real, V>(a.a[AVX] + p0, vx);
-    ld_stream<Real, V>(a.a[AVY] + p0, vy);
-    ld_stream<Real, V>(a.a[AVZ] + p0, vz);
-#pragma unroll
-    for (int k = 0; k < V; ++k) al[k] = a.alive[p0 + k];
-
-    Real rcur[V];  // sqrt(x*x + y*y) of the current position (:755; reused by the next half-step)
+    Real (&x)[V] = t.x, (&y)[V] = t.y, (&z)[V] = t.z, (&vx)[V] = t.vx, (&vy)[V] = t.vy, (&vz)[V] = t.vz;
+    Real (&q0)[V] = t.q0, (&q1)[V] = t.q1, (&q2)[V] = t.q2, (&q3)[V] = t.q3, (&rcur)[V] = t.rcur;
+    uint8_t (&al)[V] = t.al;
 #pragma unroll
     for (int k = 0; k < V; ++k) rcur[k] = fsqrt(x[k] * x[k] + y[k] * y[k]);
 
@@ -210,49 +201,86 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
         }
     }
 
-    st_stream<Real, V>(a.a[AX] + p0, x);
-    st_stream<Real, V>(a.a[AY] + p0, y);
-    st_stream<Real, V>(a.a[AZ] + p0, z);
-    st_stream<Real, V>(a.a[AVX] + p0, vx);
-    st_stream<Real, V>(a.a[AVY] + p0, vy);
-    st_stream<Real, V>(a.a[AVZ] + p0, vz);
-    st_stream<Real, V>(a.a[AQ0] + p0, q0);
-    st_stream<Real, V>(a.a[AQ1] + p0, q1);
-    st_stream<Real, V>(a.a[AQ2] + p0, q2);
-    st_stream<Real, V>(a.a[AQ3] + p0, q3);
-#pragma unroll
-    for (int k = 0; k < V; ++k) a.alive[p0 + k] = al[k];
+}
 
-    if (a.key) {  // deposit prepass on the NEW state (what density() will see): sort key, sprite
-                  // colour and the warp-aggregated histogram of the counting sort
-        const int lane = threadIdx.x & 31;
-        uint32_t newcell[V];
-        Real col[3][V];
+// Deposit prepass on the NEW state (what density() will see): sort key, sprite colour and the
+// warp-aggregated histogram of the counting sort.  Whole warps must call this converged.
+template <typename Real, int V>
+__device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int64_t p0, const Slots<Real, V> &t)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t newcell[V];
+    Real col[3][V];
 #pragma unroll
-        for (int k = 0; k < V; ++k)
-            newcell[k] = sprite_key_colour<Real>(x[k], y[k], z[k], rcur[k], vx[k], vy[k], vz[k], a.nr, a.nz,
-                                                 a.row0, a.rows, a.own_lo, a.own_hi, col[0][k], col[1][k], col[2][k]);
+    for (int k = 0; k < V; ++k)
+        newcell[k] = sprite_key_colour<Real>(t.x[k], t.y[k], t.z[k], t.rcur[k], t.vx[k], t.vy[k], t.vz[k], a.nr, a.nz,
+                                             a.row0, a.rows, a.own_lo, a.own_hi, col[0][k], col[1][k], col[2][k]);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);
+    for (int q = 0; q < 3; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const bool valid = p0 + k < a.n;
-            const uint32_t c = valid ? (newcell[k] & KEY_MASK) : 0xffffffffu;
-            if (valid) a.key[p0 + k] = newcell[k];
-            if (valid && a.leavers) {
-                const int gj = tex_idx(z[k], a.nz);
-                if (gj < a.own0 || gj >= a.own0 + a.own_rows) a.leavers[atomicAdd(a.nleavers, 1u)] = (uint32_t)(p0 + k);
-            }
-            int leader;
-            uint32_t len, rank;
-            warp_runs(c, lane, leader, len, rank);
-            if (valid && rank == 0) atomicAdd(a.counts + c, len);
+    for (int k = 0; k < V; ++k) {
+        const bool valid = p0 + k < a.n;
+        const uint32_t c = valid ? (newcell[k] & KEY_MASK) : 0xffffffffu;
+        if (valid) a.key[p0 + k] = newcell[k];
+        if (valid && a.leavers) {
+            const int gj = tex_idx(t.z[k], a.nz);
+            if (gj < a.own0 || gj >= a.own0 + a.own_rows) a.leavers[atomicAdd(a.nleavers, 1u)] = (uint32_t)(p0 + k);
         }
+        int leader;
+        uint32_t len, rank;
+        warp_runs(c, lane, leader, len, rank);
+        if (valid && rank == 0) atomicAdd(a.counts + c, len);
     }
 }
 
-template <typename Real, int V, int BLOCK, int MINB>
-static int push_impl(fsim_sim *s, bool with_hist, int nhalf)
+template <typename Real, int V>
+__device__ __forceinline__ void store_slots(const PushArgs<Real> &a, const int64_t p0, const Slots<Real, V> &t)
+{
+    st_stream<Real, V>(a.a[AX] + p0, t.x);
+    st_stream<Real, V>(a.a[AY] + p0, t.y);
+    st_stream<Real, V>(a.a[AZ] + p0, t.z);
+    st_stream<Real, V>(a.a[AVX] + p0, t.vx);
+    st_stream<Real, V>(a.a[AVY] + p0, t.vy);
+    st_stream<Real, V>(a.a[AVZ] + p0, t.vz);
+    st_stream<Real, V>(a.a[AQ0] + p0, t.q0);
+    st_stream<Real, V>(a.a[AQ1] + p0, t.q1);
+    st_stream<Real, V>(a.a[AQ2] + p0, t.q2);
+    st_stream<Real, V>(a.a[AQ3] + p0, t.q3);
+#pragma unroll
+    for (int k = 0; k < V; ++k) a.alive[p0 + k] = t.al[k];
+}
+
+// One thread = V consecutive particles, state loaded straight into registers.  (A persistent
+// variant that prefetched the next tile's state into shared memory with cp.async -- no registers
+// held while the streaming loads fly -- was measured 18 % SLOWER on B200: the sweep is not bound by
+// the latency of the streaming loads but by L1TEX wavefronts and dependent fp64 chains, and the
+// detour through shared memory adds to both.  DESIGN.md section 4.)
+template <typename Real, int V, int BLOCK, int MINB, int NH>
+__global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> a)
+{
+    // no early exit: the arrays are padded past n (common.cuh), the whole warp stays converged for
+    // the warp-aggregated histogram; side effects of slots >= n are masked.
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    Slots<Real, V> t;
+    ld_stream<Real, V>(a.a[AQ2] + p0, t.q2);
+    ld_stream<Real, V>(a.a[AQ3] + p0, t.q3);
+    ld_stream<Real, V>(a.a[AX] + p0, t.x);
+    ld_stream<Real, V>(a.a[AY] + p0, t.y);
+    ld_stream<Real, V>(a.a[AZ] + p0, t.z);
+    ld_stream<Real, V>(a.a[AQ0] + p0, t.q0);
+    ld_stream<Real, V>(a.a[AQ1] + p0, t.q1);
+    ld_stream<Real, V>(a.a[AVX] + p0, t.vx);
+    ld_stream<Real, V>(a.a[AVY] + p0, t.vy);
+    ld_stream<Real, V>(a.a[AVZ] + p0, t.vz);
+#pragma unroll
+    for (int k = 0; k < V; ++k) t.al[k] = a.alive[p0 + k];
+    advance<Real, V, NH>(a, p0, t);
+    store_slots<Real, V>(a, p0, t);
+    if (a.key) emit_prepass<Real, V>(a, p0, t);
+}
+
+template <typename Real>
+static PushArgs<Real> make_args(fsim_sim *s, bool with_hist)
 {
     PushArgs<Real> a;
     for (int k = 0; k < NPART_ARRAYS; ++k) a.a[k] = (Real *)s->part[s->cur][k];
@@ -273,9 +301,13 @@ static int push_impl(fsim_sim *s, bool with_hist, int nhalf)
     a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
     a.sf = (Real)s->step_factor;
     a.h = (Real)s->h; a.k13 = (Real)s->k13; a.k31 = (Real)s->k31;
+    return a;
+}
+
+template <typename Real, int V, int BLOCK, int MINB>
+static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf)
+{
     const int64_t nvec = (s->n + V - 1) / V;
-    if (nvec == 0) return FSIM_OK;
-    Bracket b(s, nhalf == 2 ? "push2" : "push");
     if (nhalf == 2)
         push_kernel<Real, V, BLOCK, MINB, 2><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     else
@@ -289,7 +321,7 @@ static int push_impl(fsim_sim *s, bool with_hist, int nhalf)
 static int push_variant()
 {
     const char *e = getenv("FSIM_PUSH_VARIANT");  // read per launch: tools/tune.py sweeps it in-process
-    return e ? atoi(e) : 4;  // measured fastest on B200 for fp64 (profiles/r1_tuning.md)
+    return e ? atoi(e) : 4;  // 4: 64-bit loads, 256 threads x 4 blocks per SM -- measured fastest on B200 for fp64
 }
 
 int launch_push(fsim_sim *s, bool with_hist, int nhalf)
@@ -302,14 +334,17 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf)
     int rc = dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
         constexpr int V = 16 / sizeof(Real);  // 128-bit loads and stores
+        if (s->n == 0) return (int)FSIM_OK;
+        const PushArgs<Real> a = make_args<Real>(s, with_hist);
+        Bracket b(s, nhalf == 2 ? "push2" : "push");
         switch (push_variant()) {
-        case 1: return push_impl<Real, V, 128, 4>(s, with_hist, nhalf);
-        case 2: return push_impl<Real, V, 256, 3>(s, with_hist, nhalf);
-        case 3: return push_impl<Real, V / 2, 256, 3>(s, with_hist, nhalf);
-        case 4: return push_impl<Real, V / 2, 256, 4>(s, with_hist, nhalf);
-        case 5: return push_impl<Real, V / 2, 128, 6>(s, with_hist, nhalf);
-        case 6: return push_impl<Real, V / 2, 512, 2>(s, with_hist, nhalf);
-        default: return push_impl<Real, V, 256, 2>(s, with_hist, nhalf);
+        case 1: return push_impl<Real, V, 128, 4>(s, a, nhalf);
+        case 2: return push_impl<Real, V, 256, 3>(s, a, nhalf);
+        case 3: return push_impl<Real, V / 2, 256, 3>(s, a, nhalf);
+        case 5: return push_impl<Real, V / 2, 128, 6>(s, a, nhalf);
+        case 6: return push_impl<Real, V / 2, 512, 2>(s, a, nhalf);
+        case 7: return push_impl<Real, V, 256, 2>(s, a, nhalf);
+        default: return push_impl<Real, V / 2, 256, 4>(s, a, nhalf);
         }
     });
     s->binned = false;

@@ -151,6 +151,18 @@ class CylindricalParticlePusher:
     def density(self):
         check(lib().fsim_density(self._h))
 
+    def solveFields(self, value: dict):
+        """EXTENSION (no reference counterpart): close the PIC loop.
+        value = {macro_weight, sweeps, omega=1, source="avg"|"instant"}: charge density from the
+        deposited moments -> `sweeps` weighted-Jacobi sweeps on the potential (warm start) ->
+        E = -grad(phi) -> precalc().  Specification: include/fusionsim.h (fsim_solve_fields)."""
+        validate_object(value, {"macro_weight": "number", "sweeps": "number"})
+        source = value.get("source", "avg")
+        if source not in ("avg", "instant"):
+            raise Error(".source <- 'avg' or 'instant'", _lib.ERR_INVALID)
+        check(lib().fsim_solve_fields(self._h, float(value["macro_weight"]), int(value["sweeps"]),
+                                      float(value.get("omega", 1.0)), 0 if source == "avg" else 1))
+
     def render(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
             out = np.empty((self.nz, self.nr, 4), np.uint8)
@@ -203,7 +215,8 @@ class CylindricalParticlePusher:
             return self._get(lib().fsim_get_sink_mask, (self.nr * self.nz,), np.uint8)
         shape = {"E": (nc, 3), "B": (nc, 3), "R1": (nc, 3), "R2": (nc, 3), "R3": (nc, 3), "A": (nc, 3),
                  "cell_sums": (nc, 4), "moments01": (nc, 4), "moments01_norm": (nc, 4),
-                 "moments01_avg": (nc, 4), "inv_cdf": (512 * 512, 2), "entropy": (1024 * 1024, 4)}.get(name)
+                 "moments01_avg": (nc, 4), "inv_cdf": (512 * 512, 2), "entropy": (1024 * 1024, 4),
+                 "phi": (nc,), "rho_src": (nc,)}.get(name)
         if shape is None:
             raise Error("unknown field name: " + name, _lib.ERR_INVALID)
         out = np.empty(shape, np.float64)

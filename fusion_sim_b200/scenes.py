@@ -4,7 +4,8 @@ relatives (configs C2-C5 of BASELINE.json), from a seeded generator.
 C1 restates the scene of public/javascripts/fusionsim.js:72-148 exactly; only the random source
 changes (the reference uses unseeded Math.random / window.crypto):
 NumPy PCG64(seed) draws, in this order, positions (3N), velocities (3N), rand (4N) and the
-entropy table (4*1024^2), all uniform in [0,1).
+entropy table (4*1024^2); positions, velocities and rand uniform in [0,1), the entropy table as
+the reference builds it (uint32 / 0xFFFFFFFF stored into a Float32Array, empic.js:143-155).
 """
 from __future__ import annotations
 
@@ -16,11 +17,18 @@ C1_SPEC = dict(radius=1, height=2, nr=400, nz=800, dt=2e-9, nparticles=400,
                particle_mass=1.67e-27, particle_charge=1.602e-19)  # fusionsim.js:74-83
 
 
+def entropy_table(rng):
+    """[1024*1024][4] entropy texels, empic.js:143-155: `random_bytes[k] / 0xFFFFFFFF` stored into a
+    Float32Array -- every entry is exactly a float (the fp64 engine then gathers a half-size copy)."""
+    u = rng.integers(0, 1 << 32, size=(N_ENTROPY * N_ENTROPY, 4), dtype=np.uint64)
+    return (u.astype(np.float64) / float(0xFFFFFFFF)).astype(np.float32).astype(np.float64)
+
+
 def seeded_rand_entropy(seed: int, n: int):
     """rand [n][4] in [0,1) and the entropy table [1024*1024][4] for `spec.seed`."""
     rng = np.random.Generator(np.random.PCG64(seed))
     rand = rng.random((n, 4))
-    entropy = rng.random((N_ENTROPY * N_ENTROPY, 4))
+    entropy = entropy_table(rng)
     return rand, entropy
 
 
@@ -44,7 +52,7 @@ def c1_scene(seed: int = 12345, spec: dict | None = None):
     up = rng.random((n, 3))
     uv = rng.random((n, 3))
     rand = rng.random((n, 4))
-    entropy = rng.random((N_ENTROPY * N_ENTROPY, 4))
+    entropy = entropy_table(rng)
     # fusionsim.js:126-127
     position = 0.2 * (up - 0.5)
     position[:, 2] += 1

@@ -27,6 +27,10 @@
 #define FSIM_LOOP_FAR         2.0              /* empic.js:371 near/far table switch      */
 #define FSIM_RENDER_DENSITY   0.5              /* empic.js:1105                           */
 
+/* EXTENSION (no reference counterpart): self-consistent field solve */
+#define FSIM_EPS0             8.8541878128e-12 /* vacuum permittivity (F/m), CODATA 2018  */
+#define FSIM_PI               3.14159265358979323846
+
 /* per-cell record produced by precalc(): rows of the Boris matrix and the
  * half-kick constant, 12 reals per cell: R1.xyz R2.xyz R3.xyz A.xyz
  * (empic.js:499-502 keeps them in four RGBA textures).                        */

@@ -114,6 +114,25 @@ int fsim_render_rgba8_async(fsim_sim *sim, uint8_t *rgba);
 int fsim_sort(fsim_sim *sim);      /* extension: re-sort particle storage by cell now          */
 int fsim_sync(fsim_sim *sim);      /* wait for the handle's stream                             */
 
+/* ---- EXTENSION, no reference counterpart: self-consistent
+ * electrostatic field solve.  The reference pushes test particles in static fields; this closes
+ * the loop: rho = q * macro_weight * n from the deposited density (source 0: the running average
+ * moments01_avg.a, 1: moments01_norm.a of the last density(), needs FSIM_FLAG_KEEP_MOMENTS),
+ * `sweeps` weighted-Jacobi sweeps (the iteration of matrix_webgl.makeSORIterative,
+ * matrix_webgl.js:224-300) on the 5-point cylindrical Poisson operator with grounded walls, warm
+ * started from the previous potential, E = -grad(phi) (overwrites E), then precalc().
+ *   cells (i,j) centred at r = (i+.5) dr, z = (j+.5) dz, dr = radius/nr, dz = height/nz;
+ *   src = (q macro_weight / (pi radius dr dz eps0)) * density.a;
+ *   per-column coefficients in host fp64, rounded to the engine's real type:
+ *     aE = (i+1)/((i+.5) dr^2), aW = i/((i+.5) dr^2), aZ = 1/dz^2, aC = aE + aW + 2 aZ,
+ *     cE = aE/aC, cW = aW/aC, cZ = aZ/aC, cB = 1/aC     (finite volumes on rings; no axis ghost);
+ *   one sweep, in exactly this order, no fused multiply-add, ghost cells beyond r = radius,
+ *   z = 0 and z = height hold phi = 0:
+ *     t = ((cE phi_E + cW phi_W) + cZ (phi_N + phi_S)) + cB src;  phi' = omega t + (1 - omega) phi;
+ *   E_r = -((phi_E - phi_W) / (2 dr)) with phi_W := phi at i = 0, E_z = -((phi_N - phi_S) / (2 dz))
+ *   (both as a multiplication by the host-computed reciprocal), E_theta = 0.            Single GPU. */
+int fsim_solve_fields(fsim_sim *sim, double macro_weight, int32_t sweeps, double omega, int32_t source);
+
 /* ---- accessors (extension; the reference exposes none) ---------- */
 int64_t fsim_particle_count(const fsim_sim *sim);
 int64_t fsim_local_cells(const fsim_sim *sim); /* nr * (slab_rows + 2*halo_rows) or nr*nz      */
@@ -123,7 +142,8 @@ int fsim_get_rand(fsim_sim *sim, double *out);      /* [N][4]                   
 int fsim_get_ids(fsim_sim *sim, uint64_t *out);     /* [N] ids in STORAGE order                 */
 int fsim_get_cells(fsim_sim *sim, int64_t *out);    /* [N] gather cell i+j*nr of each particle  */
 /* name: "E","B","R1","R2","R3","A" -> [cells][3]; "cell_sums","moments01","moments01_norm",
- * "moments01_avg" -> [cells][4]; "inv_cdf" -> [512*512][2]; "entropy" -> [1024*1024][4]      */
+ * "moments01_avg" -> [cells][4]; "inv_cdf" -> [512*512][2]; "entropy" -> [1024*1024][4];
+ * "phi", "rho_src" -> [cells] (after fsim_solve_fields)                                          */
 int fsim_get_field(fsim_sim *sim, const char *name, double *out);
 int fsim_get_cell_count(fsim_sim *sim, uint32_t *out); /* [cells] particles deposited per cell   */
 int fsim_get_sink_mask(fsim_sim *sim, uint8_t *out);   /* [nr*nz] 1 = keep, 0 = absorb           */

@@ -46,6 +46,32 @@ static inline float orc_floor_f32(float x) { return floorf(x); }
 #undef REAL
 #undef SFX
 
+/* EXTENSION: self-consistent electrostatic field solve ("next" row N4 of SURVEY.md section 8f) */
+#define REAL double
+#define SFX f64
+#include "fsim_oracle_fields_impl.h"
+#undef REAL
+#undef SFX
+#define REAL float
+#define SFX f32
+#include "fsim_oracle_fields_impl.h"
+#undef REAL
+#undef SFX
+
+/* per-column Jacobi coefficients [nr][4] = cE cW cZ cB (header of fsim_oracle_fields_impl.h) */
+void orc_relax_coeffs(int64_t nr, double dr, double dz, double *out)
+{
+    for (int64_t i = 0; i < nr; ++i) {
+        const double rc = ((double)i + 0.5) * dr * dr;
+        const double aE = ((double)i + 1.0) / rc, aW = (double)i / rc, aZ = 1.0 / (dz * dz);
+        const double aC = aE + aW + 2.0 * aZ;
+        out[4 * i] = aE / aC;
+        out[4 * i + 1] = aW / aC;
+        out[4 * i + 2] = aZ / aC;
+        out[4 * i + 3] = 1.0 / aC;
+    }
+}
+
 /* N(num) = num.toFixed(20) (empic.js:23-25) parsed back by the GLSL compiler. */
 double orc_tofixed20(double x)
 {

@@ -186,3 +186,44 @@ def normalize_ema(mom, avg, nr, nz):
         norm = T(1000.0) * M * T(0.5) / u[:, None]
         new_avg = T(0.01) * norm + (T(1.0) - T(0.01)) * avg
     return norm, new_avg
+
+
+# ---- EXTENSION (SURVEY 8f N4): self-consistent electrostatic field solve ----------------------
+def relax_coeffs(nr, dr, dz):
+    """[nr][4] = cE cW cZ cB in float64 (oracle/fsim_oracle_fields_impl.h)."""
+    i = np.arange(nr, dtype=np.float64)
+    rc = (i + 0.5) * dr * dr
+    aE, aW, aZ = (i + 1.0) / rc, i / rc, np.full(nr, 1.0 / (dz * dz))
+    aC = aE + aW + 2.0 * aZ
+    return np.stack([aE / aC, aW / aC, aZ / aC, 1.0 / aC], 1)
+
+
+def relax(phi, src, coef64, omega, sweeps, nr, nz):
+    """`sweeps` weighted-Jacobi sweeps of the 5-point cylindrical operator, grounded ghost cells."""
+    T = phi.dtype.type
+    k = coef64.astype(phi.dtype)
+    cE, cW, cZ, cB = (k[:, q][None, :] for q in range(4))
+    om = T(omega)
+    one_m = T(1.0) - om
+    p = phi.reshape(nz, nr).copy()
+    s = src.reshape(nz, nr)
+    for _ in range(sweeps):
+        g = np.zeros((nz + 2, nr + 2), phi.dtype)
+        g[1:-1, 1:-1] = p
+        pE, pW, pN, pS = g[1:-1, 2:], g[1:-1, :-2], g[2:, 1:-1], g[:-2, 1:-1]
+        t = ((cE * pE + cW * pW) + cZ * (pN + pS)) + cB * s
+        p = om * t + one_m * p
+    return p.reshape(-1)
+
+
+def efield(phi, nr, nz, inv2dr, inv2dz):
+    T = phi.dtype.type
+    p = phi.reshape(nz, nr)
+    g = np.zeros((nz + 2, nr + 2), phi.dtype)
+    g[1:-1, 1:-1] = p
+    g[1:-1, 0] = p[:, 0]  # axis: phi_W := phi
+    E = np.zeros((nz, nr, 4), phi.dtype)
+    E[..., 0] = -((g[1:-1, 2:] - g[1:-1, :-2]) * T(inv2dr))
+    E[..., 2] = -((g[2:, 1:-1] - g[:-2, 1:-1]) * T(inv2dz))
+    E[..., 3] = 1
+    return E.reshape(-1, 4)

@@ -21,12 +21,15 @@ _LIB = None
 
 C_LIGHT = 2.998e8  # empic.js:27
 N_ENTROPY = 1024
+FSIM_EPS0 = 8.8541878128e-12  # include/fsim_constants.h
+FSIM_PI = 3.14159265358979323846
 N_INVCDF = 512
 
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libfsim_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("fsim_oracle.c", "fsim_oracle_impl.h", "fsim_oracle_jacobi_impl.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fsim_oracle.c", "fsim_oracle_impl.h", "fsim_oracle_jacobi_impl.h",
+                                                 "fsim_oracle_fields_impl.h", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "fsim_constants.h"))
     stale = (not os.path.exists(so)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
@@ -236,6 +239,30 @@ class OraclePusher:
                                      _p(self.moments01_norm), _p(self.moments01_avg),
                                      C.c_int(self.nthreads))
 
+    # -- EXTENSION: self-consistent electrostatic field solve ------------------
+    def solveFields(self, value: dict):
+        """{macro_weight, sweeps, omega=1, source="avg"|"instant"}: charge density from the
+        deposited moments -> `sweeps` weighted-Jacobi sweeps on the potential (warm start) ->
+        E = -grad(phi) -> precalc().  Specification: oracle/fsim_oracle_fields_impl.h."""
+        sp = self.spec
+        dr, dz = sp["radius"] / self.nr, sp["height"] / self.nz
+        dens = self.moments01_avg if value.get("source", "avg") == "avg" else self.moments01_norm
+        rho_scale = (sp["particle_charge"] * float(value["macro_weight"])
+                     / (FSIM_PI * sp["radius"] * dr * dz * FSIM_EPS0))
+        if not hasattr(self, "phi"):
+            self.phi = np.zeros(self.ncell, self.dt)
+            self.rho_src = np.zeros(self.ncell, self.dt)
+        self._f("orc_charge_source")(C.c_int64(self.ncell), _p(dens), C.c_double(rho_scale), _p(self.rho_src))
+        coef = np.empty((self.nr, 4), np.float64)
+        lib().orc_relax_coeffs(C.c_int64(self.nr), C.c_double(dr), C.c_double(dz), _p(coef))
+        tmp = np.empty_like(self.phi)
+        self._f("orc_relax")(C.c_int64(self.nr), C.c_int64(self.nz), _p(self.phi), _p(tmp), _p(self.rho_src),
+                             _p(coef), C.c_double(float(value.get("omega", 1.0))), C.c_int(int(value["sweeps"])),
+                             C.c_int(self.nthreads))
+        self._f("orc_efield")(C.c_int64(self.nr), C.c_int64(self.nz), _p(self.phi), C.c_double(1 / (2 * dr)),
+                              C.c_double(1 / (2 * dz)), _p(self.E))
+        self.precalc()
+
     @property
     def canvas(self) -> np.ndarray:
         out = np.empty((self.nz, self.nr, 4), np.uint8)
@@ -261,6 +288,8 @@ class OraclePusher:
             return a[:, :2].astype(np.float64)
         if name == "cell_count":
             return a.copy()
+        if name in ("phi", "rho_src"):
+            return a.astype(np.float64)
         if name in ("E", "B", "R1", "R2", "R3", "A"):
             return a[:, :3].astype(np.float64)
         return a.astype(np.float64)

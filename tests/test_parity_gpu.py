@@ -95,6 +95,30 @@ def test_absorb_respawn_and_E(precision):
     assert np.isnan(o.position).any()  # NaN respawn texels were hit and handled alike
 
 
+@pytest.mark.parametrize("speed", [0.004, 0.2])
+def test_float_entropy_and_sink_update(speed):
+    """A reference-style entropy table (uint32 / 0xFFFFFFFF stored as floats, empic.js:143-155) and a
+    set({sink_mask}) between steps: absorption must follow the new mask at once."""
+    from fusion_sim_b200.scenes import entropy_table
+    sc = small_scene(precision="f64", n=8192, speed=speed, with_E=True, blob=(0.6, 0.9))
+    sc["entropy"] = entropy_table(np.random.Generator(np.random.PCG64(3)))
+    g, o = make_pair(sc)
+    for k in range(8):
+        g.half_step(); o.half_step()
+    compare_particles(g, o, "half-step 7")
+    rng = np.random.Generator(np.random.PCG64(4))
+    mask = (rng.random((o.nr, o.nz)) > 0.02).astype(np.float64)  # scattered absorbing cells
+    g.set({"sink_mask": mask}); o.set({"sink_mask": mask})
+    respawned = 0
+    for k in range(8):
+        g.half_step(); o.half_step()
+        respawned += int((o.position[:, 3] == 0).sum())
+        compare_particles(g, o, f"new mask, half-step {k}")
+    assert respawned > 50
+    g.step(); o.step()
+    compare_particles(g, o, "fused step()")
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_density_bit_exact(precision):
     sc = small_scene(precision=precision, n=20000, speed=0.02, blob=(0.5, 0.8))

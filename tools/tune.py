@@ -14,7 +14,7 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "c5"
 precision = sys.argv[2] if len(sys.argv) > 2 else "f64"
 variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(7))
 sc = bench.build_scene(workload, 0, 1)
-spec = dict(sc["spec"], precision=precision)
+spec = dict(sc["spec"], precision=precision, flags=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 sim = makeCylindricalParticlePusher(spec)
 apply_scene(sim, sc)
 names = ("push", "push2", "scan", "permute", "index_scatter", "cellsum", "cellsum_heavy", "conv", "prepass")
