@@ -363,7 +363,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_TRY(dalloc_bytes(&s->entropy, s->rs * 4 * FSIM_N_ENTROPY * FSIM_N_ENTROPY));
     FSIM_TRY(dalloc_bytes(&s->invcdf, s->rs * 2 * FSIM_N_INVCDF * FSIM_N_INVCDF));
     FSIM_TRY(dalloc_bytes(&s->cellsum, s->rs * 4 * s->plane));
-    FSIM_TRY(make_sums_tensor_map(s));
+    FSIM_TRY(make_sums_tensor_map(s, 18));  // re-encoded by launch_conv if its tile height differs
     FSIM_TRY(dalloc(&s->cellcount, s->ncell_local));
     FSIM_TRY(dalloc_bytes(&s->avg, s->rs * 4 * s->plane));
     if (sp->flags & FSIM_FLAG_KEEP_MOMENTS) {

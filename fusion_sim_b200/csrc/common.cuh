@@ -73,6 +73,7 @@ struct fsim_sim {
     int pitch = 0;
     int64_t plane = 0;
     alignas(64) unsigned char tm_sums[128] = {};  // CUtensorMap of the per-cell sums (deposit.cu)
+    int tm_sums_rows = 0;                         // box height the map was encoded with
     bool slab = false;
 
     // physical constants (host doubles, empic.js:44-46, :852)
@@ -193,13 +194,21 @@ inline int dispatch(const fsim_sim *s, F &&f)
 
 // ---- device helpers --------------------------------------------------------------------
 // NEAREST + CLAMP_TO_EDGE texel index (utilities.js:528-531); NaN samples texel 0.
+// Branch-free: max(t, 0) maps NaN and negatives to 0, min(.., n-1) clamps the top texel (and +inf);
+// truncation of a value in [0, n-1] is exact.  `nreal` = (Real)n, passed in so hot loops do not
+// convert the integer again (grid sides are far below 2^24, so n and n-1 are exact in fp32 too).
+__device__ __forceinline__ int tex_idx_r(double u, double nreal)
+{
+    return __double2int_rz(fmin(fmax(u * nreal, 0.0), nreal - 1.0));
+}
+__device__ __forceinline__ int tex_idx_r(float u, float nreal)
+{
+    return __float2int_rz(fminf(fmaxf(u * nreal, 0.0f), nreal - 1.0f));
+}
 template <typename Real>
 __device__ __forceinline__ int tex_idx(Real u, int n)
 {
-    Real t = u * (Real)n;
-    if (!(t > (Real)0)) return 0;
-    if (t >= (Real)n) return n - 1;
-    return (int)t;
+    return tex_idx_r(u, (Real)n);
 }
 
 __device__ __forceinline__ double fsqrt(double x) { return sqrt(x); }
@@ -279,7 +288,7 @@ int launch_apply_perm(fsim_sim *s);  // physical re-sort: storage <- storage[per
 int launch_cellsum(fsim_sim *s);
 int launch_cellsum_atomic(fsim_sim *s);
 int launch_conv(fsim_sim *s);
-int make_sums_tensor_map(fsim_sim *s);
+int make_sums_tensor_map(fsim_sim *s, int box_rows);
 int launch_halo_pack(fsim_sim *s);
 int launch_halo_unpack(fsim_sim *s);
 int launch_precalc(fsim_sim *s);

@@ -14,6 +14,7 @@
 //             (empic.js:1053-1056), programAvgMoments (avg_frag :274-277, ratio :1083) and the
 //             avgA -> avgB copy (:1490-1495).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -277,9 +278,9 @@ int launch_cellsum(fsim_sim *s)
 // (+di,-dj), (-di,+dj), (+di,+dj) -- the canonical order of the oracle; the 40 taps that are
 // exactly zero are removed at compile time.  107 fp64 operations per cell and channel: the kernel
 // is bound by the fp64 pipe.
-constexpr int CT_I = 32, CT_J = 16;             // output tile
+constexpr int CT_I = 32;                        // output tile width (one lane per column)
+constexpr int CT_J_MAX = 32;                    // tallest output tile of any variant (sizes the tensor-map box)
 constexpr int CH = FSIM_SHAPE_MID;              // halo = 5
-constexpr int CS_J = CT_J + 2 * CH;             // 26 rows
 // TMA needs the box START (innermost coordinate x element size) 16-byte aligned, and the box width
 // a multiple of 16 bytes: the box therefore begins CXOFF >= 5 cells left of the tile, CXOFF a
 // multiple of 2 reals (fp64) / 4 reals (fp32), and is CBOXW >= CXOFF + 32 + 5 wide.  (A start at
@@ -287,8 +288,6 @@ constexpr int CS_J = CT_J + 2 * CH;             // 26 rows
 template <typename Real> struct ConvBox;
 template <> struct ConvBox<double> { static constexpr int XOFF = 6, W = 44; };
 template <> struct ConvBox<float> { static constexpr int XOFF = 8, W = 48; };
-constexpr int CSTRIP = 4;                       // output rows per thread
-constexpr int CWIN = CSTRIP + 2 * CH;           // 14
 
 __constant__ double c_shape_f64[FSIM_NSHAPE * FSIM_NSHAPE];
 __constant__ float c_shape_f32[FSIM_NSHAPE * FSIM_NSHAPE];
@@ -312,11 +311,13 @@ struct ConvArgs {
     int j0, j1;               // output rows [j0, j1) (owned rows, local index)
 };
 
-template <typename Real>
-__global__ void __launch_bounds__(CT_J * 32)
+// CSTRIP = output rows per thread (window of CSTRIP + 10 values per column offset), CT_J = tile height
+template <typename Real, int CSTRIP, int CT_J>
+__global__ void __launch_bounds__(CT_J / CSTRIP * 4 * 32)
 conv_kernel(const __grid_constant__ CUtensorMap tmS, const ConvArgs<Real> a)
 {
     constexpr int CBOXW = ConvBox<Real>::W, CXOFF = ConvBox<Real>::XOFF;
+    constexpr int CS_J = CT_J + 2 * CH, CWIN = CSTRIP + 2 * CH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Real *sm = reinterpret_cast<Real *>(smem_raw);  // [4][CS_J][CBOXW], written by the TMA unit
     __shared__ __align__(8) unsigned long long bar;
@@ -406,7 +407,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmS, const ConvArgs<Real> a)
 
 // Tensor map of the planar per-cell sums: dims (i, j, channel), box (CBOXW, CS_J, 4), zero fill.
 // cuTensorMapEncodeTiled is taken from the driver through the runtime (no link against libcuda).
-int make_sums_tensor_map(fsim_sim *s)
+int make_sums_tensor_map(fsim_sim *s, int box_rows)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -420,7 +421,7 @@ int make_sums_tensor_map(fsim_sim *s)
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)s->nr, (cuuint64_t)s->rows, 4};
     const cuuint64_t gstride[2] = {(cuuint64_t)s->pitch * s->rs, (cuuint64_t)s->plane * s->rs};
-    const cuuint32_t box[3] = {(cuuint32_t)(s->prec == FSIM_F64 ? ConvBox<double>::W : ConvBox<float>::W), CS_J, 4};
+    const cuuint32_t box[3] = {(cuuint32_t)(s->prec == FSIM_F64 ? ConvBox<double>::W : ConvBox<float>::W), (cuuint32_t)box_rows, 4};
     const cuuint32_t estr[3] = {1, 1, 1};
     static_assert(sizeof(CUtensorMap) == sizeof(s->tm_sums), "tensor map storage");
     const CUresult r = ((EncodeFn)fn)(reinterpret_cast<CUtensorMap *>(s->tm_sums),
@@ -432,6 +433,7 @@ int make_sums_tensor_map(fsim_sim *s)
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         return FSIM_ERR_CUDA;
     }
+    s->tm_sums_rows = box_rows;
     return FSIM_OK;
 }
 
@@ -445,6 +447,24 @@ int upload_shape(const double *shape64, const double *shape32)
     return FSIM_OK;
 }
 
+template <typename Real, int CSTRIP, int CT_J>
+static int conv_launch(fsim_sim *s, const ConvArgs<Real> &a)
+{
+    constexpr int CS_J = CT_J + 2 * CH;
+    if (s->tm_sums_rows != CS_J) FSIM_TRY(make_sums_tensor_map(s, CS_J));  // the box height is part of the map
+    const size_t smem = sizeof(Real) * 4 * CS_J * ConvBox<Real>::W;
+    static bool attr = false;
+    if (!attr) {
+        FSIM_CUDA(cudaFuncSetAttribute(conv_kernel<Real, CSTRIP, CT_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 block(CT_J / CSTRIP * 4 * 32);
+    dim3 grid((s->nr + CT_I - 1) / CT_I, (s->own_rows + CT_J - 1) / CT_J);
+    conv_kernel<Real, CSTRIP, CT_J><<<grid, block, smem, s->stream>>>(*reinterpret_cast<const CUtensorMap *>(s->tm_sums), a);
+    FSIM_CUDA(cudaGetLastError());
+    return FSIM_OK;
+}
+
 int launch_conv(fsim_sim *s)
 {
     return dispatch(s, [&](auto tag) {
@@ -453,13 +473,18 @@ int launch_conv(fsim_sim *s)
         a.mom = (Real *)s->mom; a.norm = (Real *)s->norm; a.avg = (Real *)s->avg;
         a.nr = s->nr; a.pitch = s->pitch; a.plane = s->plane;
         a.j0 = s->own0 - s->row0; a.j1 = a.j0 + s->own_rows;
-        dim3 block(CT_J * 32);
-        dim3 grid((s->nr + CT_I - 1) / CT_I, (s->own_rows + CT_J - 1) / CT_J);
-        const size_t smem = sizeof(Real) * 4 * CS_J * ConvBox<Real>::W;
         Bracket b(s, "conv");
-        conv_kernel<Real><<<grid, block, smem, s->stream>>>(*reinterpret_cast<const CUtensorMap *>(s->tm_sums), a);
-        FSIM_CUDA(cudaGetLastError());
-        return (int)FSIM_OK;
+        const char *e = getenv("FSIM_CONV_VARIANT");  // tuning (tools/tune.py); default measured fastest on B200
+        switch (e ? atoi(e) : 0) {
+        case 1: return conv_launch<Real, 8, 16>(s, a);
+        case 2: return conv_launch<Real, 8, 32>(s, a);
+        case 3: return conv_launch<Real, 4, 32>(s, a);
+        case 4: return conv_launch<Real, 2, 16>(s, a);
+        case 5: return conv_launch<Real, 16, 16>(s, a);
+        case 6: return conv_launch<Real, 16, 32>(s, a);
+        case 8: return conv_launch<Real, 4, 16>(s, a);
+        default: return conv_launch<Real, 8, 8>(s, a);  // 0.65 ms at C5 fp64 against 0.86 for <4,16>, 0.69 <8,16>, 0.88 <16,32>
+        }
     });
 }
 
