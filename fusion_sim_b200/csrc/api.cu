@@ -720,21 +720,86 @@ int fsim_precalc(fsim_sim *s)
 // EXTENSION: charge density from the deposited moments -> weighted-Jacobi sweeps on
 // the potential (warm start) -> E = -grad(phi) -> precalc().  Specification:
 // include/fusionsim.h (fsim_solve_fields).
-int fsim_solve_fields(fsim_sim *s, double macro_weight, int32_t sweeps, double omega, int32_t source)
+static int solve_args_ok(fsim_sim *s, int32_t sweeps, double omega, int32_t source)
 {
-    FSIM_TRY(check(s));
-    if (s->slab) return fail(FSIM_ERR_UNSUPPORTED, "solveFields: not available in slab (multi-GPU) mode yet");
     if (sweeps < 0 || !(omega > 0.0 && omega < 2.0)) return fail(FSIM_ERR_INVALID, ".sweeps/.omega <- out of range");
     if (source != 0 && source != 1) return fail(FSIM_ERR_INVALID, ".source <- 0 (running average) or 1 (instantaneous)");
     if (source == 1 && !s->norm)
         return fail(FSIM_ERR_STATE, "solveFields: the instantaneous density needs FSIM_FLAG_KEEP_MOMENTS");
-    FSIM_TRY(finish(s, ensure_fieldsolve(s)));
+    return FSIM_OK;
+}
+
+static int solve_charge_source(fsim_sim *s, double macro_weight, int32_t source)
+{
     const double dr = s->spec.radius / (double)s->nr, dz = s->spec.height / (double)s->nz;
     const double rho_scale = s->spec.particle_charge * macro_weight / (FSIM_PI * s->spec.radius * dr * dz * FSIM_EPS0);
     const char *dens = (const char *)(source ? s->norm : s->avg) + s->rs * 3 * (size_t)s->plane;  // channel a
-    FSIM_TRY(finish(s, launch_field_solve(s, dens, rho_scale, sweeps, omega)));
+    return launch_charge_source(s, dens, rho_scale);
+}
+
+int fsim_solve_fields(fsim_sim *s, double macro_weight, int32_t sweeps, double omega, int32_t source)
+{
+    FSIM_TRY(check(s));
+    if (s->slab)
+        return fail(FSIM_ERR_UNSUPPORTED, "solveFields on a slab: drive fsim_solve_fields_stage with halo exchanges "
+                                          "between the stages (fusion_sim_b200/dist.py)");
+    FSIM_TRY(solve_args_ok(s, sweeps, omega, source));
+    FSIM_TRY(finish(s, ensure_fieldsolve(s)));
+    FSIM_TRY(finish(s, solve_charge_source(s, macro_weight, source)));
+    int left = sweeps;
+    for (; left >= 4; left -= 4) FSIM_TRY(finish(s, launch_relax(s, 4, omega)));
+    if (left >= 2) { FSIM_TRY(finish(s, launch_relax(s, 2, omega))); left -= 2; }
+    if (left >= 1) FSIM_TRY(finish(s, launch_relax(s, 1, omega)));
+    FSIM_TRY(finish(s, launch_efield(s)));
     FSIM_TRY(finish(s, launch_precalc(s)));
     s->have_precalc = true;
+    return FSIM_OK;
+}
+
+// slab mode: one stage at a time; the caller moves boundary rows between neighbouring ranks
+int fsim_solve_fields_stage(fsim_sim *s, int32_t stage, double macro_weight, int32_t sweeps, double omega, int32_t source)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(finish(s, ensure_fieldsolve(s)));
+    switch (stage) {
+    case 0:
+        FSIM_TRY(solve_args_ok(s, 0, omega, source));
+        return finish(s, solve_charge_source(s, macro_weight, source));
+    case 1:
+        FSIM_TRY(solve_args_ok(s, sweeps, omega, 0));
+        return finish(s, launch_relax(s, sweeps, omega));
+    case 2:
+        return finish(s, launch_efield(s));
+    case 3:
+        FSIM_TRY(finish(s, launch_precalc(s)));
+        s->have_precalc = true;
+        return FSIM_OK;
+    default:
+        return fail(FSIM_ERR_INVALID, "solve stage 0..3");
+    }
+}
+
+// device address of rows [first_row, first_row + nrows) of the LOCAL table of "phi", "rho_src" or "E"
+int fsim_field_rows(fsim_sim *s, const char *name, int64_t first_row, int64_t nrows, void **ptr, int64_t *nbytes)
+{
+    FSIM_TRY(check(s));
+    if (!name || !ptr || !nbytes) return fail(FSIM_ERR_INVALID, "null argument");
+    if (first_row < 0 || nrows < 0 || first_row + nrows > s->rows) return fail(FSIM_ERR_RANGE, "rows outside the local table");
+    const std::string n(name);
+    char *base = nullptr;
+    size_t row_bytes = 0;
+    if (n == "E") {
+        base = (char *)s->E;
+        row_bytes = s->rs * 3 * (size_t)s->nr;
+    } else if (n == "phi" || n == "rho_src") {
+        FSIM_TRY(finish(s, ensure_fieldsolve(s)));
+        base = (char *)(n == "phi" ? s->phi[s->phi_cur] : s->rho_src);
+        row_bytes = s->rs * (size_t)s->pitch;
+    } else {
+        return fail(FSIM_ERR_INVALID, "field rows: unknown name " + n);
+    }
+    *ptr = base + row_bytes * (size_t)first_row;
+    *nbytes = (int64_t)(row_bytes * (size_t)nrows);
     return FSIM_OK;
 }
 

@@ -297,7 +297,9 @@ int launch_add_loop(fsim_sim *s, double R, double Z, double I);
 int launch_add_uniform(fsim_sim *s, int kind, double val);
 int launch_render(fsim_sim *s, uint8_t *dev_rgba);
 int ensure_fieldsolve(fsim_sim *s);
-int launch_field_solve(fsim_sim *s, const void *dens_a, double rho_scale, int sweeps, double omega);
+int launch_charge_source(fsim_sim *s, const void *dens_a, double rho_scale);
+int launch_relax(fsim_sim *s, int sweeps, double omega);  // 1..4 sweeps, one launch
+int launch_efield(fsim_sim *s);
 int launch_plane_out(fsim_sim *s, const void *plane, double *dev_out);
 
 }  // namespace fsim

@@ -266,7 +266,7 @@ static int relax_launch(fsim_sim *s, Real omega)
         attr = true;
     }
     dim3 grid((s->nr + RT_I - 1) / RT_I, (s->rows + RT_J - 1) / RT_J);
-    Bracket b(s, T == 4 ? "relax4" : (T == 2 ? "relax2" : "relax1"));
+    Bracket b(s, T == 4 ? "relax4" : (T == 3 ? "relax3" : (T == 2 ? "relax2" : "relax1")));
     relax_kernel<Real, T><<<grid, RT_THREADS, smem, s->stream>>>(
         *reinterpret_cast<const CUtensorMap *>(s->tm_phi[cur]), *reinterpret_cast<const CUtensorMap *>(s->tm_src), a);
     FSIM_CUDA(cudaGetLastError());
@@ -274,29 +274,46 @@ static int relax_launch(fsim_sim *s, Real omega)
     return FSIM_OK;
 }
 
-// src from the density, `sweeps` Jacobi sweeps (4 per launch, then 2, then 1), E = -grad(phi)
-int launch_field_solve(fsim_sim *s, const void *dens_a, double rho_scale, int sweeps, double omega)
+// The stages of a solve.  One GPU runs them back to back (api.cu, fsim_solve_fields); in slab mode
+// the caller exchanges boundary rows between them (fusion_sim_b200/dist.py): every stage works on
+// ALL local rows, rows further than the halo from an owned row simply hold unused values.
+int launch_charge_source(fsim_sim *s, const void *dens_a, double rho_scale)
 {
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
-        {
-            Bracket b(s, "charge_source");
-            charge_source_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
-                (const Real *)dens_a, (Real *)s->rho_src, s->nr, s->rows, s->pitch, (Real)rho_scale);
-            FSIM_CUDA(cudaGetLastError());
+        Bracket b(s, "charge_source");
+        charge_source_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
+            (const Real *)dens_a, (Real *)s->rho_src, s->nr, s->rows, s->pitch, (Real)rho_scale);
+        FSIM_CUDA(cudaGetLastError());
+        return (int)FSIM_OK;
+    });
+}
+
+// `sweeps` in 1..4: ONE launch
+int launch_relax(fsim_sim *s, int sweeps, double omega)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        switch (sweeps) {
+        case 4: return relax_launch<Real, 4>(s, (Real)omega);
+        case 3: return relax_launch<Real, 3>(s, (Real)omega);
+        case 2: return relax_launch<Real, 2>(s, (Real)omega);
+        case 1: return relax_launch<Real, 1>(s, (Real)omega);
+        default: set_error("relax: 1..4 sweeps per launch"); return (int)FSIM_ERR_INVALID;
         }
-        int left = sweeps;
-        for (; left >= 4; left -= 4) FSIM_TRY((relax_launch<Real, 4>(s, (Real)omega)));
-        if (left >= 2) { FSIM_TRY((relax_launch<Real, 2>(s, (Real)omega))); left -= 2; }
-        if (left >= 1) FSIM_TRY((relax_launch<Real, 1>(s, (Real)omega)));
-        {
-            const double dr = s->spec.radius / (double)s->nr, dz = s->spec.height / (double)s->nz;
-            Bracket b(s, "efield");
-            efield_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
-                (const Real *)s->phi[s->phi_cur], (Real *)s->E, s->nr, s->rows, s->pitch, (Real)(1.0 / (2.0 * dr)),
-                (Real)(1.0 / (2.0 * dz)));
-            FSIM_CUDA(cudaGetLastError());
-        }
+    });
+}
+
+int launch_efield(fsim_sim *s)
+{
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        const double dr = s->spec.radius / (double)s->nr, dz = s->spec.height / (double)s->nz;
+        Bracket b(s, "efield");
+        efield_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
+            (const Real *)s->phi[s->phi_cur], (Real *)s->E, s->nr, s->rows, s->pitch, (Real)(1.0 / (2.0 * dr)),
+            (Real)(1.0 / (2.0 * dz)));
+        FSIM_CUDA(cudaGetLastError());
         return (int)FSIM_OK;
     });
 }

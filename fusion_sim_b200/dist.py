@@ -62,6 +62,31 @@ def exchange_halo(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, gro
             w.wait()
 
 
+HALO_RELAX = 4  # rows of potential a relaxation launch may consume (most sweeps per launch)
+
+
+def solve_fields_slab(backend, value: dict):
+    """EXTENSION on a slab: the stages of the field solve with the halo exchanges
+    between them.  `backend` offers fs_stage(stage, value, sweeps) and fs_exchange(name, nrows);
+    the CUDA SlabPusher and the oracle-backed test rank both run through this function.  A launch
+    of T <= 4 sweeps consumes T halo rows, so 4 boundary rows of the potential are refreshed
+    before every launch; every rank recomputes the halo cells it needs with the same arithmetic,
+    hence the result equals the single-GPU solve bit for bit."""
+    sweeps = int(value["sweeps"])
+    backend.fs_stage(0, value, 0)                 # charge source on the owned rows
+    backend.fs_exchange("rho_src", HALO_RELAX)
+    left = sweeps
+    while left > 0:
+        t = 4 if left >= 4 else (2 if left >= 2 else 1)
+        backend.fs_exchange("phi", HALO_RELAX)
+        backend.fs_stage(1, value, t)
+        left -= t
+    backend.fs_exchange("phi", HALO_RELAX)
+    backend.fs_stage(2, value, 0)                 # E = -grad(phi)
+    backend.fs_exchange("E", None)                # all halo rows of the cell table: the push gathers there
+    backend.fs_stage(3, value, 0)                 # precalc()
+
+
 class _DevPtr:
     def __init__(self, ptr: int, nbytes: int):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
@@ -128,6 +153,37 @@ class SlabPusher:
         exchange_halo(t[0], t[1], t[2], t[3], self.rank, self.world)
         torch.cuda.current_stream().synchronize()
         self._lib.check(L.fsim_density_end(h))
+
+    # -- EXTENSION: self-consistent field solve on the slab -------------------------------------------
+    def solveFields(self, value: dict):
+        solve_fields_slab(self, value)
+
+    def fs_stage(self, stage: int, value: dict, sweeps: int):
+        src = 0 if value.get("source", "avg") == "avg" else 1
+        self._lib.check(self._lib.lib().fsim_solve_fields_stage(
+            self.sim.handle, stage, float(value["macro_weight"]), int(sweeps), float(value.get("omega", 1.0)), src))
+
+    def _rows(self, name: str, first: int, nrows: int) -> torch.Tensor:
+        ptr, nb = C.c_void_p(), C.c_int64()
+        self._lib.check(self._lib.lib().fsim_field_rows(self.sim.handle, name.encode(), first, nrows,
+                                                        C.byref(ptr), C.byref(nb)))
+        return _dev_tensor(ptr.value or 0, nb.value, self.device)
+
+    def fs_exchange(self, name: str, nrows):
+        """Owned boundary rows -> the neighbours' halo rows, in place in device memory."""
+        halo = int(self.sim.spec["halo_rows"])
+        own = self.bounds[self.rank + 1] - self.bounds[self.rank]
+        lo = self.bounds[self.rank] - max(0, self.bounds[self.rank] - halo)  # local index of the first owned row
+        hi = lo + own
+        h = halo if nrows is None else int(nrows)
+        assert h <= halo and h <= own, "slab thinner than the halo"
+        empty = torch.empty(0, dtype=torch.uint8, device=self.device)
+        up, down = self.rank < self.world - 1, self.rank > 0
+        self.sim.sync()
+        exchange_halo(self._rows(name, lo, h) if down else empty, self._rows(name, hi - h, h) if up else empty,
+                      self._rows(name, lo - h, h) if down else empty, self._rows(name, hi, h) if up else empty,
+                      self.rank, self.world)
+        torch.cuda.current_stream().synchronize()
 
     # -- pass-throughs ----------------------------------------------------------------------------
     def sync(self):

@@ -132,6 +132,16 @@ int fsim_sync(fsim_sim *sim);      /* wait for the handle's stream              
  *   E_r = -((phi_E - phi_W) / (2 dr)) with phi_W := phi at i = 0, E_z = -((phi_N - phi_S) / (2 dz))
  *   (both as a multiplication by the host-computed reciprocal), E_theta = 0.            Single GPU. */
 int fsim_solve_fields(fsim_sim *sim, double macro_weight, int32_t sweeps, double omega, int32_t source);
+/* The same solve on a slab (one process per GPU): stage 0 = charge source, 1 = `sweeps` (1..4)
+ * Jacobi sweeps in one launch, 2 = E = -grad(phi), 3 = precalc().  Every stage works on all local
+ * rows; between the stages the caller copies boundary rows to the neighbouring ranks' halo rows:
+ * 4 rows of "rho_src" after stage 0, 4 rows of "phi" before every stage 1 and before stage 2,
+ * halo_rows rows of "E" before stage 3.  fsim_field_rows gives the device address of rows
+ * [first_row, first_row + nrows) of the local table (rows are contiguous).  Bit-identical to the
+ * single-GPU solve: each rank recomputes the halo cells it needs with the same arithmetic.       */
+int fsim_solve_fields_stage(fsim_sim *sim, int32_t stage, double macro_weight, int32_t sweeps, double omega,
+                            int32_t source);
+int fsim_field_rows(fsim_sim *sim, const char *name, int64_t first_row, int64_t nrows, void **ptr, int64_t *nbytes);
 
 /* ---- accessors (extension; the reference exposes none) ---------- */
 int64_t fsim_particle_count(const fsim_sim *sim);

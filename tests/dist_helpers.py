@@ -122,6 +122,56 @@ class OracleSlab:
         f("orc_normalize_ema")(C.c_int64(o.nr), C.c_int64(o.nz), orc._p(o.moments01), orc._p(o.moments01_norm),
                                orc._p(o.moments01_avg), C.c_int(1))
 
+    # EXTENSION: the staged field solve, through the same driver as the CUDA SlabPusher
+    def solveFields(self, value):
+        from fusion_sim_b200.dist import solve_fields_slab
+        solve_fields_slab(self, value)
+
+    def fs_stage(self, stage, value, sweeps):
+        import ctypes as C
+        from oracle import oracle as orc
+        o = self.o
+        sp = o.spec
+        dr, dz = sp["radius"] / o.nr, sp["height"] / o.nz
+        f = lambda name: getattr(orc.lib(), name + "_f64")
+        if not hasattr(o, "phi"):
+            o.phi = np.zeros(o.ncell, o.dt)
+            o.rho_src = np.zeros(o.ncell, o.dt)
+        if stage == 0:
+            dens = o.moments01_avg if value.get("source", "avg") == "avg" else o.moments01_norm
+            scale = sp["particle_charge"] * float(value["macro_weight"]) / (orc.FSIM_PI * sp["radius"] * dr * dz * orc.FSIM_EPS0)
+            f("orc_charge_source")(C.c_int64(o.ncell), orc._p(dens), C.c_double(scale), orc._p(o.rho_src))
+        elif stage == 1:
+            coef = np.empty((o.nr, 4), np.float64)
+            orc.lib().orc_relax_coeffs(C.c_int64(o.nr), C.c_double(dr), C.c_double(dz), orc._p(coef))
+            tmp = np.empty_like(o.phi)
+            f("orc_relax")(C.c_int64(o.nr), C.c_int64(o.nz), orc._p(o.phi), orc._p(tmp), orc._p(o.rho_src), orc._p(coef),
+                           C.c_double(float(value.get("omega", 1.0))), C.c_int(int(sweeps)), C.c_int(1))
+        elif stage == 2:
+            f("orc_efield")(C.c_int64(o.nr), C.c_int64(o.nz), orc._p(o.phi), C.c_double(1 / (2 * dr)),
+                            C.c_double(1 / (2 * dz)), orc._p(o.E))
+        else:
+            o.precalc()
+
+    def fs_exchange(self, name, nrows):
+        """This emulation keeps the WHOLE grid on every rank but only trusts its owned rows and the
+        rows it received: rows further away hold stale values, like the far halo rows of a GPU slab."""
+        from fusion_sim_b200.dist import exchange_halo
+        o = self.o
+        a = getattr(o, name).reshape(o.nz, o.nr, -1)
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        h = 8 if nrows is None else int(nrows)
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+        up, down = self.rank < self.world - 1, self.rank > 0
+        recv_lo = t(np.zeros_like(a[lo - h:lo])) if down else torch.empty(0)
+        recv_hi = t(np.zeros_like(a[hi:hi + h])) if up else torch.empty(0)
+        exchange_halo(t(a[lo:lo + h]) if down else torch.empty(0), t(a[hi - h:hi]) if up else torch.empty(0),
+                      recv_lo, recv_hi, self.rank, self.world)
+        if down:
+            a[lo - h:lo] = recv_lo.numpy()
+        if up:
+            a[hi:hi + h] = recv_hi.numpy()
+
     def owned(self, a):
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         return a.reshape(self.o.nz, self.o.nr, -1)[lo:hi].reshape((hi - lo) * self.o.nr, -1)
@@ -133,7 +183,10 @@ def _gather(rank, world, parts):
     return out
 
 
-def cpu_worker(rank, world, port, frames, result_path):
+SOLVE = {"macro_weight": 5e11, "sweeps": 7, "omega": 0.9}  # per-frame field solve of the self-consistent tests
+
+
+def cpu_worker(rank, world, port, frames, result_path, solve=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -145,8 +198,12 @@ def cpu_worker(rank, world, port, frames, result_path):
             n0 = len(s.ids)
             s.density()
             moved += abs(len(s.ids) - n0)
+            if solve:
+                s.solveFields(SOLVE)
         parts = dict(ids=s.ids, pos=s.o.position, vel=s.o.velocity, rnd=s.o.rand,
                      avg=s.owned(s.o.moments01_avg), cnt=s.owned(s.o.cell_count), moved=moved)
+        if solve:
+            parts.update(phi=s.owned(s.o.phi).reshape(-1), E=s.owned(s.o.E)[:, :3])
         out = _gather(rank, world, parts)
         if rank == 0:
             np.savez(result_path, **assemble(out))
@@ -157,14 +214,15 @@ def cpu_worker(rank, world, port, frames, result_path):
 def assemble(out):
     ids = np.concatenate([o["ids"] for o in out])
     order = np.argsort(ids, kind="stable")
-    return dict(ids=ids[order], pos=np.concatenate([o["pos"] for o in out])[order],
+    extra = {k: np.concatenate([o[k] for o in out]) for k in ("phi", "E") if k in out[0]}
+    return dict(extra, ids=ids[order], pos=np.concatenate([o["pos"] for o in out])[order],
                 vel=np.concatenate([o["vel"] for o in out])[order][:, :3],
                 rnd=np.concatenate([o["rnd"] for o in out])[order],
                 avg=np.concatenate([o["avg"] for o in out]), cnt=np.concatenate([o["cnt"] for o in out]).reshape(-1),
                 moved=sum(o["moved"] for o in out))
 
 
-def gpu_worker(rank, world, port, frames, result_path):
+def gpu_worker(rank, world, port, frames, result_path, solve=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -180,6 +238,8 @@ def gpu_worker(rank, world, port, frames, result_path):
         for _ in range(frames):
             s.step()
             s.density()
+            if solve:
+                s.solveFields(SOLVE)
         s.sync()
         pos = s.sim.getPosition()
         lo = (s.bounds[rank] - max(0, s.bounds[rank] - 8)) * s.nr
@@ -187,6 +247,8 @@ def gpu_worker(rank, world, port, frames, result_path):
         parts = dict(ids=s.sim.getIds().astype(np.uint32), pos=pos, vel=np.c_[s.sim.getVelocity(), np.ones(len(pos))],
                      rnd=s.sim.getRand(), avg=s.sim.getField("moments01_avg")[lo:hi],
                      cnt=s.sim.getField("cell_count")[lo:hi], moved=s.migrated)
+        if solve:
+            parts.update(phi=s.sim.getField("phi")[lo:hi], E=s.sim.getField("E")[lo:hi])
         out = _gather(rank, world, parts)
         if rank == 0:
             np.savez(result_path, **assemble(out))
@@ -194,7 +256,7 @@ def gpu_worker(rank, world, port, frames, result_path):
         dist.destroy_process_group()
 
 
-def single_oracle(frames):
+def single_oracle(frames, solve=False):
     from fusion_sim_b200.scenes import apply_scene
     from oracle.oracle import OraclePusher
     sc = scene_for_dist()
@@ -203,4 +265,6 @@ def single_oracle(frames):
     for _ in range(frames):
         o.step()
         o.density()
+        if solve:
+            o.solveFields(SOLVE)
     return o

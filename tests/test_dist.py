@@ -25,9 +25,13 @@ def free_port():
     return p
 
 
-def check_against_single(path):
+def check_against_single(path, solve=False):
     got = np.load(path)
-    o = dh.single_oracle(FRAMES)
+    o = dh.single_oracle(FRAMES, solve)
+    if solve:  # the slab-decomposed field solve equals the single-process one bit for bit
+        assert_same(got["phi"], o.getField("phi"), "potential")
+        assert_same(got["E"], o.getField("E"), "E")
+        assert np.abs(got["phi"]).max() > 0 and np.abs(o.A).max() > 0
     assert_same(got["ids"], np.arange(o.n, dtype=got["ids"].dtype), "every particle exactly once")
     assert_same(got["pos"], o.getPosition(), "position")
     assert_same(got["vel"], o.getVelocity(), "velocity")
@@ -57,3 +61,20 @@ def test_two_gpus_nccl_match_single_oracle(tmp_path):
     path = str(tmp_path / "res.npz")
     mp.spawn(dh.gpu_worker, args=(2, free_port(), FRAMES, path), nprocs=2, join=True)
     check_against_single(path)
+
+
+def test_two_ranks_gloo_self_consistent_fields(tmp_path):
+    """EXTENSION: step -> density -> solveFields on two slabs (halo rows of charge
+    source, potential and E exchanged between the stages) against the single-process oracle."""
+    path = str(tmp_path / "res.npz")
+    mp.spawn(dh.cpu_worker, args=(2, free_port(), FRAMES, path, True), nprocs=2, join=True)
+    check_against_single(path, solve=True)
+
+
+@pytest.mark.gpu
+def test_two_gpus_nccl_self_consistent_fields(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    path = str(tmp_path / "res.npz")
+    mp.spawn(dh.gpu_worker, args=(2, free_port(), FRAMES, path, True), nprocs=2, join=True)
+    check_against_single(path, solve=True)
