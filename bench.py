@@ -235,9 +235,13 @@ def run_ours(args):
     canvases = [t.numpy() for t in _keep3]
     canvas = canvases[0]
 
+    solve = {"macro_weight": 1.0e6, "sweeps": args.field_sweeps, "omega": 1.0} if args.field_sweeps > 0 else None
+
     def frame():
         sim.step()
         sim.density()
+        if solve:  # EXTENSION: the self-consistent frame; off by default (the reference has none)
+            sim.solveFields(solve)
 
     def barrier():
         sim.sync()
@@ -282,8 +286,8 @@ def run_ours(args):
     for _ in range(args.steps):
         frame()
     kern = {}
-    for nm in ("push", "push2", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_heavy", "conv",
-               "migrate_pack", "migrate_unpack"):
+    for nm in ("push", "push2", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_warp", "cellsum_heavy", "conv",
+               "migrate_pack", "migrate_unpack", "charge_source", "relax4", "relax2", "relax1", "efield", "precalc"):
         ms, cnt = sim.timing_get(nm)
         if cnt:
             kern[nm] = {"ms_per_launch": ms / cnt, "launches_per_step": cnt / args.steps,
@@ -340,6 +344,28 @@ def run_ours(args):
                    "canvas read-back (own rows) to pinned host memory on a copy stream, overlapping the next frame; upload "
                    "amortised over the K frames; wall clock to the last byte on the host"}
 
+    # ---- EXTENSION row N4, reported beside the headline (never inside it unless --field-sweeps is given):
+    # device time of one solveFields() of 8 sweeps and of its kernels on this workload's grid
+    ext = None
+    if world == 1 and not solve:
+        probe = {"macro_weight": 1.0e6, "sweeps": 8, "omega": 1.0}
+        sim.solveFields(probe)  # allocation + warm-up
+        sim.timing(True)
+        sim.timing_reset()
+        sim.mark(4)
+        for _ in range(5):
+            sim.solveFields(probe)
+        sim.mark(5)
+        ext = {"what": "solveFields(8 weighted-Jacobi sweeps) = charge source + 2 x relax4 (TMA-staged, 4 sweeps per "
+                       "launch) + E = -grad(phi) + precalc; EXTENSION, no reference counterpart",
+               "ms_per_solve": sim.elapsed_ms(4, 5) / 5, "kernels_ms_per_launch": {}}
+        rs = 8 if args.precision == "f64" else 4
+        for nm, nbytes in (("charge_source", 2 * rs), ("relax4", 3 * rs), ("efield", 4 * rs), ("precalc", 14 * rs)):
+            ms, cnt = sim.timing_get(nm)
+            if cnt:
+                ext["kernels_ms_per_launch"][nm] = {"ms": ms / cnt, "algorithmic_GBps": nbytes * ncell_local / (ms / cnt * 1e-3) / 1e9}
+        sim.timing(False)
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, _, _ = cpu_baseline(args.workload, args.precision, 0)
@@ -351,13 +377,16 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": desc, "particles_total": n_total, "grid": [nr, nz],
-                       "precision": args.precision, "frame": "step()+density() = 2 half-steps + deposit",
+                       "precision": args.precision,
+                       "frame": "step()+density() = 2 half-steps + deposit" + (
+                           " + solveFields(%d sweeps) [EXTENSION]" % args.field_sweeps if solve else ""),
                        "l2": "inputs larger than L2 (particle state %.1f GB per GPU)" % (
                            n_local * (81 if args.precision == "f64" else 41) / 1e9),
                        "parallelism": "slab%d" % world},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb,
             "push_only_pushes_per_s": halves * n_local * world / (push_ms * 1e-3),
+            "extension_field_solve": ext,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -374,6 +403,8 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--field-sweeps", type=int, default=0,
+                    help="EXTENSION: add solveFields(N sweeps) to every frame (self-consistent fields); 0 = the reference's frame")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:

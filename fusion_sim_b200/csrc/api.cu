@@ -370,8 +370,9 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
         FSIM_TRY(dalloc_bytes(&s->mom, s->rs * 4 * s->plane));
         FSIM_TRY(dalloc_bytes(&s->norm, s->rs * 4 * s->plane));
     }
-    FSIM_TRY(dalloc(&s->heavy_list, s->cap / 64 + 2));
-    FSIM_TRY(dalloc(&s->heavy_n, 1));
+    FSIM_TRY(dalloc(&s->heavy_list, s->cap / 256 + 2));
+    FSIM_TRY(dalloc(&s->medium_list, s->cap / 16 + 2));
+    FSIM_TRY(dalloc(&s->heavy_n, 2));
     FSIM_TRY(dalloc(&s->oob, 1));
     FSIM_TRY(dalloc(&s->mscratch, 2 * 64 + 8));
     FSIM_TRY(dalloc(&s->hole_flag, s->cap));
@@ -415,7 +416,7 @@ static void free_all(fsim_sim *s)
     }
     void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->dcol[2], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
-                    s->heavy_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf};
+                    s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf};
     for (void *p : ptrs) cudaFree(p);
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef);
     for (auto &kv : s->timers)

@@ -116,8 +116,9 @@ struct fsim_sim {
     uint32_t *cellcount = nullptr;  // [ncell_local]
     void *mom = nullptr, *norm = nullptr;  // [ncell_local][4] (FSIM_FLAG_KEEP_MOMENTS)
     void *avg = nullptr;         // [ncell_local][4]
-    uint32_t *heavy_list = nullptr;  // cells whose population exceeds the per-thread limit
-    uint32_t *heavy_n = nullptr;
+    uint32_t *heavy_list = nullptr;   // cells summed by one block each (> 256 particles)
+    uint32_t *medium_list = nullptr;  // cells summed by one warp each (17..256 particles)
+    uint32_t *heavy_n = nullptr;      // [2]: lengths of heavy_list, medium_list
     uint32_t *oob = nullptr;     // particles whose gather row fell outside the local table
 
     // EXTENSION: self-consistent field solve (fieldsolve.cu), allocated at the first fsim_solve_fields()

@@ -20,7 +20,8 @@
 
 namespace fsim {
 
-constexpr int THREAD_CELL_MAX = 64;  // larger cells go to the block-per-cell path
+constexpr int THREAD_CELL_MAX = 16;   // up to here: one thread per cell, (id, slot) pairs sorted in registers
+constexpr int WARP_CELL_MAX = 256;    // up to here: one warp per cell; larger cells: one block per cell
 
 template <typename Real>
 struct CellSumArgs {
@@ -33,7 +34,8 @@ struct CellSumArgs {
     uint32_t *count;  // [ncell]
     int pitch;
     int64_t plane;
-    uint32_t *heavy_list, *heavy_n;
+    uint32_t *heavy_list, *heavy_n;   // heavy_n[0]: cells for the block path, heavy_n[1]: for the warp path
+    uint32_t *medium_list;
     int64_t ncell;
     int nr, nz, row0;
     // scratch of the block-per-cell path (the idle half of the particle double buffer)
@@ -107,37 +109,79 @@ __global__ void __launch_bounds__(128) cellsum_kernel(const CellSumArgs<Real> a)
         cell_small<Real, 8>(a, s, k, acc, cnt);
     } else if (k <= 16) {
         cell_small<Real, 16>(a, s, k, acc, cnt);
-    } else if (k > THREAD_CELL_MAX) {
+    } else if (k > WARP_CELL_MAX) {
         a.heavy_list[atomicAdd(a.heavy_n, 1u)] = (uint32_t)c;
         return;
     } else {
-        unsigned long long done = 0ull;
-        for (uint32_t t = 0; t < k; ++t) {
-            // selection: the not-yet-used particle of this cell with the smallest id
-            // (ids are unique and < 0xffffffff)
-            uint32_t best = 0xffffffffu, bj = 0;
-            uint32_t p = 0;
-            for (uint32_t j = 0; j < k; ++j) {
-                const uint32_t pj = a.perm[s + j];
-                const uint32_t v = a.id[pj & KEY_MASK];
-                if (!((done >> j) & 1ull) && v < best) {
-                    best = v;
-                    bj = j;
-                    p = pj;
-                }
-            }
-            done |= 1ull << bj;
-            if (!(p & KEY_CLIPPED)) {
-                acc[0] += a.dcol[0][p]; acc[1] += a.dcol[1][p]; acc[2] += a.dcol[2][p];
-                acc[3] += (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
-                cnt++;
-            }
-        }
+        a.medium_list[atomicAdd(a.heavy_n + 1, 1u)] = (uint32_t)c;
+        return;
     }
     if (!live) return;
     Real *o = a.S + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr);
     o[0] = acc[0]; o[a.plane] = acc[1]; o[2 * a.plane] = acc[2]; o[3 * a.plane] = acc[3];
     a.count[c] = cnt;
+}
+
+// One warp per cell of 17..256 particles (the reference's own demo scene: 12-35 per occupied cell,
+// up to 100).  Lanes hold the (id, slot) pairs; an element's position in id order is the number of
+// smaller ids, counted with one shuffle per element; the colours are fetched in parallel and parked
+// in shared memory in id order; lanes 0..3 then add one channel each, sequentially.
+template <typename Real>
+__global__ void __launch_bounds__(128) cellsum_warp_kernel(const CellSumArgs<Real> a)
+{
+    constexpr int NQ = WARP_CELL_MAX / 32;
+    __shared__ Real s_col[4][3][WARP_CELL_MAX];
+    __shared__ uint8_t s_on[4][WARP_CELL_MAX];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t nmed = a.heavy_n[1];
+    for (uint32_t h = blockIdx.x * 4 + w; h < nmed; h += gridDim.x * 4) {
+        const uint32_t c = a.medium_list[h];
+        const uint32_t s = a.starts[c], k = a.starts[c + 1] - s;
+        uint32_t pp[NQ], ii[NQ], rank[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const uint32_t j = q * 32 + lane;
+            pp[q] = (q * 32 < k && j < k) ? a.perm[(size_t)s + j] : KEY_CLIPPED;
+            ii[q] = (q * 32 < k && j < k) ? a.id[pp[q] & KEY_MASK] : 0xffffffffu;
+            rank[q] = 0;
+        }
+#pragma unroll
+        for (int qt = 0; qt < NQ; ++qt) {
+            if (qt * 32 >= k) break;  // warp-uniform
+            const int nt = min(32u, k - qt * 32);
+            for (int lt = 0; lt < nt; ++lt) {
+                const uint32_t v = __shfl_sync(0xffffffffu, ii[qt], lt);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) rank[q] += (v < ii[q]) ? 1u : 0u;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (q * 32 >= k) break;
+            if (q * 32 + lane < k) {
+                const bool on = !(pp[q] & KEY_CLIPPED);
+                const size_t p = pp[q] & KEY_MASK;
+                const uint32_t r = rank[q];
+                s_on[w][r] = on ? 1 : 0;
+                s_col[w][0][r] = on ? a.dcol[0][p] : (Real)0;
+                s_col[w][1][r] = on ? a.dcol[1][p] : (Real)0;
+                s_col[w][2][r] = on ? a.dcol[2][p] : (Real)0;
+            }
+        }
+        __syncwarp();
+        if (lane < 4) {
+            Real acc = (Real)0;
+            uint32_t cnt = 0;
+            for (uint32_t t = 0; t < k; ++t) {
+                if (!s_on[w][t]) continue;
+                acc += (lane < 3) ? s_col[w][lane < 3 ? lane : 0][t] : (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
+                cnt++;
+            }
+            a.S[(size_t)lane * a.plane + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr)] = acc;
+            if (lane == 3) a.count[c] = cnt;
+        }
+        __syncwarp();
+    }
 }
 
 // One block per crowded cell: colours in parallel, ids sorted by an ascending-only bitonic
@@ -245,17 +289,24 @@ int launch_cellsum(fsim_sim *s)
         a.count = s->cellcount;
         a.pitch = s->pitch; a.plane = s->plane;
         a.heavy_list = s->heavy_list; a.heavy_n = s->heavy_n;
+        a.medium_list = s->medium_list;
         a.ncell = s->ncell_local;
         a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0;
         a.sid = (uint32_t *)s->part[alt][4];
         a.sidx = (uint32_t *)s->part[alt][5];
-        FSIM_CUDA(cudaMemsetAsync(s->heavy_n, 0, sizeof(uint32_t), s->stream));
+        FSIM_CUDA(cudaMemsetAsync(s->heavy_n, 0, 2 * sizeof(uint32_t), s->stream));
         {
             Bracket b(s, "cellsum");
             cellsum_kernel<Real><<<grid_for(s->ncell_local, 128), 128, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());
         }
-        {   // crowded cells (count read on the device: no host round trip)
+        // crowded cells (list lengths are read on the device: no host round trip)
+        {
+            Bracket b(s, "cellsum_warp");
+            cellsum_warp_kernel<Real><<<148 * 4, 128, 0, s->stream>>>(a);
+            FSIM_CUDA(cudaGetLastError());
+        }
+        {
             Bracket b(s, "cellsum_heavy");
             cellsum_heavy_kernel<Real><<<148 * 4, 256, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());

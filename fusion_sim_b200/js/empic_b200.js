@@ -52,6 +52,15 @@ exports.makeCylindricalParticlePusher = function (spec) {
   out.precalc = () => sim.precalc();
   out.step = () => sim.step();
   out.density = () => sim.density();
+  // EXTENSION (no reference counterpart): self-consistent electrostatic field solve, include/fusionsim.h
+  out.solveFields = function (value) {
+    for (const p of ['macro_weight', 'sweeps']) {
+      if (typeof value[p] === 'undefined') throw new Error('.' + p + ' <- Non-optional property is undefined!');
+      if (typeof value[p] !== 'number') throw new Error('.' + p + ' <- Property does not match any given possible types!');
+    }
+    sim.solveFields(value.macro_weight, value.sweeps, typeof value.omega === 'number' ? value.omega : 1.0,
+                    value.source === 'instant' ? 1 : 0);
+  };
   // accessors (extension)
   out.getPositions = () => { const a = new Float64Array(4 * spec.nparticles * spec.nparticles); sim.getArray('position', a); return a; };
   out.getVelocities = () => { const a = new Float64Array(3 * spec.nparticles * spec.nparticles); sim.getArray('velocity', a); return a; };

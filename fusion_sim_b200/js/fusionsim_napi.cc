@@ -33,6 +33,7 @@ class Sim : public Napi::ObjectWrap<Sim> {
             InstanceMethod("precalc", &Sim::Precalc),
             InstanceMethod("step", &Sim::Step),
             InstanceMethod("density", &Sim::Density),
+            InstanceMethod("solveFields", &Sim::SolveFields),
             InstanceMethod("render", &Sim::Render),
             InstanceMethod("getArray", &Sim::GetArray),
             InstanceMethod("destroy", &Sim::Destroy),
@@ -95,6 +96,13 @@ class Sim : public Napi::ObjectWrap<Sim> {
     Napi::Value Precalc(const Napi::CallbackInfo &i) { check(i.Env(), fsim_precalc(sim_)); return i.Env().Undefined(); }
     Napi::Value Step(const Napi::CallbackInfo &i) { check(i.Env(), fsim_step(sim_)); return i.Env().Undefined(); }
     Napi::Value Density(const Napi::CallbackInfo &i) { check(i.Env(), fsim_density(sim_)); return i.Env().Undefined(); }
+    // EXTENSION (no reference counterpart): solveFields(macro_weight, sweeps, omega, source)
+    Napi::Value SolveFields(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_solve_fields(sim_, i[0].As<Napi::Number>().DoubleValue(), i[1].As<Napi::Number>().Int32Value(),
+                                         i[2].As<Napi::Number>().DoubleValue(), i[3].As<Napi::Number>().Int32Value()));
+        return i.Env().Undefined();
+    }
     Napi::Value Render(const Napi::CallbackInfo &i)
     {
         check(i.Env(), fsim_render_rgba8(sim_, i[0].As<Napi::Uint8Array>().Data()));

@@ -17,7 +17,7 @@ sc = bench.build_scene(workload, 0, 1)
 spec = dict(sc["spec"], precision=precision, flags=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 sim = makeCylindricalParticlePusher(spec)
 apply_scene(sim, sc)
-names = ("push", "push2", "scan", "permute", "index_scatter", "cellsum", "cellsum_heavy", "conv", "prepass")
+names = ("push", "push2", "scan", "permute", "index_scatter", "cellsum", "cellsum_warp", "cellsum_heavy", "conv", "prepass")
 out = {}
 for v in variants:
     os.environ["FSIM_PUSH_VARIANT"] = str(v)
