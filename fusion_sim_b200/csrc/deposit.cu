@@ -321,16 +321,19 @@ int launch_cellsum(fsim_sim *s)
 // completion) brings the tile and its 5-cell halo of all four channels into shared memory;
 // coordinates outside the tensor -- the grid edge -- are zero-filled by the TMA unit, which is
 // exactly "sprites are clipped at the target edge": adding exact zeros equals skipping the source.
-// A warp owns one channel of a 32-column x 4-row strip; a lane owns one column: per column offset
-// di it loads two vertical 14-value windows (columns -di and +di; consecutive lanes read
-// consecutive words, so no bank conflicts for any plane stride) and slides them over its 4
-// outputs.  The footprint is mirror-symmetric, so the up to four mirror sources of a weight are
-// added first and weighted once: classes di = 0..5 outer, dj = 0..5 inner, sources (-di,-dj),
-// (+di,-dj), (-di,+dj), (+di,+dj) -- the canonical order of the oracle; the 40 taps that are
-// exactly zero are removed at compile time.  107 fp64 operations per cell and channel: the kernel
-// is bound by the fp64 pipe.
+// A warp owns one channel of a 32-column x CSTRIP-row strip; a lane owns one column: per column
+// offset di it reads two vertical windows of CSTRIP + 10 values (columns -di and +di; consecutive
+// lanes read consecutive words, so no bank conflicts for any plane stride) and slides them over
+// its CSTRIP outputs.  The footprint is mirror-symmetric, so the up to four mirror sources of a
+// weight are added first and weighted once: classes di = 0..5 outer, dj = 0..5 inner, sources
+// (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj) -- the canonical order of the specification; the 40
+// taps that are exactly zero are removed at compile time.  107 fp64 operations per cell and channel
+// plus the two IEEE divisions of the normalisation: the kernel is bound by the fp64 pipe (72 %
+// active in ncu).  Measured on B200 at C5 fp64 (FSIM_CONV_VARIANT, tools/tune.py): 8-row strips on
+// 32 x 8 tiles 0.65 ms, 8-row strips on 32 x 16 tiles 0.69, 4-row strips on 32 x 16 tiles 0.86,
+// 16-row strips 0.88-0.90, 2-row strips 1.50 -- longer strips need fewer shared-memory loads per
+// output, small tiles put more blocks on an SM to hide the single TMA wait of each.
 constexpr int CT_I = 32;                        // output tile width (one lane per column)
-constexpr int CT_J_MAX = 32;                    // tallest output tile of any variant (sizes the tensor-map box)
 constexpr int CH = FSIM_SHAPE_MID;              // halo = 5
 // TMA needs the box START (innermost coordinate x element size) 16-byte aligned, and the box width
 // a multiple of 16 bytes: the box therefore begins CXOFF >= 5 cells left of the tile, CXOFF a
