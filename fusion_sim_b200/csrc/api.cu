@@ -25,7 +25,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 }
 
 int upload_shape(const double *shape64, const double *shape32);
-int upload_costab(const double *c);
+int upload_costab(const double *c64, const float *c32);
 
 static int fail(int code, const std::string &msg)
 {
@@ -382,9 +382,15 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     build_shape(shape64, false);
     build_shape(shape32, true);
     FSIM_TRY(upload_shape(shape64, shape32));
+    // empic.js:317: the argument is formed in the shader's working precision, its cosine is the host libm's
     double costab[FSIM_NQUAD];
-    for (int k = 0; k < FSIM_NQUAD; ++k) costab[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);  // :317
-    FSIM_TRY(upload_costab(costab));
+    float costab32[FSIM_NQUAD];
+    for (int k = 0; k < FSIM_NQUAD; ++k) {
+        costab[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);
+        const float a = (float)FSIM_PI_GLSL * ((float)k + 0.5f) / 1000.0f;
+        costab32[k] = (float)cos((double)a);
+    }
+    FSIM_TRY(upload_costab(costab, costab32));
 
     // ids, default rand / entropy
     const uint64_t seed = 0x5EEDF0510Cull;

@@ -19,12 +19,10 @@ template <typename Real> __device__ __forceinline__ Real cos_tab(int k);
 template <> __device__ __forceinline__ double cos_tab<double>(int k) { return c_cos_f64[k]; }
 template <> __device__ __forceinline__ float cos_tab<float>(int k) { return c_cos_f32[k]; }
 
-int upload_costab(const double *c)
+int upload_costab(const double *c64, const float *c32)
 {
-    float f[FSIM_NQUAD];
-    for (int k = 0; k < FSIM_NQUAD; ++k) f[k] = (float)c[k];
-    FSIM_CUDA(cudaMemcpyToSymbol(c_cos_f64, c, sizeof(double) * FSIM_NQUAD));
-    FSIM_CUDA(cudaMemcpyToSymbol(c_cos_f32, f, sizeof(f)));
+    FSIM_CUDA(cudaMemcpyToSymbol(c_cos_f64, c64, sizeof(double) * FSIM_NQUAD));
+    FSIM_CUDA(cudaMemcpyToSymbol(c_cos_f32, c32, sizeof(float) * FSIM_NQUAD));
     return FSIM_OK;
 }
 

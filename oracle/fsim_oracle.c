@@ -2,8 +2,9 @@
  *
  * CPU oracle for the particle-step path of kcdodd/fusion-sim: a restatement of
  * the reference's GLSL shaders and host-side set() code in plain C.
- * PARITY UNPINNED (no reference tests/golden vectors exist; the reference
- * cannot run here) -- see the header of fsim_oracle_impl.h and DESIGN.md.
+ * Pinned to the reference's own shader source, executed by oracle/glsl_interp.py
+ * (tests/test_reference_glsl.py); what stays unpinned is listed in the header of
+ * fsim_oracle_impl.h and in DESIGN.md section 2.
  *
  * Build: oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
  * Callers: tests/, __graft_entry__.smoke(), bench.py cpu_baseline and
@@ -80,12 +81,20 @@ double orc_tofixed20(double x)
     return strtod(buf, NULL);
 }
 
-/* cos(PI*(k+0.5)/1000) of empic.js:317, evaluated in double by the host libm
- * (the GLSL literal 3.14159265359), one value per quadrature point.          */
-void orc_cos_table(double *out)
+/* cos(PI*(k+0.5)/1000) of empic.js:317 (the GLSL literal 3.14159265359), one value per quadrature
+ * point.  The ARGUMENT is formed in the shader's working precision -- float arithmetic when
+ * as_f32 != 0, exactly as the GLSL expression is written -- and the cosine of that argument is the
+ * host libm's (GLSL ES 1.00 gives cos no accuracy bound).                                     */
+void orc_cos_table(double *out, int as_f32)
 {
-    for (int k = 0; k < FSIM_NQUAD; ++k)
-        out[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);
+    for (int k = 0; k < FSIM_NQUAD; ++k) {
+        if (as_f32) {
+            const float a = (float)FSIM_PI_GLSL * ((float)k + 0.5f) / 1000.0f;
+            out[k] = (double)(float)cos((double)a);
+        } else {
+            out[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);
+        }
+    }
 }
 
 /* Deposit footprint, empic.js:949-971.  as_f32 != 0 reproduces the

@@ -4,10 +4,17 @@
  * (public/javascripts/empic.js).  Included twice by fsim_oracle.c, once with
  * REAL=double / SFX=f64 and once with REAL=float / SFX=f32.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and
- * cannot be executed here (WebGL + DOM, no JS engine) -- see SURVEY.md section 8c.
- * This file is therefore the written-down contract, checked by an independent
- * NumPy restatement (oracle/numpy_ref.py) and analytic invariants (tests/).
+ * PINNING: the reference ships no tests, golden vectors or fixtures and cannot run as a
+ * whole here (WebGL + DOM, no JS engine).  Its SHADERS can: their
+ * GLSL text is read out of /root/reference/public/javascripts/empic.js and executed by
+ * oracle/glsl_interp.py (tests/golden/make_reference_vectors.py); this file must
+ * reproduce those outputs bit for bit (tests/test_reference_glsl.py: static fields,
+ * precalc, half-steps, sprite deposit, normalise, running average, canvas; fp64 and
+ * fp32).  Still unpinned: what GLSL ES 1.00 / GL leave open (rounding of / and sqrt,
+ * evaluation order, NaN texture coordinates, fixed-function blending and rasterisation)
+ * -- there the documented IEEE / left-to-right choices below apply -- and the host-side
+ * JavaScript of set() (inverse-cdf table), which is restated and cross-checked by an
+ * independent NumPy restatement (oracle/numpy_ref.py) and analytic invariants (tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may call into this file.  The product never does.
@@ -89,16 +96,19 @@ void ORC(orc_half_step)(int64_t n, REAL *pos, REAL *vel, REAL *rnd,
             REAL c0 = (r1[0] * vr + r1[1] * va + r1[2] * vz) + a[0];
             REAL c1 = (r2[0] * vr + r2[1] * va + r2[2] * vz) + a[1];
             REAL c2 = (r3[0] * vr + r3[1] * va + r3[2] * vz) + a[2];
+            REAL nvw; /* the w texel channel: written, never read by any shader */
             if (alive > RC(0.5)) {
                 nvx = c0 * dx - c1 * dy;
                 nvy = c0 * dy + c1 * dx;
                 nvz = c2;
+                nvw = RC(1.0);
             } else { /* just respawned: fresh random velocity, empic.js:772 */
                 nvx = RC(FSIM_RESPAWN_SPEED) * (RC(2.0) * q0 - RC(1.0));
                 nvy = RC(FSIM_RESPAWN_SPEED) * (RC(2.0) * q1 - RC(1.0));
                 nvz = RC(FSIM_RESPAWN_SPEED) * (RC(2.0) * q2 - RC(1.0));
+                nvw = RC(FSIM_RESPAWN_SPEED) * RC(1.0); /* 0.001 * vec4(.., 1.0): found by running the shader text */
             }
-            V[0] = nvx; V[1] = nvy; V[2] = nvz; V[3] = RC(1.0);
+            V[0] = nvx; V[1] = nvy; V[2] = nvz; V[3] = nvw;
         }
 
         /* --- step_position_frag, empic.js:714-719 ------------------------- */

@@ -51,6 +51,7 @@ def half_step(pos, vel, rnd, ent, R1, R2, R3, A, sink, invcdf, nr, nz, step_fact
         fresh = T(0.001) * (T(2.0) * rnd[:, 0:3] - T(1.0))
         new_vel = np.ones_like(vel)
         new_vel[:, 0:3] = np.where((alive > T(0.5))[:, None], nv, fresh)
+        new_vel[:, 3] = np.where(alive > T(0.5), T(1.0), T(0.001) * T(1.0))  # w: written, never read (:772)
         # position
         nxt = pos[:, 0:3] + T(step_factor) * new_vel[:, 0:3]
         rn = np.sqrt(nxt[:, 0] * nxt[:, 0] + nxt[:, 1] * nxt[:, 1])

@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- ctypes front end of the CPU oracle (oracle/fsim_oracle.c).
 
-PARITY UNPINNED: the reference (kcdodd/fusion-sim, public/javascripts/empic.js) has no
-tests or golden vectors and cannot run headless; this oracle restates its shaders.
+The reference (kcdodd/fusion-sim, public/javascripts/empic.js) has no tests or golden vectors and
+cannot run headless as a whole; this oracle restates its shaders and is held bit for bit to the
+outputs of executing the reference's own GLSL text (tests/test_reference_glsl.py).
 
 ``OraclePusher`` mirrors the reference's simulation object (empic.js:1157-1526: set,
 addCurrentLoop, addCurrentZ, addBZ, addBTheta, precalc, step, density, canvas) so that a
@@ -27,14 +28,23 @@ N_INVCDF = 512
 
 
 def build(force: bool = False) -> str:
+    """Build libfsim_oracle.so if it is missing or older than its sources.  Serialised with a file
+    lock: the multi-rank tests import this module from several processes at once."""
+    import fcntl
     so = os.path.join(_HERE, "libfsim_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("fsim_oracle.c", "fsim_oracle_impl.h", "fsim_oracle_jacobi_impl.h",
-                                                 "fsim_oracle_fields_impl.h", "Makefile")]
+                                             "fsim_oracle_fields_impl.h", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "fsim_constants.h"))
-    stale = (not os.path.exists(so)) or any(
-        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
-    if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+
+    def stale():
+        return (not os.path.exists(so)) or any(
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+
+    if force or stale():
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or stale():  # another process may have built it while we waited
+                subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
     return so
 
 
@@ -55,9 +65,9 @@ def tofixed20(x: float) -> float:
     return float(lib().orc_tofixed20(float(x)))
 
 
-def cos_table() -> np.ndarray:
+def cos_table(as_f32: bool = False) -> np.ndarray:
     out = np.empty(1000, np.float64)
-    lib().orc_cos_table(_p(out))
+    lib().orc_cos_table(_p(out), C.c_int(1 if as_f32 else 0))
     return out
 
 
@@ -110,7 +120,7 @@ class OraclePusher:
         self.cell_count = np.zeros(self.ncell, np.uint32)
         self.moments01, self.moments01_norm, self.moments01_avg = (z4(self.ncell) for _ in range(3))
         self.shape = shape_table(self.precision == "f32").astype(self.dt)
-        self.costab = cos_table().astype(self.dt)
+        self.costab = cos_table(self.precision == "f32").astype(self.dt)
         self._loop_tables = None
         self.last_cell = np.zeros(self.n, np.int64)
         self.deposit_cell = np.zeros(self.n, np.int64)

@@ -1,0 +1,277 @@
+"""Generates tests/golden/reference_glsl_{f64,f32}.npz by EXECUTING THE REFERENCE'S OWN SHADER SOURCE.
+
+Runs only where /root/reference exists (this container).  The GLSL text of every program on the
+hot path is read out of /root/reference/public/javascripts/empic.js at run time (string arrays,
+with the `N(expr)` = expr.toFixed(20) insertions of empic.js:23-25 evaluated as the JS would) and
+executed fragment by fragment with the interpreter in oracle/glsl_interp.py.  Nothing of the
+reference's source is copied into this repository: only the numeric inputs and outputs of that
+execution are saved, and tests/test_reference_glsl.py holds the CPU oracle to them bit for bit.
+
+What the draw calls bind to what (cited from empic.js) is restated here, in `run()`:
+  addCurrentLoop :1352-1363 (shape tables :295-345), addCurrentZ/BZ/BTheta :1380-1411,
+  precalc :1413-1434, step :1436-1469 with the program bindings :814-928, density :1471-1495.
+Fixed-function GL behaviour (additive blending ONE,ONE = a floating-point add in draw order, NEAREST
++ CLAMP_TO_EDGE sampling, the identity quad mapping of empic.js:66-92, GLES2 point-sprite coverage)
+is not shader text; it is emulated here as the oracle documents it.
+
+    python tests/golden/make_reference_vectors.py
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF_JS = "/root/reference/public/javascripts/empic.js"
+
+from oracle.glsl_interp import Shader, Texture  # noqa: E402
+
+C_LIGHT = 2.998e8  # empic.js:27
+SPEC = dict(radius=1.0, height=2.0, nr=24, nz=40, dt=2e-9, nparticles=16,
+            particle_mass=1.67e-27, particle_charge=1.602e-19)
+
+
+# ---- reading the shader strings out of the JavaScript ------------------------------------------
+def _js_array_elements(text, start):
+    """Elements of the JS array literal whose '[' is at text[start]; returns (elements, end)."""
+    i, depth, cur, out = start + 1, 0, [], []
+    while True:
+        c = text[i]
+        if c == '"' or c == "'":
+            j = i + 1
+            while text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            cur.append(text[i:j + 1])
+            i = j + 1
+        elif text.startswith("//", i):
+            i = text.index("\n", i)
+        elif text.startswith("/*", i):
+            i = text.index("*/", i) + 2
+        elif c in "([":
+            depth += 1; cur.append(c); i += 1
+        elif c == ")" or (c == "]" and depth > 0):
+            depth -= 1; cur.append(c); i += 1
+        elif c == "]":
+            if "".join(cur).strip():
+                out.append("".join(cur).strip())
+            return out, i
+        elif c == "," and depth == 0:
+            out.append("".join(cur).strip()); cur = []; i += 1
+        else:
+            cur.append(c); i += 1
+
+
+def _js_string_expr(expr, env):
+    """Value of `"lit" + N(expr) + "lit" ...` (the only forms empic.js uses inside src_arr)."""
+    out, i = [], 0
+    while i < len(expr):
+        c = expr[i]
+        if c in "\"'":
+            j = i + 1
+            while expr[j] != c:
+                j += 2 if expr[j] == "\\" else 1
+            out.append(bytes(expr[i + 1:j], "utf-8").decode("unicode_escape"))
+            i = j + 1
+        elif expr.startswith("N(", i):
+            j, depth = i + 2, 1
+            while depth:
+                depth += {"(": 1, ")": -1}.get(expr[j], 0)
+                j += 1
+            value = eval(expr[i + 2:j - 1], {"__builtins__": {}}, env)  # e.g. factor_r/factor_z
+            out.append("%.20f" % value)  # Number.prototype.toFixed(20)
+            i = j
+        elif c in "+ \t\n":
+            i += 1
+        else:
+            raise SyntaxError("unexpected JS in a shader string array: " + expr[i:i + 40])
+    return "".join(out)
+
+
+def shader_sources(env):
+    """{name: [GLSL source, ...]} -- name = the `var NAME =` that owns each `src_arr` array."""
+    text = open(REF_JS).read()
+    owners = [(m.start(), m.group(1)) for m in
+              re.finditer(r"var\s+(\w+)\s*=\s*(?:function\s*\(|webgl\.linkProgram\s*\()", text)]
+    out = {}
+    for m in re.finditer(r"var\s+src_arr\s*=\s*\[", text):
+        name = [n for pos, n in owners if pos < m.start()][-1]
+        elems, _ = _js_array_elements(text, m.end() - 1)
+        out.setdefault(name, []).append("\n".join(_js_string_expr(e, env) for e in elems))
+    return out
+
+
+# ---- the scene ------------------------------------------------------------------------------------
+def entropy_table():
+    k = np.arange(1024 * 1024 * 4, dtype=np.float64)
+    return np.mod(k * 0.6180339887498949, 1.0).reshape(-1, 4)  # no 32 MB fixture: a formula both sides know
+
+
+def scene(dtype):
+    rng = np.random.Generator(np.random.PCG64(20261018))
+    nr, nz, side = SPEC["nr"], SPEC["nz"], SPEC["nparticles"]
+    n, nc = side * side, nr * nz
+    pos = np.ones((n, 4))
+    pos[:, 0] = 0.55 * (rng.random(n) - 0.5) * 2
+    pos[:, 1] = 0.55 * (rng.random(n) - 0.5) * 2
+    pos[:, 2] = 0.5 + 0.45 * (rng.random(n) - 0.5) * 2
+    pos[:8, 3] = 0.0                      # "just respawned": fresh random velocity (empic.js:772)
+    pos[8, 0] = pos[8, 1] = 0.0           # r = 0: direction = 0/0
+    vel = np.ones((n, 4))
+    vel[:, :3] = 0.3 * (rng.random((n, 3)) - 0.5)   # fast: absorption and respawn within a few half-steps
+    rnd = rng.random((n, 4))
+    E = np.ones((nc, 4))
+    E[:, :3] = 1.0e5 * (rng.random((nc, 3)) - 0.5)
+    sink = np.ones((nr, nz))
+    sink[nr - 1, :] = 0
+    sink[1:nr - 1, 0] = 0
+    sink[1:nr - 1, nz - 1] = 0
+    sink_tex = np.zeros((nc, 4))
+    sink_tex[:, 0] = sink.T.reshape(-1)
+    source = np.zeros((nr, nz))
+    source[0:3, 17:23] = 1.0
+    mom = np.zeros((nc, 4))
+    mom[:, :3] = rng.random((nc, 3)) - 0.5
+    mom[:, 3] = np.where(rng.random(nc) > 0.3, rng.random(nc), 0.0)
+    avg = rng.random((nc, 4))
+    cast = lambda a: a.astype(dtype)
+    return dict(position=cast(pos), velocity=cast(vel), rand=cast(rnd), E=cast(E), sink=cast(sink_tex),
+                source_pdf=source, moments01=cast(mom), avg0=cast(avg))
+
+
+def quad_coords(w, h, dtype):
+    """v_texCoord of the fragment at texel (i, j): ((i+.5)/w, (j+.5)/h), fragments in texel order i + j*w."""
+    T = np.dtype(dtype).type
+    i = np.tile(np.arange(w), h).astype(dtype)
+    j = np.repeat(np.arange(h), w).astype(dtype)
+    return np.stack([(i + T(0.5)) / T(w), (j + T(0.5)) / T(h)], 1)
+
+
+def run(dtype):
+    from oracle import oracle as orc
+    dtype = np.dtype(dtype)
+    sp = SPEC
+    nr, nz, side = sp["nr"], sp["nz"], sp["nparticles"]
+    n, nc = side * side, nr * nz
+    h = sp["particle_charge"] * sp["dt"] / (2 * sp["particle_mass"])  # empic.js:44
+    env = dict(factor_r=1 / sp["radius"], factor_z=1 / sp["height"], h=h, speed_of_light=C_LIGHT)
+    src = shader_sources(env)
+    sh = lambda name, k=0: Shader(src[name][k], dtype)
+    sc = scene(dtype)
+    out = {k: v for k, v in sc.items()}
+    grid = quad_coords(nr, nz, dtype)
+    part = quad_coords(side, side, dtype)
+    tex = lambda a, w, hh: Texture(a, w, hh)
+    frag = lambda prog, coords, **u: prog.run(len(coords), dict(u, v_texCoord=coords))["gl_FragColor"]
+
+    # -- static field: loop tables (:295-345), two opposing loops (:1352-1363, blend ONE,ONE), uniform terms
+    shape_prog = sh("programCurrentLoopShape")
+    half = frag(shape_prog, grid, u_R=0.5)
+    tenth = frag(shape_prog, grid, u_R=0.1)
+    out["loop_half"], out["loop_tenth"] = half, tenth
+    B = np.zeros((nc, 4), dtype)
+    loops = [(0.8, 2.0, -1.0e7), (0.8, 0.0, 1.0e7)]
+    for r, z, I in loops:
+        B = B + frag(sh("programCurrentLoop"), grid, u_R=r * env["factor_r"], u_Z=z * env["factor_z"], u_I=I,
+                     u_shape_half=tex(half, nr, nz), u_shape_tenth=tex(tenth, nr, nz))
+    out["B_loops"] = B.copy()
+    # gl_FragColor += on an unwritten colour: taken as "=" (documented), then blended into B
+    B = B + frag(sh("programCurrentZ"), grid, u_I=3.0e5)
+    B = B + frag(sh("programBZ"), grid, u_Bz=0.02)
+    B = B + frag(sh("programBTheta"), grid, u_Btheta=-0.01)
+    out["B"] = B
+    out["uniform_terms"] = np.array([3.0e5, 0.02, -0.01])
+    out["loops"] = np.array(loops)
+
+    # -- precalc (:1413-1434)
+    tB, tE = tex(B, nr, nz), tex(sc["E"], nr, nz)
+    R1 = frag(sh("programPre1"), grid, u_B=tB, u_h=h)
+    R2 = frag(sh("programPre2"), grid, u_B=tB, u_h=h)
+    R3 = frag(sh("programPre3"), grid, u_B=tB, u_h=h)
+    A = frag(sh("programPreA"), grid, u_B=tB, u_E=tE, u_h=h)
+    out.update(R1=R1, R2=R2, R3=R3, A=A)
+
+    # -- step (:1436-1469): rand, velocity, position, each reading the buffers empic.js:814-928 binds
+    invcdf = np.zeros((512 * 512, 4), dtype)
+    invcdf[:, :2] = orc.inv_cdf(sc["source_pdf"]).astype(dtype)  # host JS code (:1268-1339), an INPUT here
+    ent = entropy_table().astype(dtype)
+    t_ent, t_inv, t_sink = tex(ent, 1024, 1024), tex(invcdf, 512, 512), tex(sc["sink"], nr, nz)
+    tR = [tex(a, nr, nz) for a in (R1, R2, R3, A)]
+    pos, vel, rnd = sc["position"], sc["velocity"], sc["rand"]
+    rand_prog, vel_prog, pos_prog = sh("programStepRandB"), sh("step_velocity_frag"), sh("step_position_frag")
+    assert src["programStepRandA"] == src["programStepRandB"]
+    states = []
+    for k in range(8):
+        tp, tv, tr = tex(pos, side, side), tex(vel, side, side), tex(rnd, side, side)
+        new_rnd = frag(rand_prog, part, u_entropy=t_ent, u_rand=tr)
+        new_vel = frag(vel_prog, part, u_position=tp, u_velocity=tv, u_rand=tr, u_R_1=tR[0], u_R_2=tR[1],
+                       u_R_3=tR[2], u_A=tR[3])
+        new_pos = frag(pos_prog, part, u_position=tp, u_velocity=tex(new_vel, side, side), u_rand=tr,
+                       u_sink=t_sink, u_inv_cdf=t_inv, u_step_factor=sp["dt"] * C_LIGHT)
+        pos, vel, rnd = new_pos, new_vel, new_rnd
+        states.append((pos.copy(), vel.copy(), rnd.copy()))
+    out["step_position"] = np.stack([s[0] for s in states])
+    out["step_velocity"] = np.stack([s[1] for s in states])
+    out["step_rand"] = np.stack([s[2] for s in states])
+
+    # -- density (:1471-1495): vertex shader of the sprites, normalise, running average
+    vert = sh("programMoments01", 0).run(n, dict(a_particleTexCoord=part, u_position=tex(pos, side, side),
+                                                 u_velocity=tex(vel, side, side), u_pointsize=11.0),
+                                         outputs=("gl_Position", "gl_PointSize", "v_color"))
+    out["sprite_color"], out["sprite_position"] = vert["v_color"], vert["gl_Position"]
+    # fragment shader of the sprites (:1022) on every pixel GLES2 lets a size-11 sprite cover, additive
+    # blend in particle order; window coordinates from the vertex shader's gl_Position as the viewport maps them
+    shape = orc.shape_table(dtype == np.float32).astype(dtype)
+    t_shape = tex(np.repeat(shape[:, None], 4, 1), 11, 11)
+    frag_prog = sh("programMoments01", 1)
+    mom = np.zeros((nz, nr, 4), dtype)
+    T = dtype.type
+    for p in range(n):
+        r = np.sqrt(pos[p, 0] * pos[p, 0] + pos[p, 1] * pos[p, 1])
+        xw, yw = r * T(nr), pos[p, 2] * T(nz)   # (ndc + 1)/2 * size with ndc = 2 r - 1 as written at :997
+        if not (xw >= 0 and xw < nr and yw >= 0 and yw < nz):
+            continue
+        xs = [x for x in range(int(np.floor(xw - T(5.5))) - 1, int(np.floor(xw - T(5.5))) + 14)
+              if 0 <= x < nr and (T(x) + T(0.5)) >= xw - T(5.5) and (T(x) + T(0.5)) < xw + T(5.5)]
+        ys = [y for y in range(int(np.floor(yw - T(5.5))) - 1, int(np.floor(yw - T(5.5))) + 14)
+              if 0 <= y < nz and (T(y) + T(0.5)) >= yw - T(5.5) and (T(y) + T(0.5)) < yw + T(5.5)]
+        if not xs or not ys:
+            continue
+        px = np.array([[x, y] for y in ys for x in xs])
+        pc = np.stack([T(0.5) + ((px[:, 0].astype(dtype) + T(0.5)) - xw) / T(11),
+                       T(0.5) + ((px[:, 1].astype(dtype) + T(0.5)) - yw) / T(11)], 1)
+        col = frag_prog.run(len(px), dict(v_color=np.repeat(vert["v_color"][p:p + 1], len(px), 0), u_shape=t_shape,
+                                          gl_PointCoord=pc))["gl_FragColor"]
+        for (x, y), c in zip(px, col):
+            mom[y, x] = mom[y, x] + c
+    out["sprite_moments01"] = mom.reshape(nc, 4)
+    norm = frag(sh("programNormalizeMoments01"), grid, u_moments01=tex(sc["moments01"], nr, nz))
+    avg = frag(sh("avg_frag"), grid, u_ratio=0.01, u_next=tex(norm, nr, nz), u_avg=tex(sc["avg0"], nr, nz))
+    out.update(moments01_norm=norm, moments01_avg=avg)
+
+    # -- canvas (:1497-1504): programBMag, then programDensity blended SRC_ALPHA,ONE into the RGBA8 canvas.
+    # The two colours are the reference's shader text; clamping to [0,1], rounding to k/255 and the blend are
+    # fixed-function GL, emulated as the oracle documents them; canvas rows run top to bottom.
+    c1 = frag(sh("programBMag"), grid, u_B=tB)
+    c2 = frag(sh("programDensity"), grid, u_moments01=tex(avg, nr, nz))
+    out["bmag_color"], out["density_color"] = c1, c2
+    T = dtype.type
+    with np.errstate(invalid="ignore"):
+        clamp = lambda v: np.where(v > 0, np.where(v > 1, T(1), v), T(0)).astype(dtype)
+        quant = lambda v: np.floor(v * T(255) + T(0.5))
+        dst = quant(clamp(c1)) / T(255)
+        blended = clamp(c2) * clamp(c2[:, 3:4]) + dst
+        img = quant(clamp(blended)).astype(np.uint8).reshape(nz, nr, 4)
+    out["canvas"] = img[::-1].copy()
+    return out
+
+
+if __name__ == "__main__":
+    if not os.path.exists(REF_JS):
+        sys.exit("the reference tree is not present: the committed vectors cannot be regenerated here")
+    for name, dt in (("f64", np.float64), ("f32", np.float32)):
+        res = run(dt)
+        np.savez_compressed(os.path.join(HERE, f"reference_glsl_{name}.npz"), **res)
+        print("wrote", name, {k: v.shape for k, v in res.items() if hasattr(v, "shape")})
