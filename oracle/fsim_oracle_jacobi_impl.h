@@ -2,7 +2,10 @@
  *
  * CPU restatement of matrix_webgl.makeSORIterative (public/javascripts/matrix_webgl.js:35-711):
  * dense weighted Jacobi  x <- omega (R x + C) + (1-omega) x  on RGBA-packed textures.
- * PARITY UNPINNED (no reference tests; its only live caller, spindle.js, does not run).
+ * Pinned to the reference's shader source: programR, programC, programMVproduct, the sum_frag
+ * chain, programResult and programStats are executed from matrix_webgl.js by oracle/glsl_interp.py
+ * (tests/golden/make_reference_vectors_jacobi.py) and the LITERAL mode below reproduces them bit
+ * for bit (tests/test_reference_glsl.py) -- which also confirms defect (1) by execution.
  *
  * Packing restated from the shaders: vec_height vh = 2^n_power; the vector has L = 4 vh^2
  * entries, entry e = 4 (px + vh py) + channel (:107-127).  Row `row` of the iteration matrix is a

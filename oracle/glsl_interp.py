@@ -23,7 +23,8 @@ Semantics where GLSL ES 1.00 leaves freedom (the same choices the oracle documen
 
 Supported: precision/uniform/attribute/varying declarations, float/vec2/vec3/vec4 locals, swizzles
 (xyzw/rgba), constructors, + - * / unary -, comparisons, || &&, ?:, = += -= *= /=, ++ in for
-headers, if/else, for, and the builtins abs cos cross dot length max min sign sqrt texture2D.
+headers, if/else, for, and the builtins abs cos cross dot floor length max min mod sign sqrt
+texture2D.
 """
 from __future__ import annotations
 
@@ -316,6 +317,10 @@ class Shader:
         with np.errstate(all="ignore"):
             if name == "sqrt": return np.sqrt(args[0])
             if name == "abs": return np.abs(args[0])
+            if name == "floor": return np.floor(args[0])
+            if name == "mod":  # GLSL ES 1.00 section 8.3: x - y * floor(x / y)
+                a, b = self._align(*args)
+                return a - b * np.floor(a / b)
             if name == "sign": return np.sign(args[0]).astype(self.dtype)
             if name == "cos":  # host libm, element by element, like the oracle's table (fsim_oracle.c: orc_cos_table)
                 a = args[0]

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle of matrix_webgl.makeSORIterative
 (public/javascripts/matrix_webgl.js:35-711), front end of oracle/fsim_oracle_jacobi_impl.h.
-PARITY UNPINNED: the reference has no tests and its only live caller does not run."""
+The literal mode is held bit for bit to the outputs of the reference's own shader text
+(tests/test_reference_glsl.py); the reference has no tests and its only live caller does not run."""
 from __future__ import annotations
 
 import ctypes as C

@@ -25,6 +25,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
 REF_JS = "/root/reference/public/javascripts/empic.js"
 
 from oracle.glsl_interp import Shader, Texture  # noqa: E402
@@ -34,73 +35,11 @@ SPEC = dict(radius=1.0, height=2.0, nr=24, nz=40, dt=2e-9, nparticles=16,
             particle_mass=1.67e-27, particle_charge=1.602e-19)
 
 
-# ---- reading the shader strings out of the JavaScript ------------------------------------------
-def _js_array_elements(text, start):
-    """Elements of the JS array literal whose '[' is at text[start]; returns (elements, end)."""
-    i, depth, cur, out = start + 1, 0, [], []
-    while True:
-        c = text[i]
-        if c == '"' or c == "'":
-            j = i + 1
-            while text[j] != c:
-                j += 2 if text[j] == "\\" else 1
-            cur.append(text[i:j + 1])
-            i = j + 1
-        elif text.startswith("//", i):
-            i = text.index("\n", i)
-        elif text.startswith("/*", i):
-            i = text.index("*/", i) + 2
-        elif c in "([":
-            depth += 1; cur.append(c); i += 1
-        elif c == ")" or (c == "]" and depth > 0):
-            depth -= 1; cur.append(c); i += 1
-        elif c == "]":
-            if "".join(cur).strip():
-                out.append("".join(cur).strip())
-            return out, i
-        elif c == "," and depth == 0:
-            out.append("".join(cur).strip()); cur = []; i += 1
-        else:
-            cur.append(c); i += 1
-
-
-def _js_string_expr(expr, env):
-    """Value of `"lit" + N(expr) + "lit" ...` (the only forms empic.js uses inside src_arr)."""
-    out, i = [], 0
-    while i < len(expr):
-        c = expr[i]
-        if c in "\"'":
-            j = i + 1
-            while expr[j] != c:
-                j += 2 if expr[j] == "\\" else 1
-            out.append(bytes(expr[i + 1:j], "utf-8").decode("unicode_escape"))
-            i = j + 1
-        elif expr.startswith("N(", i):
-            j, depth = i + 2, 1
-            while depth:
-                depth += {"(": 1, ")": -1}.get(expr[j], 0)
-                j += 1
-            value = eval(expr[i + 2:j - 1], {"__builtins__": {}}, env)  # e.g. factor_r/factor_z
-            out.append("%.20f" % value)  # Number.prototype.toFixed(20)
-            i = j
-        elif c in "+ \t\n":
-            i += 1
-        else:
-            raise SyntaxError("unexpected JS in a shader string array: " + expr[i:i + 40])
-    return "".join(out)
+from js_shader_source import shader_sources as _shader_sources  # noqa: E402
 
 
 def shader_sources(env):
-    """{name: [GLSL source, ...]} -- name = the `var NAME =` that owns each `src_arr` array."""
-    text = open(REF_JS).read()
-    owners = [(m.start(), m.group(1)) for m in
-              re.finditer(r"var\s+(\w+)\s*=\s*(?:function\s*\(|webgl\.linkProgram\s*\()", text)]
-    out = {}
-    for m in re.finditer(r"var\s+src_arr\s*=\s*\[", text):
-        name = [n for pos, n in owners if pos < m.start()][-1]
-        elems, _ = _js_array_elements(text, m.end() - 1)
-        out.setdefault(name, []).append("\n".join(_js_string_expr(e, env) for e in elems))
-    return out
+    return _shader_sources(REF_JS, env)
 
 
 # ---- the scene ------------------------------------------------------------------------------------

@@ -178,3 +178,61 @@ def test_gpu_fields_match_the_reference_shaders(precision):
     g.precalc()
     for nm in ("R1", "R2", "R3", "A"):
         assert_same(g.getField(nm), d[nm][:, :3].astype(np.float64), nm)
+
+
+# ---- matrix_webgl.makeSORIterative (row N3) against ITS shader source ----------------------------
+JACOBI_CASES = [(1, 1.0), (2, 1.0), (2, 0.8)]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("n_power,omega", JACOBI_CASES)
+def test_jacobi_oracle_matches_the_reference_shaders(precision, n_power, omega):
+    """programR, programC, programMVproduct + sum_frag chain + programResult (two iterations) and
+    programStats of matrix_webgl.js, executed from source, against the LITERAL mode of the oracle
+    (the mode that keeps the row numbering of programResult :408-411 as written)."""
+    from oracle import oracle as orc
+    from oracle.jacobi import OracleSOR
+    d = np.load(os.path.join(HERE, "golden", "reference_glsl_jacobi.npz"))
+    g = lambda k: d[f"{precision}_p{n_power}_w{int(10 * omega)}_{k}"]
+    o = OracleSOR({"n_power": n_power, "relaxation": omega, "literal": True, "precision": precision})
+    vh, L = o.vec_height, o.vec_length
+    o.set_matrix(g("A")).set_b(g("b"))
+    o._f("orcj_setup")(C.c_int64(L), orc._p(o.A), orc._p(o.b), C.c_double(orc.tofixed20(o.omega)),
+                       C.c_int(1 if o.omega == 1.0 else 0), orc._p(o.R), orc._p(o.Cv), C.c_int(1))
+    # R texture (mat_height^2 RGBA) -> natural [row][col]: programR :238-243
+    mat_h = 2 * vh * vh
+    Rt = g("R").reshape(mat_h, mat_h, 4)
+    Rnat = np.empty((L, L), Rt.dtype)
+    for py in range(mat_h):
+        for px in range(mat_h):
+            row = px // vh + 2 * vh * (py // vh)
+            col = 4 * (px % vh + vh * (py % vh))
+            Rnat[row, col:col + 4] = Rt[py, px]
+    assert_same(o.R, Rnat, "programR")
+    assert_same(o.Cv, g("C").reshape(-1), "programC")
+    o.x_guess = g("x").copy()
+    x1 = o.mv_product()
+    assert_same(x1, g("x1").reshape(-1), "mv_product, first iteration")
+    o.x_guess = x1.copy()
+    x2 = o.mv_product()
+    assert_same(x2, g("x2").reshape(-1), "mv_product, second iteration")
+    stats = np.zeros(L, o.dt)
+    o._f("orcj_stats")(C.c_int64(L // 4), orc._p(x1), orc._p(x2), orc._p(stats))
+    assert_same(stats, g("stats").reshape(-1), "programStats")
+    if vh >= 2:  # the defect the literal mode keeps: x' is NOT omega (R x + C) + (1 - omega) x in natural row order
+        intended = OracleSOR({"n_power": n_power, "relaxation": omega, "literal": False, "precision": precision})
+        intended.R, intended.Cv, intended.x_guess = o.R, o.Cv, g("x").copy()
+        assert not np.array_equal(intended.mv_product(), x1)
+
+
+def test_jacobi_vectors_regenerate_from_the_reference_tree():
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_reference_vectors_jacobi as gen
+    if not os.path.exists(gen.REF_JS):
+        pytest.skip("reference tree not present")
+    d = np.load(os.path.join(HERE, "golden", "reference_glsl_jacobi.npz"))
+    for name, dt in (("f64", np.float64), ("f32", np.float32)):
+        for n_power, omega in gen.CASES:
+            for k, v in gen.run_case(n_power, omega, dt).items():
+                assert_same(v, d[f"{name}_p{n_power}_w{int(10 * omega)}_{k}"], f"{name} {n_power} {omega} {k}")
