@@ -12,8 +12,9 @@
  * precalc, half-steps, sprite deposit, normalise, running average, canvas; fp64 and
  * fp32).  Still unpinned: what GLSL ES 1.00 / GL leave open (rounding of / and sqrt,
  * evaluation order, NaN texture coordinates, fixed-function blending and rasterisation)
- * -- there the documented IEEE / left-to-right choices below apply -- and the host-side
- * JavaScript of set() (inverse-cdf table), which is restated and cross-checked by an
+ * -- there the documented IEEE / left-to-right choices below apply.  The host-side
+ * JavaScript of set() that builds the inverse-cdf table is pinned by executing a mechanical
+ * transliteration of it (tests/golden/js_transliterate.py).  Further cross-checks: an
  * independent NumPy restatement (oracle/numpy_ref.py) and analytic invariants (tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl

@@ -42,6 +42,36 @@ def shader_sources(env):
     return _shader_sources(REF_JS, env)
 
 
+# ---- the host-side JavaScript of set(): inverse-cdf table (empic.js:1263-1339), executed ----------
+def inverse_cdf_js(pdf):
+    """Runs the reference's own source_pdf code (transliterated mechanically, js_transliterate.py) and
+    returns the [512*512][2] table of (x, y) as doubles -- the values BEFORE the Float32Array store."""
+    import types
+    import js_transliterate as jt
+    text = open(REF_JS).read()
+    a = text.index("if (value.source_pdf) {")
+    a = text.index("\n", a) + 1
+    b = text.index("inv_cdf_tex.update();", a)
+    rows = [[np.float64(v) for v in row] for row in np.asarray(pdf, np.float64)]
+    arr = np.zeros(4 * 512 * 512, np.float64)
+    with np.errstate(all="ignore"):
+        jt.run(text[a:b], dict(value=types.SimpleNamespace(source_pdf=rows), inv_cdf_arr=arr))
+    return arr.reshape(-1, 4)[:, :2].copy()
+
+
+def table_digest(t):
+    import hashlib
+    c = np.array(t, np.float64)
+    c[np.isnan(c)] = np.nan  # one NaN bit pattern
+    return np.frombuffer(hashlib.sha256(c.tobytes()).digest(), np.uint8).copy()
+
+
+def demo_pdf():
+    source = np.zeros((400, 800))  # fusionsim.js:116-122
+    source[0:50, 350:450] = 1.0
+    return source
+
+
 # ---- the scene ------------------------------------------------------------------------------------
 def entropy_table():
     k = np.arange(1024 * 1024 * 4, dtype=np.float64)
@@ -88,7 +118,7 @@ def quad_coords(w, h, dtype):
     return np.stack([(i + T(0.5)) / T(w), (j + T(0.5)) / T(h)], 1)
 
 
-def run(dtype):
+def run(dtype, full=False):
     from oracle import oracle as orc
     dtype = np.dtype(dtype)
     sp = SPEC
@@ -190,6 +220,16 @@ def run(dtype):
     avg = frag(sh("avg_frag"), grid, u_ratio=0.01, u_next=tex(norm, nr, nz), u_avg=tex(sc["avg0"], nr, nz))
     out.update(moments01_norm=norm, moments01_avg=avg)
 
+    # -- set({source_pdf}) (:1263-1339): the reference's host-side JavaScript, executed
+    if dtype == np.float64:
+        small = inverse_cdf_js(sc["source_pdf"])
+        out["invcdf_small_digest"] = table_digest(small)
+        out["invcdf_small_sub"] = small.reshape(512, 512, 2)[::5, ::5].copy()
+        if full:  # the demo scene's pdf: ~2 minutes of interpreted loops, not part of the regeneration check
+            demo = inverse_cdf_js(demo_pdf())
+            out["invcdf_demo_digest"] = table_digest(demo)
+            out["invcdf_demo_nan_texels"] = np.array(int(np.isnan(demo).any(1).sum()))
+
     # -- canvas (:1497-1504): programBMag, then programDensity blended SRC_ALPHA,ONE into the RGBA8 canvas.
     # The two colours are the reference's shader text; clamping to [0,1], rounding to k/255 and the blend are
     # fixed-function GL, emulated as the oracle documents them; canvas rows run top to bottom.
@@ -211,6 +251,6 @@ if __name__ == "__main__":
     if not os.path.exists(REF_JS):
         sys.exit("the reference tree is not present: the committed vectors cannot be regenerated here")
     for name, dt in (("f64", np.float64), ("f32", np.float32)):
-        res = run(dt)
+        res = run(dt, full=True)
         np.savez_compressed(os.path.join(HERE, f"reference_glsl_{name}.npz"), **res)
         print("wrote", name, {k: v.shape for k, v in res.items() if hasattr(v, "shape")})
