@@ -3,7 +3,7 @@
 out of /root/reference at run time, never copied -- can be executed here and the oracle's restatement
 of it compared with its results.  Line-oriented, for the regular formatting the reference uses:
 
-    for(i = 0; i < N; i++) {        ->  for i in range(int(N)):
+    for(i = a; i < N; i++) {        ->  for i in range(int(a), int(N)):
     while(cond) { / if (cond) {     ->  while cond: / if cond:
     var f = function(a, b) {        ->  def f(a, b):
     var x = e; / x++; / return e;   ->  x = e / x += 1 / return e
@@ -48,6 +48,7 @@ def _expr(e):
     e = e.replace("===", "==").replace("!==", "!=").replace("||", " or ").replace("&&", " and ")
     e = re.sub(r"([A-Za-z_][\w\.]*(?:\[[^\]]*\])*)\.length", r"len(\1)", e)
     e = e.replace("Math.min", "js_min").replace("Math.floor", "js_floor").replace("Math.max", "max")
+    e = e.replace("Math.random", "js_random")
     e = re.sub(r"\[\s*\]", "JsArray()", e)
     return e
 
@@ -66,9 +67,9 @@ def transliterate(js: str) -> str:
         if m:
             depth -= 1; emit("else:"); depth += 1
             continue
-        m = re.match(r"^for\s*\(\s*(\w+)\s*=\s*0\s*;\s*\1\s*<\s*(.+?)\s*;\s*\1\+\+\s*\)\s*{$", line)
+        m = re.match(r"^for\s*\(\s*(\w+)\s*=\s*(.+?)\s*;\s*\1\s*<\s*(.+?)\s*;\s*\1\+\+\s*\)\s*{$", line)
         if m:
-            emit(f"for {m.group(1)} in range(int({_expr(m.group(2))})):"); depth += 1
+            emit(f"for {m.group(1)} in range(int({_expr(m.group(2))}), int({_expr(m.group(3))})):"); depth += 1
             continue
         m = re.match(r"^(while|if)\s*\((.*)\)\s*{$", line)
         if m:

@@ -59,6 +59,26 @@ def inverse_cdf_js(pdf):
     return arr.reshape(-1, 4)[:, :2].copy()
 
 
+FUSIONSIM_JS = "/root/reference/public/javascripts/fusionsim.js"
+
+
+def demo_scene_js(nparticles, uniforms):
+    """The scene construction of the reference's page (fusionsim.js:94-128: sink mask, source pdf,
+    initial positions and velocities), executed; Math.random() returns `uniforms` in call order."""
+    import types
+    import js_transliterate as jt
+    text = open(FUSIONSIM_JS).read()
+    a = text.index("for(i = 0; i < spec.nr; i++) {")
+    b = text.index("simulation.set({", a)
+    it = iter(uniforms)
+    spec = types.SimpleNamespace(nr=400, nz=800)
+    scope = jt.run(text[a:b], dict(spec=spec, nparticles=nparticles, js_random=lambda: float(next(it)),
+                                   source=jt.JsArray(), sink=jt.JsArray(), init_position=jt.JsArray(),
+                                   init_velocity=jt.JsArray()))
+    return (np.array(scope["sink"], np.float64), np.array(scope["source"], np.float64),
+            np.array(scope["init_position"], np.float64), np.array(scope["init_velocity"], np.float64))
+
+
 def table_digest(t):
     import hashlib
     c = np.array(t, np.float64)
@@ -225,6 +245,11 @@ def run(dtype, full=False):
         small = inverse_cdf_js(sc["source_pdf"])
         out["invcdf_small_digest"] = table_digest(small)
         out["invcdf_small_sub"] = small.reshape(512, 512, 2)[::5, ::5].copy()
+        u = np.random.Generator(np.random.PCG64(7)).random(6 * 500)
+        sink, source, p0, v0 = demo_scene_js(500, u)
+        out.update(demo_uniforms=u, demo_position=p0, demo_velocity=v0,
+                   demo_sink_packed=np.packbits(sink.astype(np.uint8)), demo_source_packed=np.packbits(source.astype(np.uint8)))
+        assert set(np.unique(sink)) <= {0.0, 1.0} and set(np.unique(source)) <= {0.0, 1.0}
         if full:  # the demo scene's pdf: ~2 minutes of interpreted loops, not part of the regeneration check
             demo = inverse_cdf_js(demo_pdf())
             out["invcdf_demo_digest"] = table_digest(demo)

@@ -271,6 +271,24 @@ def test_inverse_cdf_matches_the_reference_javascript():
     assert_same(_digest(t), d["invcdf_demo_digest"], "demo-scene inverse cdf, all texels (sha256)")
 
 
+def test_demo_scene_matches_the_reference_javascript():
+    """fusion_sim_b200/scenes.py (config C1) against the scene construction of the reference's page
+    (fusionsim.js:94-128), executed: sink mask, source pdf, and the particle formulas fed the same
+    uniform numbers in the same order (x, y, z, vx, vy, vz per particle)."""
+    from fusion_sim_b200.scenes import c1_sink_source
+    d = load("f64")
+    sink, source = c1_sink_source(400, 800)
+    assert_same(np.packbits(sink.astype(np.uint8)), d["demo_sink_packed"], "sink mask")
+    assert_same(np.packbits(source.astype(np.uint8)), d["demo_source_packed"], "source pdf")
+    assert sink[0, 0] == 1 and sink[0, 799] == 1 and sink[399, 5] == 0 and sink[7, 0] == 0  # :105-112
+    u = d["demo_uniforms"].reshape(-1, 6)
+    position = 0.2 * (u[:, :3] - 0.5)   # scenes.c1_scene
+    position[:, 2] += 1
+    velocity = 0.002 * (u[:, 3:] - 0.5)
+    assert_same(position, d["demo_position"], "initial positions (fusionsim.js:126)")
+    assert_same(velocity, d["demo_velocity"], "initial velocities (fusionsim.js:127)")
+
+
 @pytest.mark.gpu
 def test_gpu_inverse_cdf_matches_the_reference_javascript():
     """fsim_set_source_pdf (api.cu: the product's own restatement) against the executed reference code."""
