@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "sortnet.cuh"
 
 namespace fsim {
 
@@ -43,7 +44,7 @@ struct CellSumArgs {
 };
 
 // Register path for a cell with k <= KR particles: (id, slot) pairs are loaded once, ordered by id
-// with a compile-time bitonic network (padding = 0xffffffff sorts last), then the colours are
+// with a compile-time sorting network (padding = 0xffffffff sorts last), then the colours are
 // added in that order.  All loads of a wave are independent, so they overlap.
 template <typename Real, int KR>
 __device__ __forceinline__ void cell_small(const CellSumArgs<Real> &a, uint32_t s, uint32_t k, Real (&acc)[4],
@@ -55,21 +56,12 @@ __device__ __forceinline__ void cell_small(const CellSumArgs<Real> &a, uint32_t 
 #pragma unroll
     for (int j = 0; j < KR; ++j) ii[j] = (uint32_t)j < k ? a.id[pp[j] & KEY_MASK] : 0xffffffffu;
 #pragma unroll
-    for (int kk = 2; kk <= KR; kk <<= 1) {
-#pragma unroll
-        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-#pragma unroll
-            for (int i = 0; i < KR; ++i) {
-                const int l = i ^ jj;
-                if (l > i) {
-                    const bool up = (i & kk) == 0;
-                    const bool sw = up ? (ii[i] > ii[l]) : (ii[i] < ii[l]);
-                    const uint32_t ti = sw ? ii[l] : ii[i], tl = sw ? ii[i] : ii[l];
-                    const uint32_t qi = sw ? pp[l] : pp[i], ql = sw ? pp[i] : pp[l];
-                    ii[i] = ti; ii[l] = tl; pp[i] = qi; pp[l] = ql;
-                }
-            }
-        }
+    for (int c = 0; c < SortNet<KR>::COUNT; ++c) {  // Batcher odd-even merge network (sortnet.cuh), ascending
+        const int i = SortNet<KR>::A(c), l = SortNet<KR>::B(c);
+        const bool sw = ii[i] > ii[l];
+        const uint32_t ti = sw ? ii[l] : ii[i], tl = sw ? ii[i] : ii[l];
+        const uint32_t qi = sw ? pp[l] : pp[i], ql = sw ? pp[i] : pp[l];
+        ii[i] = ti; ii[l] = tl; pp[i] = qi; pp[l] = ql;
     }
     Real c0[KR], c1[KR], c2[KR];
 #pragma unroll
@@ -102,13 +94,18 @@ __global__ void __launch_bounds__(128) cellsum_kernel(const CellSumArgs<Real> a)
     }
     Real acc[4] = {(Real)0, (Real)0, (Real)0, (Real)0};
     uint32_t cnt = 0;
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);  // warp-uniform choice of the path
-    if (kmax <= 4) {
-        cell_small<Real, 4>(a, s, k, acc, cnt);
-    } else if (kmax <= 8) {
-        cell_small<Real, 8>(a, s, k, acc, cnt);
-    } else if (k <= 16) {
-        cell_small<Real, 16>(a, s, k, acc, cnt);
+    // warp-uniform choice of the network: the largest cell of the warp that stays on this path
+    // (a warp of 32 cells with a mean of 4 particles needs 8 wires half of the time, 10 or 12 otherwise)
+    const uint32_t ks = k <= THREAD_CELL_MAX ? k : 0;  // crowded cells go to the warp / block kernels
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, ks);
+    if (kmax <= 4) cell_small<Real, 4>(a, s, ks, acc, cnt);
+    else if (kmax <= 6) cell_small<Real, 6>(a, s, ks, acc, cnt);
+    else if (kmax <= 8) cell_small<Real, 8>(a, s, ks, acc, cnt);
+    else if (kmax <= 10) cell_small<Real, 10>(a, s, ks, acc, cnt);
+    else if (kmax <= 12) cell_small<Real, 12>(a, s, ks, acc, cnt);
+    else cell_small<Real, 16>(a, s, ks, acc, cnt);
+    if (k <= THREAD_CELL_MAX) {
+        // summed above
     } else if (k > WARP_CELL_MAX) {
         a.heavy_list[atomicAdd(a.heavy_n, 1u)] = (uint32_t)c;
         return;
