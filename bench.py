@@ -57,6 +57,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.recording = index, False, False
         self.sm, self.reasons, self.sm_max = [], set(), None
+        self.ready = threading.Event()  # NVML is initialised: the timed region may start
 
     def run(self):
         try:
@@ -71,6 +72,7 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
             }
+            self.ready.set()
             while not self.stop_flag:
                 if self.recording:  # only samples taken DURING the timed region count
                     self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
@@ -81,9 +83,10 @@ class ClockSampler(threading.Thread):
                     for bit, nm in names.items():
                         if r & bit:
                             self.reasons.add(nm)
-                time.sleep(0.004)
+                time.sleep(0.002)
         except Exception as e:  # NVML missing: record that, never fail the bench
             self.reasons.add("nvml_unavailable:" + type(e).__name__)
+            self.ready.set()
 
     def result(self):
         sm = sorted(self.sm)
@@ -263,6 +266,7 @@ def run_ours(args):
     sampler.start()
     for _ in range(args.warmup):
         frame()
+    sampler.ready.wait(timeout=20)  # NVML start-up must not eat the timed region
     barrier()
     sampler.recording = True
     l0 = sim.launch_count
