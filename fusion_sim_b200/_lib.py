@@ -98,6 +98,8 @@ _SIGS = {
     "fsim_jacobi_get_result": (C.c_int, [_P, _P]),
     "fsim_jacobi_launch_count": (C.c_int64, [_P]),
     "fsim_jacobi_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "fsim_set_state": (C.c_int, [_P, _P, _P, _P]),
+    "fsim_set_field": (C.c_int, [_P, C.c_char_p, _P]),
     "fsim_solve_fields": (C.c_int, [_P, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_solve_fields_stage": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_field_rows": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(C.c_int64)]),

@@ -121,6 +121,29 @@ __global__ void part4_in_kernel(const double *__restrict__ in, Real *a0, Real *a
     a2[p] = (Real)in[4 * src + 2]; a3[p] = (Real)in[4 * src + 3];
 }
 
+// checkpoint restore: [N][4] normalised x, y, z, alive (exactly what fsim_get_position returns)
+template <typename Real>
+__global__ void state_pos_in_kernel(const double *__restrict__ in, Real *x, Real *y, Real *z, uint8_t *alive,
+                                    const uint32_t *__restrict__ pid, uint32_t id_base, int64_t n, int by_id)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const size_t src = by_id ? (size_t)(pid[p] - id_base) : (size_t)p;
+    x[p] = (Real)in[4 * src]; y[p] = (Real)in[4 * src + 1]; z[p] = (Real)in[4 * src + 2];
+    alive[p] = in[4 * src + 3] > 0.5 ? 1 : 0;
+}
+
+// [cells][4] doubles -> planar grid field (inverse of planar_out_kernel); [cells] -> one plane when nch == 1
+template <typename Real>
+__global__ void planar_in_kernel(const double *__restrict__ in, Real *__restrict__ out, int nr, int rows, int pitch,
+                                 int64_t plane, int nch)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (int64_t)nr * rows) return;
+    const size_t o = (size_t)(c / nr) * pitch + (size_t)(c % nr);
+    for (int q = 0; q < nch; ++q) out[q * plane + o] = (Real)in[nch * c + q];
+}
+
 // storage order -> id order (or storage order when by_id == 0)
 template <typename Real>
 __global__ void part_out_kernel(double *__restrict__ out, int width, const Real *a0, const Real *a1,
@@ -660,6 +683,61 @@ int fsim_set_rand(fsim_sim *s, const double *rnd)
         return (int)FSIM_OK;
     }));
 }
+// Checkpoint restore (extension): the exact inverses of fsim_get_position / fsim_get_velocity /
+// fsim_get_rand -- normalised units, alive flags included -- so that a run can be resumed, or started
+// from a state no set() call can express (particles that were "just respawned").
+int fsim_set_state(fsim_sim *s, const double *pos4, const double *vel3, const double *rand4)
+{
+    FSIM_TRY(check(s));
+    if (s->n == 0) return FSIM_OK;
+    if (pos4) {
+        FSIM_TRY(finish(s, stage_in(s, pos4, sizeof(double) * 4 * s->n)));
+        FSIM_TRY(finish(s, dispatch(s, [&](auto tag) {
+            using Real = decltype(tag);
+            const int c = s->cur;
+            state_pos_in_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+                (const double *)s->stage, (Real *)s->part[c][AX], (Real *)s->part[c][AY], (Real *)s->part[c][AZ],
+                s->alive[c], s->pid[c], s->id_base, s->n, s->slab ? 0 : 1);
+            FSIM_CUDA(cudaGetLastError());
+            s->launches++;
+            return (int)FSIM_OK;
+        })));
+        s->binned = false;
+        s->keys_valid = false;
+        s->have_leavers = false;
+        s->steps_since_sort = 1 << 20;  // re-sort at the next density()
+    }
+    if (vel3) FSIM_TRY(finish(s, particles_in3(s, vel3, AVX, 1.0, 1.0, 1.0, false)));
+    if (rand4) FSIM_TRY(fsim_set_rand(s, rand4));
+    if (vel3 && s->keys_valid) s->keys_valid = false;  // the sprite colours carry the velocity
+    return FSIM_OK;
+}
+
+// "moments01_avg" [cells][4] (the running average density() blends into) or "phi" [cells]
+int fsim_set_field(fsim_sim *s, const char *name, const double *data)
+{
+    FSIM_TRY(check(s));
+    if (!name || !data) return fail(FSIM_ERR_INVALID, "null argument");
+    const std::string n(name);
+    const int64_t nc = s->ncell_local;
+    int nch = 0;
+    void *dst = nullptr;
+    if (n == "moments01_avg") { nch = 4; dst = s->avg; }
+    else if (n == "phi") {
+        FSIM_TRY(finish(s, ensure_fieldsolve(s)));
+        nch = 1; dst = s->phi[s->phi_cur];
+    } else return fail(FSIM_ERR_INVALID, "set field: unknown name " + n);
+    FSIM_TRY(finish(s, stage_in(s, data, sizeof(double) * nch * nc)));
+    return finish(s, dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        planar_in_kernel<Real><<<grid_for(nc, 256), 256, 0, s->stream>>>((const double *)s->stage, (Real *)dst, s->nr,
+                                                                        s->rows, s->pitch, s->plane, nch);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
+        return (int)FSIM_OK;
+    }));
+}
+
 int fsim_set_particle_count(fsim_sim *s, int64_t n)
 {
     FSIM_TRY(check(s));

@@ -223,6 +223,40 @@ class CylindricalParticlePusher:
         check(lib().fsim_get_field(self._h, name.encode(), ptr(out)))
         return out
 
+    # -- checkpoint / restore (extension: the reference keeps its state in closure-private textures) ----
+    def checkpoint(self) -> dict:
+        """Everything a run needs to continue bit for bit: particle state (normalised units, alive
+        flags, RNG state), fields, running average, potential."""
+        ck = {"position": self.getPosition(), "velocity": self.getVelocity(), "rand": self.getRand(),
+              "E": self.getField("E"), "B": self.getField("B"), "moments01_avg": self.getField("moments01_avg")}
+        try:
+            ck["phi"] = self.getField("phi")
+        except Error:
+            pass  # no solveFields() yet
+        return ck
+
+    def restore(self, ck: dict):
+        """Inverse of checkpoint() on a simulation created with the same spec and the same static
+        tables (sink mask, source pdf, entropy); runs precalc()."""
+        L, h = lib(), self._h
+        nc = self.ncell_local
+        cells = lambda a: np.ascontiguousarray(np.asarray(a, np.float64).reshape(self.nz, self.nr, 3).transpose(1, 0, 2))
+        check(L.fsim_set_E(h, ptr(cells(ck["E"]))))
+        check(L.fsim_set_B(h, ptr(cells(ck["B"]))))
+        check(L.fsim_precalc(h))
+        check(L.fsim_set_state(h, ptr(_f64(ck["position"], (self.n, 4))), ptr(_f64(ck["velocity"], (self.n, 3))),
+                               ptr(_f64(ck["rand"], (self.n, 4)))))
+        check(L.fsim_set_field(h, b"moments01_avg", ptr(_f64(ck["moments01_avg"], (nc, 4)))))
+        if ck.get("phi") is not None:
+            check(L.fsim_set_field(h, b"phi", ptr(_f64(ck["phi"], (nc,)))))
+
+    def setState(self, position4=None, velocity3=None, rand4=None):
+        """Raw particle state in normalised units (see fsim_set_state)."""
+        p = ptr(_f64(position4, (self.n, 4))) if position4 is not None else None
+        v = ptr(_f64(velocity3, (self.n, 3))) if velocity3 is not None else None
+        r = ptr(_f64(rand4, (self.n, 4))) if rand4 is not None else None
+        check(lib().fsim_set_state(self._h, p, v, r))
+
     # -- measurement hooks ---------------------------------------------------------------------
     def timing(self, on: bool):
         check(lib().fsim_timing_enable(self._h, 1 if on else 0))

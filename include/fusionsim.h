@@ -143,6 +143,13 @@ int fsim_solve_fields_stage(fsim_sim *sim, int32_t stage, double macro_weight, i
                             int32_t source);
 int fsim_field_rows(fsim_sim *sim, const char *name, int64_t first_row, int64_t nrows, void **ptr, int64_t *nbytes);
 
+/* ---- checkpoint restore (extension; the reference can neither read nor restore its state) ---------
+ * fsim_set_state is the exact inverse of fsim_get_position / _velocity / _rand: normalised units,
+ * particle-id order, alive flag in position[..][3]; any pointer may be NULL.  fsim_set_field restores
+ * "moments01_avg" [cells][4] (the running average of density()) or "phi" [cells].                  */
+int fsim_set_state(fsim_sim *sim, const double *position4, const double *velocity3, const double *rand4);
+int fsim_set_field(fsim_sim *sim, const char *name, const double *data);
+
 /* ---- accessors (extension; the reference exposes none) ---------- */
 int64_t fsim_particle_count(const fsim_sim *sim);
 int64_t fsim_local_cells(const fsim_sim *sim); /* nr * (slab_rows + 2*halo_rows) or nr*nz      */

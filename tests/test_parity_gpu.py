@@ -314,3 +314,30 @@ def test_long_run_c1_energy_and_population():
     assert q.min() >= 0 and q.max() <= 1 and g.n == 160000
     ids = np.sort(g.getIds())
     assert_same(ids, np.arange(160000, dtype=np.uint64), "ids after 200 frames")
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_checkpoint_restore_resumes_bit_for_bit(precision):
+    """checkpoint() on a running simulation (self-consistent fields included), restore() into a fresh
+    handle with the same static tables: both continue identically."""
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene
+    sc = small_scene(precision=precision, n=20000, speed=0.02, blob=(0.5, 0.8))
+    a = makeCylindricalParticlePusher(sc["spec"])
+    apply_scene(a, sc)
+    v = {"macro_weight": 5e11, "sweeps": 6, "omega": 0.9}
+    for _ in range(3):
+        a.step(); a.density(); a.solveFields(v)
+    ck = a.checkpoint()
+    b = makeCylindricalParticlePusher(sc["spec"])
+    b.set({k: sc[k] for k in ("sink_mask", "source_pdf", "entropy")})
+    b.restore(ck)
+    for sim in (a, b):
+        for _ in range(3):
+            sim.step(); sim.density(); sim.solveFields(v)
+    for nm, fa, fb in (("position", a.getPosition(), b.getPosition()), ("velocity", a.getVelocity(), b.getVelocity()),
+                       ("rand", a.getRand(), b.getRand())):
+        assert_same(fa, fb, "resumed " + nm)
+    for nm in ("moments01_avg", "phi", "E", "A", "cell_count"):
+        assert_same(a.getField(nm), b.getField(nm), "resumed " + nm)
+    assert_same(a.canvas, b.canvas, "resumed canvas")

@@ -301,3 +301,39 @@ def test_gpu_inverse_cdf_matches_the_reference_javascript():
     g = makeCylindricalParticlePusher(dict(SPEC, nr=400, nz=800, precision="f64"))
     g.set({"source_pdf": demo})
     assert_same(_digest(g.getField("inv_cdf")), d["invcdf_demo_digest"], "demo-scene inverse cdf (sha256)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_gpu_half_steps_match_the_reference_shaders(precision):
+    """libfusionsim.so straight against the outputs of the reference's step shaders: the state the
+    vectors start from (just-respawned particles included) is restored with fsim_set_state, then 8
+    half-steps; same documented NaN deviation as in the oracle test above."""
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    d = load(precision)
+    nr, nz = SPEC["nr"], SPEC["nz"]
+    g = makeCylindricalParticlePusher(dict(SPEC, precision=precision))
+    cells = lambda a: np.ascontiguousarray(a[:, :3].astype(np.float64).reshape(nz, nr, 3).transpose(1, 0, 2))
+    g.set({"E": cells(d["E"]), "B": cells(d["B"]), "sink_mask": d["sink"][:, 0].astype(np.float64).reshape(nz, nr).T,
+           "source_pdf": d["source_pdf"], "entropy": entropy_table()})
+    g.precalc()
+    for nm in ("R1", "R2", "R3", "A"):
+        assert_same(g.getField(nm), d[nm][:, :3].astype(np.float64), nm)
+    f64 = lambda a: a.astype(np.float64)
+    g.setState(f64(d["position"]), f64(d["velocity"][:, :3]), f64(d["rand"]))
+    live = np.ones(g.n, bool)
+    for k in range(d["step_position"].shape[0]):
+        g.half_step()
+        ref_pos = f64(d["step_position"][k])
+        pos = g.getPosition()
+        nan_kept = live & (ref_pos[:, 3] == 1) & np.isnan(ref_pos[:, :3]).any(1)
+        assert (pos[nan_kept, 3] == 0).all()
+        live &= ~nan_kept
+        assert_same(g.getRand()[live], f64(d["step_rand"][k])[live], f"half-step {k}: programStepRand")
+        assert_same(g.getVelocity()[live], f64(d["step_velocity"][k])[live, :3], f"half-step {k}: step_velocity_frag")
+        assert_same(pos[live], ref_pos[live], f"half-step {k}: step_position_frag")
+        if (~live).any():  # keep the excluded particles on the reference's track
+            p, v, r = pos.copy(), g.getVelocity(), g.getRand()
+            p[~live], v[~live], r[~live] = ref_pos[~live], f64(d["step_velocity"][k])[~live, :3], f64(d["step_rand"][k])[~live]
+            g.setState(p, v, r)
+    assert live.sum() >= g.n - 8
