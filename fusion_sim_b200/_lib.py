@@ -82,6 +82,7 @@ _SIGS = {
     "fsim_launch_count": (C.c_int64, [_P]),
     "fsim_mark": (C.c_int, [_P, C.c_int]),
     "fsim_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "fsim_set_stream": (C.c_int, [_P, _P]),
     "fsim_migrate_record_bytes": (C.c_int64, [_P]),
     "fsim_migrate_pack": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "fsim_migrate_unpack": (C.c_int, [_P, _P, C.c_int64]),

@@ -461,7 +461,7 @@ static void free_all(fsim_sim *s)
         if (s->copy_done[k]) cudaEventDestroy(s->copy_done[k]);
     }
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->stream && !s->ext_stream) cudaStreamDestroy(s->stream);
 }
 
 static int particles_in3(fsim_sim *s, const double *host, int a0, double f0, double f1, double f2,
@@ -924,6 +924,19 @@ int fsim_step(fsim_sim *s)
     s->steps_since_sort++;
     if (s->steps_since_sort >= 4 * sort_interval(s))  // push-only loops: keep the gather coherent
         FSIM_TRY(finish(s, physical_sort(s)));
+    return FSIM_OK;
+}
+
+// Run every kernel of this handle on a stream the caller owns (a cudaStream_t), e.g. the stream a
+// communication library orders its collectives on: the multi-GPU driver then needs no host
+// synchronisation between a kernel and the collective that consumes its output.
+int fsim_set_stream(fsim_sim *s, void *cuda_stream)
+{
+    FSIM_TRY(check(s));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->stream && !s->ext_stream) FSIM_CUDA(cudaStreamDestroy(s->stream));
+    s->stream = (cudaStream_t)cuda_stream;
+    s->ext_stream = true;
     return FSIM_OK;
 }
 

@@ -61,6 +61,7 @@ struct fsim_sim {
     size_t rs = 8;  // sizeof(real)
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool ext_stream = false;  // `stream` belongs to the caller (fsim_set_stream): collectives are stream-ordered
     bool sticky_error = false;
 
     // geometry

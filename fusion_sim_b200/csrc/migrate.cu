@@ -47,12 +47,13 @@ find_leavers_kernel(const Real *__restrict__ z, int64_t n, int nz, int own0, int
 
 template <typename Real>
 __global__ void __launch_bounds__(256)
-migrate_count_kernel(const Real *__restrict__ z, const uint32_t *__restrict__ list, uint32_t nlist, int nz,
-                     RankBounds rb, uint32_t *__restrict__ counts)
+migrate_count_kernel(const Real *__restrict__ z, const uint32_t *__restrict__ list,
+                     const uint32_t *__restrict__ nlist_d, int nz, RankBounds rb, uint32_t *__restrict__ counts)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nlist) return;
-    atomicAdd(counts + dest_rank(rb, z[list[t]], nz), 1u);
+    // the list length stays on the device (no host round trip before this launch): grid-stride
+    const uint32_t nlist = *nlist_d;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nlist; t += gridDim.x * blockDim.x)
+        atomicAdd(counts + dest_rank(rb, z[list[t]], nz), 1u);
 }
 
 template <typename Real>
@@ -250,21 +251,21 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
             s->launches++;
         }
         s->have_leavers = false;
+        // destination counts of the leavers and the list length: ONE read-back per frame
+        migrate_count_kernel<Real><<<148 * 2, 256, 0, s->stream>>>((const Real *)s->part[c][AZ], s->perm, nlist_d, s->nz, rb,
+                                                                   scr);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches++;
         uint32_t nlist = 0;
+        uint32_t hc[MAX_RANKS] = {}, off[MAX_RANKS] = {};
         FSIM_CUDA(cudaMemcpyAsync(&nlist, nlist_d, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        FSIM_CUDA(cudaMemcpyAsync(hc, scr, sizeof(uint32_t) * nranks, cudaMemcpyDeviceToHost, s->stream));
         FSIM_CUDA(cudaStreamSynchronize(s->stream));
         if (nlist == 0) return (int)FSIM_OK;
         if ((int64_t)nlist > s->cap / 2) {
             set_error("fsim_migrate_pack: more than half of the particle slots leave the slab at once");
             return (int)FSIM_ERR_RANGE;
         }
-        migrate_count_kernel<Real><<<grid_for(nlist, 256), 256, 0, s->stream>>>(
-            (const Real *)s->part[c][AZ], s->perm, nlist, s->nz, rb, scr);
-        FSIM_CUDA(cudaGetLastError());
-        s->launches++;
-        uint32_t hc[MAX_RANKS] = {}, off[MAX_RANKS] = {};
-        FSIM_CUDA(cudaMemcpyAsync(hc, scr, sizeof(uint32_t) * nranks, cudaMemcpyDeviceToHost, s->stream));
-        FSIM_CUDA(cudaStreamSynchronize(s->stream));
         int64_t total = 0;
         for (int k = 0; k < nranks; ++k) {
             send_counts[k] = hc[k];
@@ -289,7 +290,8 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
             migrate_pack_kernel<Real><<<grid_for(nlist, 256), 256, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());
         }
-        FSIM_CUDA(cudaStreamSynchronize(s->stream));
+        // an external (caller-owned) stream orders the collective after this kernel by itself
+        if (!s->ext_stream) FSIM_CUDA(cudaStreamSynchronize(s->stream));
         s->nholes_host = nlist;
         *send_buf_dev = s->migr;
         return (int)FSIM_OK;

@@ -118,6 +118,12 @@ class SlabPusher:
         self.sim = CylindricalParticlePusher(lspec)
         apply_scene(self.sim, scene)
         self._lib = _lib
+        # one stream for the engine's kernels AND the NCCL collectives: torch orders a collective after
+        # the current stream's work and makes the current stream wait for it, so no host
+        # synchronisation is needed between a kernel and the exchange that consumes its output
+        self.stream = torch.cuda.Stream(self.device)
+        self.sim.sync()
+        _lib.check(_lib.lib().fsim_set_stream(self.sim.handle, C.c_void_p(self.stream.cuda_stream)))
         self.record_bytes = int(_lib.lib().fsim_migrate_record_bytes(self.sim.handle))
         self.ncell_local = self.sim.ncell_local
         self._bounds_c = (C.c_int64 * (world + 1))(*self.bounds)
@@ -134,11 +140,11 @@ class SlabPusher:
         buf = C.c_void_p()
         self._lib.check(L.fsim_migrate_pack(h, self._bounds_c, self.world, self.rank, counts, C.byref(buf)))
         sc = list(counts)
-        send = _dev_tensor(buf.value or 0, sum(sc) * self.record_bytes, self.device)
-        recv, nrecv = exchange_records(send, sc, self.record_bytes)
-        torch.cuda.current_stream().synchronize()
-        self._lib.check(L.fsim_migrate_unpack(h, C.c_void_p(recv.data_ptr() if nrecv else 0), nrecv))
-        self.sim.sync()  # recv may be freed after this
+        with torch.cuda.stream(self.stream):
+            send = _dev_tensor(buf.value or 0, sum(sc) * self.record_bytes, self.device)
+            recv, nrecv = exchange_records(send, sc, self.record_bytes)  # the count exchange is the frame's one host wait
+            self._lib.check(L.fsim_migrate_unpack(h, C.c_void_p(recv.data_ptr() if nrecv else 0), nrecv))
+            del recv  # allocated on self.stream: the caching allocator reuses it in stream order
         self.migrated += sum(sc)
 
     def density(self):
@@ -148,10 +154,9 @@ class SlabPusher:
         ptrs = [C.c_void_p() for _ in range(4)]
         nbytes = C.c_int64()
         self._lib.check(L.fsim_halo_ptrs(h, *[C.byref(p) for p in ptrs], C.byref(nbytes)))
-        t = [_dev_tensor(p.value or 0, nbytes.value if p.value else 0, self.device) for p in ptrs]
-        self.sim.sync()
-        exchange_halo(t[0], t[1], t[2], t[3], self.rank, self.world)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(self.stream):
+            t = [_dev_tensor(p.value or 0, nbytes.value if p.value else 0, self.device) for p in ptrs]
+            exchange_halo(t[0], t[1], t[2], t[3], self.rank, self.world)
         self._lib.check(L.fsim_density_end(h))
 
     # -- EXTENSION: self-consistent field solve on the slab -------------------------------------------
@@ -179,11 +184,10 @@ class SlabPusher:
         assert h <= halo and h <= own, "slab thinner than the halo"
         empty = torch.empty(0, dtype=torch.uint8, device=self.device)
         up, down = self.rank < self.world - 1, self.rank > 0
-        self.sim.sync()
-        exchange_halo(self._rows(name, lo, h) if down else empty, self._rows(name, hi - h, h) if up else empty,
-                      self._rows(name, lo - h, h) if down else empty, self._rows(name, hi, h) if up else empty,
-                      self.rank, self.world)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(self.stream):
+            exchange_halo(self._rows(name, lo, h) if down else empty, self._rows(name, hi - h, h) if up else empty,
+                          self._rows(name, lo - h, h) if down else empty, self._rows(name, hi, h) if up else empty,
+                          self.rank, self.world)
 
     # -- pass-throughs ----------------------------------------------------------------------------
     def sync(self):

@@ -181,6 +181,9 @@ int fsim_elapsed_ms(fsim_sim *sim, int slot_a, int slot_b, double *ms);
 /* Particles leaving the slab are packed into a device buffer grouped by destination rank;
  * row_bounds[k]..row_bounds[k+1] are the grid rows rank k owns.  The caller (one process per
  * GPU) moves the packed records with its own collective and hands them to fsim_migrate_unpack.  */
+/* Put the handle on a stream the caller owns (cudaStream_t), so that kernels and the caller's
+ * collectives are ordered by the stream instead of by host synchronisation.                        */
+int fsim_set_stream(fsim_sim *sim, void *cuda_stream);
 int64_t fsim_migrate_record_bytes(const fsim_sim *sim);
 int fsim_migrate_pack(fsim_sim *sim, const int64_t *row_bounds, int32_t nranks, int32_t self,
                       int64_t *send_counts /* host [nranks] */, void **send_buf_dev);
