@@ -224,7 +224,10 @@ def run_ours(args):
     pos_h, _keep1 = pinned_copy(sc["position"])
     vel_h, _keep2 = pinned_copy(sc["velocity"])
     sc["position"], sc["velocity"] = pos_h, vel_h
-    if world > 1:
+    if world > 1 and args.decomposition == "replicated":
+        from fusion_sim_b200.dist import ReplicatedPusher
+        sim = ReplicatedPusher(spec, sc, rank, world)  # measured alternative: no migration, all-reduce of the sums
+    elif world > 1:
         from fusion_sim_b200.dist import SlabPusher
         sim = SlabPusher(spec, sc, rank, world)
     else:
@@ -327,7 +330,7 @@ def run_ours(args):
     # of the canvas (this rank's rows) into pinned host memory; all inside the timed region.
     from fusion_sim_b200._lib import check, lib
     base = sim.sim if world > 1 else sim
-    own_rows = nz // world
+    own_rows = nz if args.decomposition == "replicated" else nz // world  # replicated: every rank renders the whole canvas
     h2d = 2 * pos_h.nbytes
     d2h = 4 * nr * own_rows
     def e2e_pass(frames):
@@ -390,7 +393,7 @@ def run_ours(args):
                            " + solveFields(%d sweeps) [EXTENSION]" % args.field_sweeps if solve else ""),
                        "l2": "inputs larger than L2 (particle state %.1f GB per GPU)" % (
                            n_local * (81 if args.precision == "f64" else 41) / 1e9),
-                       "parallelism": "slab%d" % world},
+                       "parallelism": ("replicated%d" if args.decomposition == "replicated" and world > 1 else "slab%d") % world},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb,
             "push_only_pushes_per_s": halves * n_local * world / (push_ms * 1e-3),
@@ -411,6 +414,8 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decomposition", default="slab", choices=["slab", "replicated"],
+                    help="multi-GPU: slab decomposition (default) or the measured alternative (replicated tables + all-reduce)")
     ap.add_argument("--field-sweeps", type=int, default=0,
                     help="EXTENSION: add solveFields(N sweeps) to every frame (self-consistent fields); 0 = the reference's frame")
     args = ap.parse_args()

@@ -104,6 +104,7 @@ _SIGS = {
     "fsim_solve_fields": (C.c_int, [_P, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_solve_fields_stage": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_field_rows": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "fsim_cellsum_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fsim_density_begin": (C.c_int, [_P]),
     "fsim_density_end": (C.c_int, [_P]),
 }

@@ -759,7 +759,12 @@ int fsim_set_ids(fsim_sim *s, const uint64_t *ids)
     FSIM_TRY(check(s));
     if (!ids) return fail(FSIM_ERR_INVALID, "null array");
     std::vector<uint32_t> tmp((size_t)s->n);
-    for (int64_t k = 0; k < s->n; ++k) tmp[k] = (uint32_t)ids[k];
+    for (int64_t k = 0; k < s->n; ++k) {
+        // outside slab mode the accessors place particle `id` at row id - id_base of the caller's arrays
+        if (!s->slab && (ids[k] < s->id_base || ids[k] >= (uint64_t)s->id_base + (uint64_t)s->n))
+            return fail(FSIM_ERR_RANGE, ".ids <- outside [id_base, id_base + N): only a slab rank holds arbitrary global ids");
+        tmp[k] = (uint32_t)ids[k];
+    }
     FSIM_CUDA(cudaMemcpyAsync(s->pid[s->cur], tmp.data(), sizeof(uint32_t) * s->n, cudaMemcpyHostToDevice, s->stream));
     FSIM_CUDA(cudaStreamSynchronize(s->stream));
     return FSIM_OK;
@@ -966,6 +971,20 @@ int fsim_density_end(fsim_sim *s)
     if (s->slab) FSIM_TRY(finish(s, launch_halo_unpack(s)));  // neighbours' boundary rows -> halo rows of the sums
     return finish(s, launch_conv(s));
 }
+// device addresses of the per-cell sums (planar, 4 planes of rows x pitch reals) and the per-cell
+// counts -- for a caller that reduces them across ranks between fsim_density_begin and _end
+// (the replicated-table alternative of the multi-GPU driver)
+int fsim_cellsum_ptrs(fsim_sim *s, void **sums, int64_t *sum_bytes, void **counts, int64_t *count_bytes)
+{
+    FSIM_TRY(check(s));
+    if (!sums || !sum_bytes || !counts || !count_bytes) return fail(FSIM_ERR_INVALID, "null argument");
+    *sums = s->cellsum;
+    *sum_bytes = (int64_t)(s->rs * 4 * (size_t)s->plane);
+    *counts = s->cellcount;
+    *count_bytes = (int64_t)(sizeof(uint32_t) * (size_t)s->ncell_local);
+    return FSIM_OK;
+}
+
 int fsim_density(fsim_sim *s)
 {
     FSIM_TRY(fsim_density_begin(s));

@@ -246,3 +246,49 @@ class SlabPusher:
         out = [None] * self.world if self.rank == 0 else None
         dist.gather_object(a[lo:hi], out, dst=0)
         return np.concatenate(out) if self.rank == 0 else None
+
+
+class ReplicatedPusher:
+    """MEASURED ALTERNATIVE to the slab decomposition: particles sharded by index,
+    every table replicated on every rank.  No migration and no halo -- a particle never leaves its
+    rank -- but every rank bins over the WHOLE grid, the per-cell sums and counts of all ranks are
+    added with an all-reduce (32 + 4 bytes per cell of the whole grid per frame), and every rank runs
+    the stencil over the whole grid.  The floating-point sums are added across ranks in the order the
+    collective chooses, not in particle-id order: equal to the single-GPU result to rounding only
+    (tests/test_dist.py holds it to 1e-12), where the slab decomposition is bit-identical."""
+
+    def __init__(self, spec: dict, scene: dict, rank: int, world: int):
+        from . import _lib
+        from .pusher import CylindricalParticlePusher
+        from .scenes import apply_scene
+        self.rank, self.world = rank, world
+        n_local = len(scene["position"])
+        lspec = dict(spec, nparticles_total=n_local, id_base=rank * n_local)
+        self.device = torch.device("cuda", int(lspec.get("device", 0)))
+        self.sim = CylindricalParticlePusher(lspec)
+        apply_scene(self.sim, scene)
+        self._lib = _lib
+        self.ncell_local = self.sim.ncell_local
+        self.stream = torch.cuda.Stream(self.device)
+        self.sim.sync()
+        _lib.check(_lib.lib().fsim_set_stream(self.sim.handle, C.c_void_p(self.stream.cuda_stream)))
+        sums, nb_s, cnt, nb_c = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        _lib.check(_lib.lib().fsim_cellsum_ptrs(self.sim.handle, C.byref(sums), C.byref(nb_s), C.byref(cnt), C.byref(nb_c)))
+        real = torch.float64 if self.sim.spec.get("precision", "f64") in ("f64", 0) else torch.float32
+        self._sums = _dev_tensor(sums.value, nb_s.value, self.device).view(real)
+        self._counts = _dev_tensor(cnt.value, nb_c.value, self.device).view(torch.int32)
+        self.allreduce_bytes = nb_s.value + nb_c.value
+
+    def step(self):
+        self.sim.step()
+
+    def density(self):
+        L, h = self._lib.lib(), self.sim.handle
+        self._lib.check(L.fsim_density_begin(h))
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self._sums)
+            dist.all_reduce(self._counts)
+        self._lib.check(L.fsim_density_end(h))
+
+    def __getattr__(self, name):  # sync, mark, elapsed_ms, timing*, render*, set, launch_count, n, getField ...
+        return getattr(self.sim, name)

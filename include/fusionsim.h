@@ -191,6 +191,9 @@ int fsim_migrate_unpack(fsim_sim *sim, const void *recv_buf_dev, int64_t nrecv);
 /* Halo of the per-cell sums (5 rows each side) for the slab convolution. */
 int fsim_halo_ptrs(fsim_sim *sim, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi,
                    int64_t *bytes_each);
+/* measured alternative (replicated tables, index-sharded particles): the per-cell sums and counts of
+ * every rank are added between fsim_density_begin and fsim_density_end; these are their addresses. */
+int fsim_cellsum_ptrs(fsim_sim *sim, void **sums, int64_t *sum_bytes, void **counts, int64_t *count_bytes);
 int fsim_density_begin(fsim_sim *sim); /* sort + per-cell sums (before the halo exchange)        */
 int fsim_density_end(fsim_sim *sim);   /* convolution + normalise + running average              */
 

@@ -78,3 +78,23 @@ def test_two_gpus_nccl_self_consistent_fields(tmp_path):
     path = str(tmp_path / "res.npz")
     mp.spawn(dh.gpu_worker, args=(2, free_port(), FRAMES, path, True), nprocs=2, join=True)
     check_against_single(path, solve=True)
+
+
+@pytest.mark.gpu
+def test_two_gpus_replicated_alternative(tmp_path):
+    """The measured alternative: particles bit-identical (the push does not communicate), counts exact,
+    running average equal to 1e-12 (cross-rank sums are not in id order) and identical on both ranks."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    path = str(tmp_path / "res.npz")
+    mp.spawn(dh.gpu_worker_replicated, args=(2, free_port(), FRAMES, path), nprocs=2, join=True)
+    got = np.load(path)
+    o = dh.single_oracle(FRAMES)
+    assert_same(got["ids"], np.arange(o.n, dtype=got["ids"].dtype), "every particle exactly once")
+    assert_same(got["pos"], o.getPosition(), "position")
+    assert_same(got["vel"], o.getVelocity(), "velocity")
+    assert_same(got["cnt"], o.cell_count, "cell counts")
+    ref = o.moments01_avg
+    ok = ~np.isnan(ref)
+    assert np.abs(got["avg"][ok] - ref[ok]).max() <= 1e-12 * np.abs(ref[ok]).max()
+    assert_same(got["avg"], got["avg_other"], "both ranks hold the same reduced field")

@@ -210,6 +210,17 @@ def test_async_canvas_matches_sync():
         assert_same(imgs[k], want[k], f"async canvas {k}")
 
 
+def test_ids_outside_the_block_are_refused():
+    from fusion_sim_b200 import Error, makeCylindricalParticlePusher
+    import ctypes as C
+    sc = small_scene(n=256)
+    g = makeCylindricalParticlePusher(sc["spec"])
+    ids = np.arange(256, dtype=np.uint64) * 2  # not a permutation of [0, N)
+    from fusion_sim_b200._lib import check, lib
+    with pytest.raises(Error):
+        check(lib().fsim_set_ids(g.handle, ids.ctypes.data_as(C.c_void_p)))
+
+
 def test_errors_are_thrown():
     from fusion_sim_b200 import Error, makeCylindricalParticlePusher
     sc = small_scene(n=64)
