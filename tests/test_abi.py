@@ -7,6 +7,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -81,3 +82,53 @@ def test_product_does_not_touch_the_oracle():
     code = "import sys; import fusion_sim_b200, fusion_sim_b200.scenes, fusion_sim_b200.pusher; " \
            "assert not [m for m in sys.modules if m.startswith('oracle')]"
     subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+
+
+def _uniform01(k):
+    """splitmix64 of the draw index -> [0,1), as examples/headless_demo.c."""
+    with np.errstate(over="ignore"):
+        x = k.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def test_c_host_is_built(built):
+    """The plain C host of the ABI (examples/headless_demo.c) links against libfusionsim.so alone."""
+    exe = os.path.join(ROOT, "fusion_sim_b200", "csrc", "headless_demo")
+    assert os.path.exists(exe)
+    out = subprocess.run(["ldd", exe], stdout=subprocess.PIPE, text=True).stdout
+    assert "libfusionsim.so" in out and "python" not in out.lower() and "torch" not in out.lower()
+
+
+@pytest.mark.gpu
+def test_c_host_matches_the_python_mirror(built, tmp_path):
+    """The same demo scene driven from C and from the Python mirror: identical canvas bytes."""
+    import json
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import C1_SPEC, c1_sink_source
+    exe = os.path.join(ROOT, "fusion_sim_b200", "csrc", "headless_demo")
+    ppm = str(tmp_path / "canvas.ppm")
+    res = json.loads(subprocess.run([exe, "6", ppm], stdout=subprocess.PIPE, check=True, text=True).stdout)
+    n = 160000
+    u = _uniform01(np.arange(6 * n, dtype=np.uint64)).reshape(n, 6)
+    pos = 0.2 * (u[:, :3] - 0.5)
+    pos[:, 2] += 1
+    vel = 0.002 * (u[:, 3:] - 0.5)
+    sink, source = c1_sink_source(400, 800)
+    g = makeCylindricalParticlePusher(C1_SPEC)
+    g.set({"position": pos, "velocity": vel, "sink_mask": sink, "source_pdf": source})
+    g.addCurrentLoop(0.8, 2.0, -10000000)
+    g.addCurrentLoop(0.8, 0.0, 10000000)
+    g.precalc()
+    for _ in range(6):
+        g.step(); g.density()
+    canvas = g.canvas
+    h = 1469598103934665603
+    for b in canvas.reshape(-1).tolist():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert res["canvas_fnv1a"] == "%016x" % h and res["particles"] == n and res["launches"] > 0
+    raw = open(ppm, "rb").read()
+    assert raw.startswith(b"P6\n400 800\n255\n")
+    assert np.array_equal(np.frombuffer(raw[len(b"P6\n400 800\n255\n"):], np.uint8).reshape(800, 400, 3), canvas[..., :3])
