@@ -180,7 +180,17 @@ def cpu_baseline(workload, precision, steps, target_s=12.0, threads=None):
     for _ in range(k):
         frame()
     dt = time.perf_counter() - t0
-    return {"value": 2.0 * o.n * k / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    # the same sample on ONE host thread (SURVEY.md section 8d asks for both), a few frames only
+    one = None
+    if threads > 1 and not steps:
+        o.nthreads = 1
+        k1 = max(2, min(k, int(4.0 / max(t1 * threads * 0.6, 1e-6))))
+        t0 = time.perf_counter()
+        for _ in range(k1):
+            frame()
+        one = 2.0 * o.n * k1 / (time.perf_counter() - t0)
+        o.nthreads = threads
+    return {"value": 2.0 * o.n * k / dt, "unit": UNIT, "cores": threads, "kind": "port", "value_1_thread": one,
             "sample": sample + f", {k} frames in {dt:.1f} s",
             "what": "CPU restatement of the reference's shader arithmetic (C, OpenMP); the reference "
                     "itself is WebGL and has no CPU path"}, dt / k * 1e3, k
