@@ -374,7 +374,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     }
     FSIM_TRY(dalloc(&s->key, s->cap));
     FSIM_TRY(dalloc(&s->perm, s->cap));
-    for (int q = 0; q < 3; ++q) FSIM_TRY(dalloc_bytes(&s->dcol[q], s->rs * s->cap));
+    for (int q = 0; q < 2; ++q) FSIM_TRY(dalloc_bytes(&s->dcol[q], s->rs * s->cap));
     FSIM_TRY(dalloc(&s->counts, s->ncell_local + 1));
     FSIM_TRY(dalloc(&s->starts, s->ncell_local + 2));
     FSIM_TRY(dalloc(&s->cursor, s->ncell_local + 1));
@@ -443,7 +443,7 @@ static void free_all(fsim_sim *s)
         cudaFree(s->alive[b]);
         cudaFree(s->pid[b]);
     }
-    void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->dcol[2], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
+    void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
                     s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf};
     for (void *p : ptrs) cudaFree(p);

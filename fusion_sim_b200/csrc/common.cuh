@@ -97,7 +97,8 @@ struct fsim_sim {
     uint32_t *cursor = nullptr;   // [ncell_local + 1]
     uint32_t *blocksums = nullptr;
     uint32_t *perm = nullptr;     // [cap] particle slots ordered by cell (index sort)
-    void *dcol[3] = {};           // [cap] sprite colour 0.001*(v_r, v_a, v_z) of each slot (deposit prepass)
+    void *dcol[2] = {};           // [cap] sprite colour 0.001*(v_r, v_a) of each slot (deposit prepass); 0.001*v_z is
+                                  // formed by the per-cell pass from the stored v_z (8 bytes less written per particle)
     bool keys_valid = false;      // key[] and the histogram in counts[] match the current positions
     bool counts_dirty = false;    // counts[] holds a histogram that no scan has consumed yet
     bool binned = false;          // starts[] and perm[] match the current positions
@@ -196,21 +197,16 @@ inline int dispatch(const fsim_sim *s, F &&f)
 
 // ---- device helpers --------------------------------------------------------------------
 // NEAREST + CLAMP_TO_EDGE texel index (utilities.js:528-531); NaN samples texel 0.
-// Branch-free: max(t, 0) maps NaN and negatives to 0, min(.., n-1) clamps the top texel (and +inf);
-// truncation of a value in [0, n-1] is exact.  `nreal` = (Real)n, passed in so hot loops do not
-// convert the integer again (grid sides are far below 2^24, so n and n-1 are exact in fp32 too).
-__device__ __forceinline__ int tex_idx_r(double u, double nreal)
-{
-    return __double2int_rz(fmin(fmax(u * nreal, 0.0), nreal - 1.0));
-}
-__device__ __forceinline__ int tex_idx_r(float u, float nreal)
-{
-    return __float2int_rz(fminf(fmaxf(u * nreal, 0.0f), nreal - 1.0f));
-}
+// Four instructions: the conversion itself maps NaN to 0 and saturates +-inf / out-of-range values
+// (cvt.rzi.s32), so the clamp to [0, n-1] is done on the INTEGER (two IMNMX) -- an fp64 min/max
+// clamp costs ~25 instructions per call, which was a third of the step kernel's instruction stream.
 template <typename Real>
 __device__ __forceinline__ int tex_idx(Real u, int n)
 {
-    return tex_idx_r(u, (Real)n);
+    if constexpr (sizeof(Real) == 8)
+        return min(max(__double2int_rz(u * (Real)n), 0), n - 1);
+    else
+        return min(max(__float2int_rz(u * (Real)n), 0), n - 1);
 }
 
 __device__ __forceinline__ double fsqrt(double x) { return sqrt(x); }

@@ -26,7 +26,8 @@ constexpr int WARP_CELL_MAX = 256;    // up to here: one warp per cell; larger c
 
 template <typename Real>
 struct CellSumArgs {
-    const Real *dcol[3];   // sprite colour of each slot (deposit prepass)
+    const Real *dcol[2];   // sprite colour 0.001 (v_r, v_a) of each slot (deposit prepass)
+    const Real *vz;        // stored v_z of each slot: the third colour is 0.001 * v_z (empic.js:1006)
     const uint32_t *key;   // KEY_CLIPPED marks sprites that are not deposited
     const uint32_t *id;
     const uint32_t *perm;  // particle slots in cell order
@@ -70,7 +71,7 @@ __device__ __forceinline__ void cell_small(const CellSumArgs<Real> &a, uint32_t 
         const size_t p = pp[j] & KEY_MASK;
         c0[j] = on ? a.dcol[0][p] : (Real)0;
         c1[j] = on ? a.dcol[1][p] : (Real)0;
-        c2[j] = on ? a.dcol[2][p] : (Real)0;
+        c2[j] = on ? (Real)FSIM_DEPOSIT_WEIGHT * a.vz[p] : (Real)0;
     }
 #pragma unroll
     for (int j = 0; j < KR; ++j) {
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(128) cellsum_warp_kernel(const CellSumArgs<Rea
                 s_on[w][r] = on ? 1 : 0;
                 s_col[w][0][r] = on ? a.dcol[0][p] : (Real)0;
                 s_col[w][1][r] = on ? a.dcol[1][p] : (Real)0;
-                s_col[w][2][r] = on ? a.dcol[2][p] : (Real)0;
+                s_col[w][2][r] = on ? (Real)FSIM_DEPOSIT_WEIGHT * a.vz[p] : (Real)0;
             }
         }
         __syncwarp();
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
             const uint32_t j = sidx[t];
             if (j & KEY_CLIPPED) continue;
             const size_t p = a.perm[(size_t)s + j] & KEY_MASK;
-            acc[0] += a.dcol[0][p]; acc[1] += a.dcol[1][p]; acc[2] += a.dcol[2][p];
+            acc[0] += a.dcol[0][p]; acc[1] += a.dcol[1][p]; acc[2] += (Real)FSIM_DEPOSIT_WEIGHT * a.vz[p];
             acc[3] += (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
             cnt++;
         }
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
 template <typename Real>
 __global__ void __launch_bounds__(256)
 cellsum_atomic_kernel(const uint32_t *__restrict__ key, const Real *__restrict__ c0, const Real *__restrict__ c1,
-                      const Real *__restrict__ c2, int64_t n, Real *__restrict__ S, uint32_t *__restrict__ count,
+                      const Real *__restrict__ vz, int64_t n, Real *__restrict__ S, uint32_t *__restrict__ count,
                       int nr, int pitch, int64_t plane)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,7 +251,7 @@ cellsum_atomic_kernel(const uint32_t *__restrict__ key, const Real *__restrict__
     Real *o = S + (size_t)(k / nr) * pitch + (size_t)(k % nr);
     atomicAdd(o, c0[p]);
     atomicAdd(o + plane, c1[p]);
-    atomicAdd(o + 2 * plane, c2[p]);
+    atomicAdd(o + 2 * plane, (Real)FSIM_DEPOSIT_WEIGHT * vz[p]);
     atomicAdd(o + 3 * plane, (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0);
     atomicAdd(count + k, 1u);
 }
@@ -264,7 +265,7 @@ int launch_cellsum_atomic(fsim_sim *s)
         if (s->n == 0) return (int)FSIM_OK;
         Bracket b(s, "cellsum_atomic");
         cellsum_atomic_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
-            s->key, (const Real *)s->dcol[0], (const Real *)s->dcol[1], (const Real *)s->dcol[2], s->n,
+            s->key, (const Real *)s->dcol[0], (const Real *)s->dcol[1], (const Real *)s->part[s->cur][AVZ], s->n,
             (Real *)s->cellsum, s->cellcount, s->nr, s->pitch, s->plane);
         FSIM_CUDA(cudaGetLastError());
         return (int)FSIM_OK;
@@ -277,7 +278,8 @@ int launch_cellsum(fsim_sim *s)
         using Real = decltype(tag);
         const int cur = s->cur, alt = s->cur ^ 1;
         CellSumArgs<Real> a;
-        for (int q = 0; q < 3; ++q) a.dcol[q] = (const Real *)s->dcol[q];
+        for (int q = 0; q < 2; ++q) a.dcol[q] = (const Real *)s->dcol[q];
+        a.vz = (const Real *)s->part[cur][AVZ];
         a.key = s->key;
         a.id = s->pid[cur];
         a.perm = s->perm;

@@ -104,7 +104,7 @@ struct UnpackArgs {
     int64_t nrecv;
     // non-null key: arrivals get their deposit prepass here (key, colour, histogram)
     uint32_t *key, *counts;
-    Real *dcol[3];
+    Real *dcol[2];
     int nr, nz, row0, rows, own_lo, own_hi;
 };
 
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(256) migrate_unpack_kernel(const UnpackArgs<Re
         const uint32_t key = sprite_key_colour<Real>(v[AX], v[AY], v[AZ], rr, v[AVX], v[AVY], v[AVZ], a.nr, a.nz,
                                                      a.row0, a.rows, a.own_lo, a.own_hi, c0, c1, c2);
         a.key[slot] = key;
-        a.dcol[0][slot] = c0; a.dcol[1][slot] = c1; a.dcol[2][slot] = c2;
+        a.dcol[0][slot] = c0; a.dcol[1][slot] = c1;
+        (void)c2;
         atomicAdd(a.counts + (key & KEY_MASK), 1u);
     }
 }
@@ -169,7 +170,7 @@ struct MoveArgs {
     const uint32_t *targets, *sources;
     const uint32_t *ntargets;
     uint32_t *key;  // non-null: the per-slot prepass data moves along
-    Real *dcol[3];
+    Real *dcol[2];
 };
 
 template <typename Real>
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) compact_move_kernel(const MoveArgs<Real> 
     if (m.key) {
         m.key[d] = m.key[s];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) m.dcol[q][d] = m.dcol[q][s];
+        for (int q = 0; q < 2; ++q) m.dcol[q][d] = m.dcol[q][s];
     }
 }
 
@@ -325,7 +326,7 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
             a.nholes = (uint32_t)nholes; a.n_old = n_old; a.nrecv = nrecv;
             a.key = s->keys_valid ? s->key : nullptr;
             a.counts = s->counts;
-            for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
+            for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
             a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
             a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
             Bracket b(s, "migrate_unpack");
@@ -344,7 +345,7 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
             m.alive = s->alive[c]; m.id = s->pid[c];
             m.targets = targets; m.sources = sources; m.ntargets = scr + 2 * MAX_RANKS + 1;
             m.key = s->keys_valid ? s->key : nullptr;
-            for (int q = 0; q < 3; ++q) m.dcol[q] = (Real *)s->dcol[q];
+            for (int q = 0; q < 2; ++q) m.dcol[q] = (Real *)s->dcol[q];
             compact_move_kernel<Real><<<grid_for(nholes - nrecv, 256), 256, 0, s->stream>>>(m);
             FSIM_CUDA(cudaGetLastError());
             s->launches += 2;

@@ -27,7 +27,7 @@ struct PushArgs {
     const uint8_t *__restrict__ sink;
     const Real *__restrict__ invcdf;
     uint32_t *key;      // optional deposit prepass: sort key, sprite colour, histogram
-    Real *dcol[3];
+    Real *dcol[2];
     uint32_t *counts;
     uint32_t *oob;
     uint32_t *leavers, *nleavers;  // slab mode: slots whose new row is not owned (migration list)
@@ -216,7 +216,7 @@ __device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int6
         newcell[k] = sprite_key_colour<Real>(t.x[k], t.y[k], t.z[k], t.rcur[k], t.vx[k], t.vy[k], t.vz[k], a.nr, a.nz,
                                              a.row0, a.rows, a.own_lo, a.own_hi, col[0][k], col[1][k], col[2][k]);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);
+    for (int q = 0; q < 2; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);  // 0.001 v_z is formed by the per-cell pass from v_z itself
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const bool valid = p0 + k < a.n;
@@ -290,7 +290,7 @@ static PushArgs<Real> make_args(fsim_sim *s, bool with_hist)
     a.sink = s->sink;
     a.invcdf = (const Real *)s->invcdf;
     a.key = with_hist ? s->key : nullptr;
-    for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
+    for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
     a.counts = s->counts;
     a.oob = s->oob;
     a.leavers = (with_hist && s->slab) ? s->perm : nullptr;

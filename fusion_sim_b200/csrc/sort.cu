@@ -23,7 +23,7 @@ template <typename Real>
 struct PrepassArgs {
     const Real *x, *y, *z, *vx, *vy, *vz;
     uint32_t *key, *counts;
-    Real *dcol[3];
+    Real *dcol[2];
     int64_t n;
     int nr, nz, row0, rows, own_lo, own_hi;
 };
@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(256) prepass_kernel(const PrepassArgs<Real> a)
         const uint32_t key = sprite_key_colour<Real>(xx, yy, a.z[p], r, a.vx[p], a.vy[p], a.vz[p], a.nr,
                                                      a.nz, a.row0, a.rows, a.own_lo, a.own_hi, c0, c1, c2);
         a.key[p] = key;
-        a.dcol[0][p] = c0; a.dcol[1][p] = c1; a.dcol[2][p] = c2;
+        a.dcol[0][p] = c0; a.dcol[1][p] = c1;  // c2 = 0.001 v_z: formed by the per-cell pass from v_z itself
+        (void)c2;
         c = key & KEY_MASK;
     }
     // warp-aggregated histogram: one atomic per run of equal keys
@@ -253,7 +254,7 @@ int launch_keys(fsim_sim *s)
             a.z = (const Real *)s->part[c][AZ]; a.vx = (const Real *)s->part[c][AVX];
             a.vy = (const Real *)s->part[c][AVY]; a.vz = (const Real *)s->part[c][AVZ];
             a.key = s->key; a.counts = s->counts;
-            for (int q = 0; q < 3; ++q) a.dcol[q] = (Real *)s->dcol[q];
+            for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
             a.n = s->n; a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
             a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
             Bracket b(s, "prepass");

@@ -13,6 +13,6 @@ if [ "$rev" = WORK ]; then
 else
   git archive "$rev" fusion_sim_b200/csrc include | tar -x -C "$d"
 fi
-make -C "$d/fusion_sim_b200/csrc" -j8 EXTRA="$*" >/dev/null
+make -C "$d/fusion_sim_b200/csrc" -j8 libfusionsim.so EXTRA="$*" >/dev/null
 rm -f "$d"/fusion_sim_b200/csrc/*.o
 echo "$d/fusion_sim_b200/csrc/libfusionsim.so"
