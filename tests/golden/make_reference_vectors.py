@@ -138,10 +138,16 @@ def quad_coords(w, h, dtype):
     return np.stack([(i + T(0.5)) / T(w), (j + T(0.5)) / T(h)], 1)
 
 
-def run(dtype, full=False):
+# a second scene whose unit factors are NOT powers of two: N(factor_r/factor_z).toFixed(20) etc. then
+# round the literals the shaders multiply with (empic.js:527,566,606,647), which SPEC cannot show
+SPEC_ODD = dict(SPEC, radius=0.7, height=1.3)
+
+
+def run(dtype, full=False, sp=None):
     from oracle import oracle as orc
     dtype = np.dtype(dtype)
-    sp = SPEC
+    odd = sp is not None
+    sp = SPEC if sp is None else sp
     nr, nz, side = sp["nr"], sp["nz"], sp["nparticles"]
     n, nc = side * side, nr * nz
     h = sp["particle_charge"] * sp["dt"] / (2 * sp["particle_mass"])  # empic.js:44
@@ -241,7 +247,7 @@ def run(dtype, full=False):
     out.update(moments01_norm=norm, moments01_avg=avg)
 
     # -- set({source_pdf}) (:1263-1339): the reference's host-side JavaScript, executed
-    if dtype == np.float64:
+    if dtype == np.float64 and not odd:
         small = inverse_cdf_js(sc["source_pdf"])
         out["invcdf_small_digest"] = table_digest(small)
         out["invcdf_small_sub"] = small.reshape(512, 512, 2)[::5, ::5].copy()
@@ -279,3 +285,7 @@ if __name__ == "__main__":
         res = run(dt, full=True)
         np.savez_compressed(os.path.join(HERE, f"reference_glsl_{name}.npz"), **res)
         print("wrote", name, {k: v.shape for k, v in res.items() if hasattr(v, "shape")})
+        res = run(dt, sp=SPEC_ODD)
+        keep = ("position", "velocity", "rand", "E", "sink", "source_pdf", "B", "loops", "uniform_terms", "R1", "R2", "R3", "A",
+                "step_position", "step_velocity", "step_rand")
+        np.savez_compressed(os.path.join(HERE, f"reference_glsl_odd_{name}.npz"), **{k: res[k] for k in keep})
