@@ -79,6 +79,30 @@ def demo_scene_js(nparticles, uniforms):
             np.array(scope["init_position"], np.float64), np.array(scope["init_velocity"], np.float64))
 
 
+def set_js(sp, dtype, value):
+    """out.set(value) of the reference (empic.js:1157-1261: E, B, position, velocity, sink_mask), executed.
+    The typed arrays are NumPy arrays of `dtype`: float32 reproduces the Float32Array stores, float64 shows
+    the products before that rounding.  GL plumbing lines (tex.update(), programSet...) are dropped."""
+    import types
+    import js_transliterate as jt
+    text = open(REF_JS).read()
+    a = text.index("out.set = function(value) {")
+    a = text.index("\n", a) + 1
+    b = text.index("if (value.source_pdf) {", a)
+    body = re.sub(r"programSet\.draw\(\{.*?\}\);", "", text[a:b], flags=re.S)
+    body = re.sub(r"^\s*(\w+_tex\.update\(\);|programSet\.set\(.*\);)\s*$", "", body, flags=re.M)
+    nr, nz, n = sp["nr"], sp["nz"], sp["nparticles"] ** 2
+    arrs = {k: np.zeros(4 * (nr * nz if k in ("E_arr", "B_arr", "sink_mask_arr") else n), dtype)
+            for k in ("E_arr", "B_arr", "position_arr", "velocity_arr", "sink_mask_arr")}
+    ns = types.SimpleNamespace(E=None, B=None, position=None, velocity=None, sink_mask=None, source_pdf=None)
+    for k, v in value.items():
+        setattr(ns, k, [[list(map(np.float64, c)) if np.ndim(c) else np.float64(c) for c in row] for row in v]
+                if np.ndim(v) == 3 else [list(map(np.float64, row)) for row in v])
+    jt.run(body, dict(value=ns, spec=types.SimpleNamespace(nr=nr, nz=nz), nparticles=n, i=0, j=0,
+                      factor_r=1 / sp["radius"], factor_z=1 / sp["height"], **arrs))
+    return {k[:-4]: v.reshape(-1, 4) for k, v in arrs.items()}
+
+
 def table_digest(t):
     import hashlib
     c = np.array(t, np.float64)
@@ -261,6 +285,15 @@ def run(dtype, full=False, sp=None):
             out["invcdf_demo_digest"] = table_digest(demo)
             out["invcdf_demo_nan_texels"] = np.array(int(np.isnan(demo).any(1).sum()))
 
+    # -- set({E, B, position, velocity, sink_mask}) (:1157-1261): the reference's host-side JavaScript, executed
+    rng = np.random.Generator(np.random.PCG64(99))
+    setv = dict(E=rng.random((nr, nz, 3)) - 0.5, B=rng.random((nr, nz, 3)) - 0.5, position=rng.random((n, 3)) - 0.5,
+                velocity=1e-3 * (rng.random((n, 3)) - 0.5), sink_mask=(rng.random((nr, nz)) > 0.3).astype(np.float64))
+    for k, v in setv.items():
+        out["setin_" + k] = v
+    for k, v in set_js(sp, dtype, setv).items():
+        out["setout_" + k] = v
+
     # -- canvas (:1497-1504): programBMag, then programDensity blended SRC_ALPHA,ONE into the RGBA8 canvas.
     # The two colours are the reference's shader text; clamping to [0,1], rounding to k/255 and the blend are
     # fixed-function GL, emulated as the oracle documents them; canvas rows run top to bottom.
@@ -288,4 +321,5 @@ if __name__ == "__main__":
         res = run(dt, sp=SPEC_ODD)
         keep = ("position", "velocity", "rand", "E", "sink", "source_pdf", "B", "loops", "uniform_terms", "R1", "R2", "R3", "A",
                 "step_position", "step_velocity", "step_rand")
-        np.savez_compressed(os.path.join(HERE, f"reference_glsl_odd_{name}.npz"), **{k: res[k] for k in keep})
+        np.savez_compressed(os.path.join(HERE, f"reference_glsl_odd_{name}.npz"),
+                            **{k: v for k, v in res.items() if k in keep or k.startswith(("setin_", "setout_"))})

@@ -415,3 +415,36 @@ def test_gpu_odd_units_match_the_reference_shaders(precision):
             p, v, r = pos.copy(), g.getVelocity(), g.getRand()
             p[~live], v[~live], r[~live] = ref_pos[~live], f64(d["step_velocity"][k])[~live, :3], f64(d["step_rand"][k])[~live]
             g.setState(p, v, r)
+
+
+# ---- out.set(value), empic.js:1157-1261: layout conversions and unit factors --------------------------
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("scene", ["", "odd_"])
+def test_set_conversions_match_the_reference_javascript(precision, scene):
+    """The typed arrays the reference's set() fills (its JavaScript executed, Float32Array stores emulated
+    in fp32 mode) against the oracle's set(): texel order i + j*nr, the unit factors, w = 1."""
+    from oracle.oracle import OraclePusher
+    d = np.load(os.path.join(HERE, "golden", f"reference_glsl_{scene}{precision}.npz"))
+    o = OraclePusher(dict(SPEC_ODD if scene else SPEC, precision=precision))
+    o.set({k: d["setin_" + k] for k in ("E", "B", "position", "velocity", "sink_mask")})
+    assert_same(o.E, d["setout_E"], "E_arr")
+    assert_same(o.B, d["setout_B"], "B_arr")
+    assert_same(o.position, d["setout_position"], "position_arr")
+    assert_same(o.velocity, d["setout_velocity"], "velocity_arr")
+    assert_same(o.sink_mask[:, 0], d["setout_sink_mask"][:, 0], "sink_mask_arr")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("scene", ["", "odd_"])
+def test_gpu_set_conversions_match_the_reference_javascript(precision, scene):
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    d = np.load(os.path.join(HERE, "golden", f"reference_glsl_{scene}{precision}.npz"))
+    g = makeCylindricalParticlePusher(dict(SPEC_ODD if scene else SPEC, precision=precision))
+    g.set({k: d["setin_" + k] for k in ("E", "B", "position", "velocity", "sink_mask")})
+    f64 = lambda a: a.astype(np.float64)
+    assert_same(g.getField("E"), f64(d["setout_E"][:, :3]), "E")
+    assert_same(g.getField("B"), f64(d["setout_B"][:, :3]), "B")
+    assert_same(g.getPosition(), f64(d["setout_position"]), "position (w = alive = 1)")
+    assert_same(g.getVelocity(), f64(d["setout_velocity"][:, :3]), "velocity")
+    assert_same(g.getField("sink_mask"), (d["setout_sink_mask"][:, 0] > 0.5).astype(np.uint8), "sink mask")
