@@ -157,3 +157,109 @@ def shader_sources(path, env, owner_env=None):
         except KeyError:
             out.setdefault(name, []).append(None)  # needs variables the caller did not give (not on this path)
     return out
+
+
+# ---- which texture feeds which uniform, and in which order the draws happen -------------------------
+def _match(text, i):
+    """Index of the bracket matching the opening bracket at text[i] (strings and comments skipped)."""
+    pairs = {"(": ")", "{": "}", "[": "]"}
+    stack = [pairs[text[i]]]
+    i += 1
+    while stack:
+        c = text[i]
+        if c in "\"'":
+            j = i + 1
+            while text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            i = j
+        elif text.startswith("//", i):
+            i = text.index("\n", i)
+        elif text.startswith("/*", i):
+            i = text.index("*/", i) + 1
+        elif c in pairs:
+            stack.append(pairs[c])
+        elif c == stack[-1]:
+            stack.pop()
+        i += 1
+    return i - 1
+
+
+def _object_literal(text):
+    """{'key': 'value text'} of a flat JS object literal body (keys quoted or bare)."""
+    out, i, depth, cur = {}, 0, 0, []
+    parts = []
+    while i < len(text):
+        c = text[i]
+        if text.startswith("//", i):
+            i = text.index("\n", i) if "\n" in text[i:] else len(text)
+            continue
+        if c in "([{":
+            depth += 1
+        elif c in ")]}":
+            depth -= 1
+        if c == "," and depth == 0:
+            parts.append("".join(cur)); cur = []
+        else:
+            cur.append(c)
+        i += 1
+    parts.append("".join(cur))
+    for p in parts:
+        if ":" in p:
+            k, v = p.split(":", 1)
+            out[k.strip().strip("\"'")] = v.strip()
+    return out
+
+
+def _strip_comments(text):
+    out, i = [], 0
+    while i < len(text):
+        c = text[i]
+        if c in "\"'":
+            j = i + 1
+            while text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            out.append(text[i:j + 1]); i = j + 1
+        elif text.startswith("//", i):
+            i = text.index("\n", i) if "\n" in text[i:] else len(text)
+        elif text.startswith("/*", i):
+            i = text.index("*/", i) + 2
+        else:
+            out.append(c); i += 1
+    return "".join(out)
+
+
+def program_bindings(path):
+    """{program: {"fragment": owner of its fragment source, "uniforms": {name: JS value text}}} from
+    `var P = webgl.linkProgram({...}).set({...})`."""
+    text = open(path).read()
+    out = {}
+    for m in re.finditer(r"var\s+(\w+)\s*=\s*webgl\.linkProgram\s*\(", text):
+        name = m.group(1)
+        end = _match(text, m.end() - 1)
+        args = text[m.end():end]
+        f = re.search(r"fragmentShaderSource\s*:\s*(\w+)\s*\(\s*\)", args)
+        entry = {"fragment": f.group(1) if f else name, "uniforms": {}}
+        rest = text[end + 1:]
+        s = re.match(r"\s*\.set\s*\(\s*\{", rest)
+        if s:
+            close = _match(rest, s.end() - 1)
+            entry["uniforms"] = _object_literal(rest[s.end():close])
+        out[name] = entry
+    return out
+
+
+def draw_sequence(path, method):
+    """[(program, {draw options}, {uniforms set in the same statement})] of `out.METHOD = function...`."""
+    text = open(path).read()
+    m = re.search(r"out\." + method + r"\s*=\s*function\s*\([^)]*\)\s*\{", text)
+    body = _strip_comments(text[m.end():_match(text, m.end() - 1)])
+    seq = []
+    for d in re.finditer(r"(\w+)((?:\s*\.set\s*\(\s*\{[^}]*\}\s*\))?)\s*\.draw\s*\(\s*\{", body):
+        close = _match(body, d.end() - 1)
+        opts = _object_literal(body[d.end():close])
+        sets = {}
+        s = re.search(r"\{([^}]*)\}", d.group(2)) if d.group(2) else None
+        if s:
+            sets = _object_literal(s.group(1))
+        seq.append((d.group(1), opts, sets))
+    return seq

@@ -7,9 +7,11 @@ executed fragment by fragment with the interpreter in oracle/glsl_interp.py.  No
 reference's source is copied into this repository: only the numeric inputs and outputs of that
 execution are saved, and tests/test_reference_glsl.py holds the CPU oracle to them bit for bit.
 
-What the draw calls bind to what (cited from empic.js) is restated here, in `run()`:
-  addCurrentLoop :1352-1363 (shape tables :295-345), addCurrentZ/BZ/BTheta :1380-1411,
-  precalc :1413-1434, step :1436-1469 with the program bindings :814-928, density :1471-1495.
+The orchestration comes from the reference too: which program draws when and into which buffer
+(out.precalc :1413-1434, out.step :1436-1469, the quad draws of out.density :1480-1504) and which buffer
+feeds which uniform (the `.set({...})` after every `webgl.linkProgram`, :506-659, :783-928, :1042-1116) are
+PARSED out of empic.js (js_shader_source.draw_sequence / program_bindings).  Restated by hand, with the
+lines cited: the uniforms addCurrentLoop/Z/BZ/BTheta set per call (:1352-1411) and the point-sprite draw.
 Fixed-function GL behaviour (additive blending ONE,ONE = a floating-point add in draw order, NEAREST
 + CLAMP_TO_EDGE sampling, the identity quad mapping of empic.js:66-92, GLES2 point-sprite coverage)
 is not shader text; it is emulated here as the oracle documents it.
@@ -35,6 +37,7 @@ SPEC = dict(radius=1.0, height=2.0, nr=24, nz=40, dt=2e-9, nparticles=16,
             particle_mass=1.67e-27, particle_charge=1.602e-19)
 
 
+from js_shader_source import JsExpr, draw_sequence, program_bindings  # noqa: E402
 from js_shader_source import shader_sources as _shader_sources  # noqa: E402
 
 
@@ -204,33 +207,52 @@ def run(dtype, full=False, sp=None):
     out["uniform_terms"] = np.array([3.0e5, 0.02, -0.01])
     out["loops"] = np.array(loops)
 
-    # -- precalc (:1413-1434)
-    tB, tE = tex(B, nr, nz), tex(sc["E"], nr, nz)
-    R1 = frag(sh("programPre1"), grid, u_B=tB, u_h=h)
-    R2 = frag(sh("programPre2"), grid, u_B=tB, u_h=h)
-    R3 = frag(sh("programPre3"), grid, u_B=tB, u_h=h)
-    A = frag(sh("programPreA"), grid, u_B=tB, u_E=tE, u_h=h)
-    out.update(R1=R1, R2=R2, R3=R3, A=A)
-
-    # -- step (:1436-1469): rand, velocity, position, each reading the buffers empic.js:814-928 binds
+    # -- the draw calls of out.precalc (:1413-1434) and out.step (:1436-1469) are PARSED out of the reference:
+    # which program runs when, into which buffer, and which buffer feeds which uniform (:506-659, :783-928)
+    bind = program_bindings(REF_JS)
+    jsenv = {"spec.dt": sp["dt"], "speed_of_light": C_LIGHT, "h": h}
     invcdf = np.zeros((512 * 512, 4), dtype)
     invcdf[:, :2] = orc.inv_cdf(sc["source_pdf"]).astype(dtype)  # host JS code (:1268-1339), an INPUT here
-    ent = entropy_table().astype(dtype)
-    t_ent, t_inv, t_sink = tex(ent, 1024, 1024), tex(invcdf, 512, 512), tex(sc["sink"], nr, nz)
-    tR = [tex(a, nr, nz) for a in (R1, R2, R3, A)]
-    pos, vel, rnd = sc["position"], sc["velocity"], sc["rand"]
-    rand_prog, vel_prog, pos_prog = sh("programStepRandB"), sh("step_velocity_frag"), sh("step_position_frag")
+    zeros = lambda m: np.zeros((m, 4), dtype)
+    buf = {"B": (B, nr, nz), "E": (sc["E"], nr, nz), "R1": (zeros(nc), nr, nz), "R2": (zeros(nc), nr, nz),
+           "R3": (zeros(nc), nr, nz), "A": (zeros(nc), nr, nz), "sink_mask": (sc["sink"], nr, nz),
+           "inv_cdf": (invcdf, 512, 512), "entropy_tex": (entropy_table().astype(dtype), 1024, 1024),
+           "position_A": (sc["position"], side, side), "velocity_A": (sc["velocity"], side, side),
+           "rand_A": (sc["rand"], side, side), "position_B": (zeros(n), side, side),
+           "velocity_B": (zeros(n), side, side), "rand_B": (zeros(n), side, side)}
+
+    def draw(program, target, extra_uniforms=None):
+        """One `program.draw({triangles: 6, target})`: the quad covers the target, one fragment per texel."""
+        info = bind[program]
+        uniforms = dict(info["uniforms"], **(extra_uniforms or {}))
+        args = {}
+        for name, js in uniforms.items():
+            if name.startswith("a_"):
+                continue  # the quad's vertex attributes
+            if js in buf:
+                args[name] = tex(*buf[js])
+            else:
+                args[name] = JsExpr(js, jsenv).value()
+        _, w, hh = buf[target]
+        text = src[info["fragment"]][-1]
+        buf[target] = (frag(Shader(text, dtype), quad_coords(w, hh, dtype), **args), w, hh)
+
+    for program, opts, sets in draw_sequence(REF_JS, "precalc"):
+        draw(program, opts["target"], sets)
+    R1, R2, R3, A = (buf[k][0] for k in ("R1", "R2", "R3", "A"))
+    out.update(R1=R1, R2=R2, R3=R3, A=A)
+
     assert src["programStepRandA"] == src["programStepRandB"]
+    step_seq = draw_sequence(REF_JS, "step")
+    assert len(step_seq) == 6
     states = []
-    for k in range(8):
-        tp, tv, tr = tex(pos, side, side), tex(vel, side, side), tex(rnd, side, side)
-        new_rnd = frag(rand_prog, part, u_entropy=t_ent, u_rand=tr)
-        new_vel = frag(vel_prog, part, u_position=tp, u_velocity=tv, u_rand=tr, u_R_1=tR[0], u_R_2=tR[1],
-                       u_R_3=tR[2], u_A=tR[3])
-        new_pos = frag(pos_prog, part, u_position=tp, u_velocity=tex(new_vel, side, side), u_rand=tr,
-                       u_sink=t_sink, u_inv_cdf=t_inv, u_step_factor=sp["dt"] * C_LIGHT)
-        pos, vel, rnd = new_pos, new_vel, new_rnd
-        states.append((pos.copy(), vel.copy(), rnd.copy()))
+    for k in range(4):                      # four out.step() = eight half-steps
+        for q, (program, opts, sets) in enumerate(step_seq):
+            draw(program, opts["target"], sets)
+            if q % 3 == 2:                  # a half-step is complete: its three targets are the new state
+                suffix = step_seq[q][1]["target"][-2:]
+                states.append(tuple(buf[nm + suffix][0].copy() for nm in ("position", "velocity", "rand")))
+    pos, vel, rnd = states[-1]
     out["step_position"] = np.stack([s[0] for s in states])
     out["step_velocity"] = np.stack([s[1] for s in states])
     out["step_rand"] = np.stack([s[2] for s in states])
@@ -266,8 +288,16 @@ def run(dtype, full=False, sp=None):
         for (x, y), c in zip(px, col):
             mom[y, x] = mom[y, x] + c
     out["sprite_moments01"] = mom.reshape(nc, 4)
-    norm = frag(sh("programNormalizeMoments01"), grid, u_moments01=tex(sc["moments01"], nr, nz))
-    avg = frag(sh("avg_frag"), grid, u_ratio=0.01, u_next=tex(norm, nr, nz), u_avg=tex(sc["avg0"], nr, nz))
+    # the quad draws of out.density (:1480-1495), parsed: normalise -> running average -> copy avgA to avgB
+    buf.update(moments01=(sc["moments01"], nr, nz), moments01_norm=(zeros(nc), nr, nz),
+               moments01_avgA=(zeros(nc), nr, nz), moments01_avgB=(sc["avg0"], nr, nz))
+    dens_seq = draw_sequence(REF_JS, "density")
+    assert [d[0] for d in dens_seq] == ["programMoments01", "programNormalizeMoments01", "programAvgMoments",
+                                        "programSet", "programBMag", "programDensity"]
+    for program, opts, sets in dens_seq[1:4]:
+        draw(program, opts["target"], sets)
+    norm, avg = buf["moments01_norm"][0], buf["moments01_avgA"][0]
+    assert np.array_equal(buf["moments01_avgB"][0], avg, equal_nan=True)  # programSet: a copy
     out.update(moments01_norm=norm, moments01_avg=avg)
 
     # -- set({source_pdf}) (:1263-1339): the reference's host-side JavaScript, executed
@@ -297,8 +327,13 @@ def run(dtype, full=False, sp=None):
     # -- canvas (:1497-1504): programBMag, then programDensity blended SRC_ALPHA,ONE into the RGBA8 canvas.
     # The two colours are the reference's shader text; clamping to [0,1], rounding to k/255 and the blend are
     # fixed-function GL, emulated as the oracle documents them; canvas rows run top to bottom.
-    c1 = frag(sh("programBMag"), grid, u_B=tB)
-    c2 = frag(sh("programDensity"), grid, u_moments01=tex(avg, nr, nz))
+    def canvas_colour(program):  # a draw without target: the canvas, nr x nz; bindings parsed like the others
+        info = bind[program]
+        args = {name: tex(*buf[js]) for name, js in info["uniforms"].items() if not name.startswith("a_")}
+        return frag(Shader(src[info["fragment"]][-1], dtype), grid, **args)
+
+    c1, c2 = canvas_colour(dens_seq[4][0]), canvas_colour(dens_seq[5][0])
+    assert "SRC_ALPHA" in dens_seq[5][1]["blend"] and "blend" not in dens_seq[4][1]
     out["bmag_color"], out["density_color"] = c1, c2
     T = dtype.type
     with np.errstate(invalid="ignore"):
