@@ -925,6 +925,9 @@ int fsim_step(fsim_sim *s)
     // emits the deposit prepass (sort key, sprite colour, histogram) of the new state for the
     // density() that follows.
     // Both are done in ONE sweep over the particle storage (push.cu, NH = 2).
+    // After set({position}) the storage order says nothing about the new positions: put the storage into
+    // cell order BEFORE the sweep (an unsorted sweep costs 6.8 ms instead of 2.9 at 64 Mi particles).
+    if (s->steps_since_sort >= (1 << 20) && s->n) FSIM_TRY(finish(s, physical_sort(s)));
     FSIM_TRY(finish(s, launch_push(s, true, 2)));
     s->steps_since_sort++;
     if (s->steps_since_sort >= 4 * sort_interval(s))  // push-only loops: keep the gather coherent
