@@ -324,11 +324,13 @@ int launch_cellsum(fsim_sim *s)
 // offset di it reads two vertical windows of CSTRIP + 10 values (columns -di and +di; consecutive
 // lanes read consecutive words, so no bank conflicts for any plane stride) and slides them over
 // its CSTRIP outputs.  The footprint is mirror-symmetric, so the up to four mirror sources of a
-// weight are added first and weighted once: classes di = 0..5 outer, dj = 0..5 inner, sources
-// (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj) -- the canonical order of the specification; the 40
-// taps that are exactly zero are removed at compile time.  107 fp64 operations per cell and channel
-// plus the two IEEE divisions of the normalisation: the kernel is bound by the fp64 pipe (72 %
-// active in ncu).  Measured on B200 at C5 fp64 (FSIM_CONV_VARIANT, tools/tune.py): 8-row strips on
+// weight are added first and weighted once: classes di = 0..5 outer, dj = 0..5 inner, the two
+// sources of a row first, then the two rows, (S[-di,-dj] + S[+di,-dj]) + (S[-di,+dj] + S[+di,+dj])
+// -- the canonical order of the specification.  The row pairs do not depend on the output row: they
+// are formed once per window (18 adds per column offset for 8 outputs) and shared, ~82 fp64
+// operations per cell and channel instead of 107 (162 without the symmetry); the 40 taps that are
+// exactly zero are removed at compile time.  With the two IEEE divisions of the normalisation the
+// kernel is bound by the fp64 pipe.  Measured on B200 at C5 fp64 (FSIM_CONV_VARIANT, tools/tune.py): 8-row strips on
 // 32 x 8 tiles 0.65 ms, 8-row strips on 32 x 16 tiles 0.69, 4-row strips on 32 x 16 tiles 0.86,
 // 16-row strips 0.88-0.90, 2-row strips 1.50 -- longer strips need fewer shared-memory loads per
 // output, small tiles put more blocks on an SM to hide the single TMA wait of each.
@@ -418,23 +420,21 @@ conv_kernel(const __grid_constant__ CUtensorMap tmS, const ConvArgs<Real> a)
     if (occupied) {
 #pragma unroll
     for (int di = 0; di <= CH; ++di) {
-        Real wm[CWIN], wp[CWIN];
+        // the row pair S[-di] + S[+di] of every window row, formed ONCE and shared by the CSTRIP outputs
+        // that slide over the window (the canonical order adds the two sources of a row first)
+        Real hw[CWIN];
 #pragma unroll
         for (int k = 0; k < CWIN; ++k) {
-            wm[k] = col[k * CBOXW - di];
-            wp[k] = di ? col[k * CBOXW + di] : (Real)0;
+            hw[k] = col[k * CBOXW - di];
+            if (di) hw[k] = hw[k] + col[k * CBOXW + di];
         }
 #pragma unroll
         for (int o = 0; o < CSTRIP; ++o) {
 #pragma unroll
             for (int dj = 0; dj <= CH; ++dj) {
                 if (!tap_nonzero(CH + di, CH + dj)) continue;
-                Real sum = wm[o + CH - dj];
-                if (di) sum = sum + wp[o + CH - dj];
-                if (dj) {
-                    sum = sum + wm[o + CH + dj];
-                    if (di) sum = sum + wp[o + CH + dj];
-                }
+                Real sum = hw[o + CH - dj];
+                if (dj) sum = sum + hw[o + CH + dj];
                 acc[o] = acc[o] + sum * shape_w<Real>((CH + di) + FSIM_NSHAPE * (CH + dj));
             }
         }

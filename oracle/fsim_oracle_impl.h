@@ -387,7 +387,29 @@ void ORC(orc_cell_sums_mt)(int64_t n, const REAL *pos, const REAL *vel, int64_t 
  * are clipped at the target edge).  The footprint is mirror-symmetric, shape[5+di,5+dj] =
  * shape[5-di,5+dj] = shape[5+di,5-dj] = shape[5-di,5-dj] bit for bit, so the (up to four) mirror
  * sources of a weight are added first and weighted once.  Fixed order: di = 0..5 outer, dj = 0..5
- * inner; inside a class (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj), duplicates (di or dj = 0) once. */
+ * inner; inside a class the two sources of a ROW are added first, then the two rows:
+ *     (S[-di,-dj] + S[+di,-dj]) + (S[-di,+dj] + S[+di,+dj]),   duplicates (di or dj = 0) once;
+ * a source outside the grid counts as an exact zero (x + 0 = x).  The row pairs do not depend on the
+ * output row, which is what lets the device kernel form them once per window and share them. */
+static inline void ORC(conv_row_pair)(const REAL *S, int64_t nr, int64_t nz, int64_t i, int64_t jj, int di,
+                                      REAL h[4])
+{
+    h[0] = h[1] = h[2] = h[3] = RC(0.0);
+    if (jj < 0 || jj >= nz) return;
+    if (i - di >= 0) {
+        const REAL *s = S + 4 * ((i - di) + jj * nr);
+        h[0] = s[0]; h[1] = s[1]; h[2] = s[2]; h[3] = s[3];
+    }
+    if (di) {
+        REAL b[4] = {RC(0.0), RC(0.0), RC(0.0), RC(0.0)};
+        if (i + di < nr) {
+            const REAL *s = S + 4 * ((i + di) + jj * nr);
+            b[0] = s[0]; b[1] = s[1]; b[2] = s[2]; b[3] = s[3];
+        }
+        h[0] = h[0] + b[0]; h[1] = h[1] + b[1]; h[2] = h[2] + b[2]; h[3] = h[3] + b[3];
+    }
+}
+
 void ORC(orc_convolve)(int64_t nr, int64_t nz, const REAL *S, const REAL *shape,
                        REAL *mom, int nthreads)
 {
@@ -400,17 +422,12 @@ void ORC(orc_convolve)(int64_t nr, int64_t nz, const REAL *S, const REAL *shape,
                 for (int dj = 0; dj <= FSIM_SHAPE_MID; ++dj) {
                     REAL w = shape[(FSIM_SHAPE_MID + di) + FSIM_NSHAPE * (FSIM_SHAPE_MID + dj)];
                     if (w == RC(0.0)) continue;
-                    REAL sum[4] = {RC(0.0), RC(0.0), RC(0.0), RC(0.0)};
-                    for (int sj = -1; sj <= 1; sj += 2) {
-                        if (dj == 0 && sj > 0) continue;
-                        for (int si = -1; si <= 1; si += 2) {
-                            if (di == 0 && si > 0) continue;
-                            int64_t ii = i + si * di, jj = j + sj * dj;
-                            if (ii < 0 || ii >= nr || jj < 0 || jj >= nz) continue;
-                            const REAL *s = S + 4 * (ii + jj * nr);
-                            sum[0] = sum[0] + s[0]; sum[1] = sum[1] + s[1];
-                            sum[2] = sum[2] + s[2]; sum[3] = sum[3] + s[3];
-                        }
+                    REAL sum[4], hp[4];
+                    ORC(conv_row_pair)(S, nr, nz, i, j - dj, di, sum);
+                    if (dj) {
+                        ORC(conv_row_pair)(S, nr, nz, i, j + dj, di, hp);
+                        sum[0] = sum[0] + hp[0]; sum[1] = sum[1] + hp[1];
+                        sum[2] = sum[2] + hp[2]; sum[3] = sum[3] + hp[3];
                     }
                     acc[0] = acc[0] + sum[0] * w; acc[1] = acc[1] + sum[1] * w;
                     acc[2] = acc[2] + sum[2] * w; acc[3] = acc[3] + sum[3] * w;

@@ -148,9 +148,9 @@ def cell_sums(pos, vel, nr, nz):
 
 def convolve(S, shape, nr, nz):
     """moments01 = S (*) shape with the mirror sources of each weight added first (the footprint is
-    mirror-symmetric): classes di = 0..5 outer, dj = 0..5 inner; inside a class the sources
-    (-di,-dj), (+di,-dj), (-di,+dj), (+di,+dj); zero weights skipped; sources outside the grid are
-    absent (padding with exact zeros is the same arithmetic)."""
+    mirror-symmetric): classes di = 0..5 outer, dj = 0..5 inner; inside a class the two sources of a row
+    first, then the two rows: (S[-di,-dj] + S[+di,-dj]) + (S[-di,+dj] + S[+di,+dj]), duplicates once; zero
+    weights skipped; sources outside the grid are exact zeros."""
     S2 = np.zeros((nz + 10, nr + 10, 4), S.dtype)
     S2[5:5 + nz, 5:5 + nr] = S.reshape(nz, nr, 4)
     out = np.zeros((nz, nr, 4), S.dtype)
@@ -158,19 +158,15 @@ def convolve(S, shape, nr, nz):
     def src(di, dj):
         return S2[5 + dj:5 + dj + nz, 5 + di:5 + di + nr]
 
+    def row_pair(di, dj):
+        return src(-di, dj) + src(di, dj) if di else src(0, dj)
+
     for di in range(6):
         for dj in range(6):
             w = shape[(5 + di) + 11 * (5 + dj)]
             if w == 0:
                 continue
-            tot = np.zeros((nz, nr, 4), S.dtype)
-            for sj in (-1, 1):
-                if dj == 0 and sj > 0:
-                    continue
-                for si in (-1, 1):
-                    if di == 0 and si > 0:
-                        continue
-                    tot = tot + src(si * di, sj * dj)
+            tot = row_pair(di, -dj) + row_pair(di, dj) if dj else row_pair(di, 0)
             out = out + tot * w
     return out.reshape(nr * nz, 4)
 
