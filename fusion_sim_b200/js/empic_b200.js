@@ -61,6 +61,25 @@ exports.makeCylindricalParticlePusher = function (spec) {
     sim.solveFields(value.macro_weight, value.sweeps, typeof value.omega === 'number' ? value.omega : 1.0,
                     value.source === 'instant' ? 1 : 0);
   };
+  // checkpoint / restore (extension): everything a run needs to continue bit for bit
+  out.checkpoint = function () {
+    const n = spec.nparticles * spec.nparticles, nc = spec.nr * spec.nz;
+    const get = (name, len) => { const a = new Float64Array(len); sim.getArray(name, a); return a; };
+    return { position: get('position', 4 * n), velocity: get('velocity', 3 * n), rand: get('rand', 4 * n),
+             E: get('E', 3 * nc), B: get('B', 3 * nc), moments01_avg: get('moments01_avg', 4 * nc) };
+  };
+  out.restore = function (ck) {  // on a simulation created with the same spec and static tables
+    const toIJ = (a) => {  // [cell = i + j*nr][3] as getArray returns it -> value.E[i][j][k] order
+      const o = new Float64Array(a.length);
+      for (let j = 0; j < spec.nz; j++) for (let i = 0; i < spec.nr; i++) for (let k = 0; k < 3; k++)
+        o[(i * spec.nz + j) * 3 + k] = a[(i + j * spec.nr) * 3 + k];
+      return o;
+    };
+    sim.setArray('E', toIJ(ck.E)); sim.setArray('B', toIJ(ck.B));
+    sim.precalc();
+    sim.setState(ck.position, ck.velocity, ck.rand);
+    sim.setField('moments01_avg', ck.moments01_avg);
+  };
   // accessors (extension)
   out.getPositions = () => { const a = new Float64Array(4 * spec.nparticles * spec.nparticles); sim.getArray('position', a); return a; };
   out.getVelocities = () => { const a = new Float64Array(3 * spec.nparticles * spec.nparticles); sim.getArray('velocity', a); return a; };

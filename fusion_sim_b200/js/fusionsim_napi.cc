@@ -34,6 +34,8 @@ class Sim : public Napi::ObjectWrap<Sim> {
             InstanceMethod("step", &Sim::Step),
             InstanceMethod("density", &Sim::Density),
             InstanceMethod("solveFields", &Sim::SolveFields),
+            InstanceMethod("setState", &Sim::SetState),
+            InstanceMethod("setField", &Sim::SetField),
             InstanceMethod("render", &Sim::Render),
             InstanceMethod("getArray", &Sim::GetArray),
             InstanceMethod("destroy", &Sim::Destroy),
@@ -96,6 +98,21 @@ class Sim : public Napi::ObjectWrap<Sim> {
     Napi::Value Precalc(const Napi::CallbackInfo &i) { check(i.Env(), fsim_precalc(sim_)); return i.Env().Undefined(); }
     Napi::Value Step(const Napi::CallbackInfo &i) { check(i.Env(), fsim_step(sim_)); return i.Env().Undefined(); }
     Napi::Value Density(const Napi::CallbackInfo &i) { check(i.Env(), fsim_density(sim_)); return i.Env().Undefined(); }
+    // checkpoint restore (extension): setState(position4 | null, velocity3 | null, rand4 | null) as Float64Arrays
+    Napi::Value SetState(const Napi::CallbackInfo &i)
+    {
+        const double *p[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3; ++k)
+            if (i[k].IsTypedArray()) p[k] = i[k].As<Napi::Float64Array>().Data();
+        check(i.Env(), fsim_set_state(sim_, p[0], p[1], p[2]));
+        return i.Env().Undefined();
+    }
+    // setField("moments01_avg" | "phi", Float64Array)
+    Napi::Value SetField(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_set_field(sim_, i[0].As<Napi::String>().Utf8Value().c_str(), i[1].As<Napi::Float64Array>().Data()));
+        return i.Env().Undefined();
+    }
     // EXTENSION (no reference counterpart): solveFields(macro_weight, sweeps, omega, source)
     Napi::Value SolveFields(const Napi::CallbackInfo &i)
     {
