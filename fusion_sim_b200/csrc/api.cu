@@ -332,6 +332,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
                                        cudaGetErrorString(e) + ")");
     if (sp->device < 0 || sp->device >= ndev) return fail(FSIM_ERR_INVALID, ".device <- no such CUDA device");
     FSIM_CUDA(cudaSetDevice(s->device));
+    FSIM_CUDA(cudaDeviceGetAttribute(&s->nsm, cudaDevAttrMultiProcessorCount, s->device));
     FSIM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 
     s->nr = (int)sp->nr;

@@ -60,6 +60,7 @@ struct fsim_sim {
     int prec = FSIM_F64;
     size_t rs = 8;  // sizeof(real)
     int device = 0;
+    int nsm = 148;            // multiprocessors of the device (grid sizes of the grid-stride kernels)
     cudaStream_t stream = nullptr;
     bool ext_stream = false;  // `stream` belongs to the caller (fsim_set_stream): collectives are stream-ordered
     bool sticky_error = false;

@@ -302,12 +302,12 @@ int launch_cellsum(fsim_sim *s)
         // crowded cells (list lengths are read on the device: no host round trip)
         {
             Bracket b(s, "cellsum_warp");
-            cellsum_warp_kernel<Real><<<148 * 4, 128, 0, s->stream>>>(a);
+            cellsum_warp_kernel<Real><<<s->nsm * 4, 128, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());
         }
         {
             Bracket b(s, "cellsum_heavy");
-            cellsum_heavy_kernel<Real><<<148 * 4, 256, 0, s->stream>>>(a);
+            cellsum_heavy_kernel<Real><<<s->nsm * 4, 256, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());
         }
         return (int)FSIM_OK;

@@ -253,7 +253,7 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
         }
         s->have_leavers = false;
         // destination counts of the leavers and the list length: ONE read-back per frame
-        migrate_count_kernel<Real><<<148 * 2, 256, 0, s->stream>>>((const Real *)s->part[c][AZ], s->perm, nlist_d, s->nz, rb,
+        migrate_count_kernel<Real><<<s->nsm * 2, 256, 0, s->stream>>>((const Real *)s->part[c][AZ], s->perm, nlist_d, s->nz, rb,
                                                                    scr);
         FSIM_CUDA(cudaGetLastError());
         s->launches++;
