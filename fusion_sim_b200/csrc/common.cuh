@@ -61,6 +61,7 @@ struct fsim_sim {
     size_t rs = 8;  // sizeof(real)
     int device = 0;
     int nsm = 148;            // multiprocessors of the device (grid sizes of the grid-stride kernels)
+    uint32_t smem_opt_in = 0; // kernels whose dynamic shared-memory limit was raised ON THIS DEVICE (one bit each)
     cudaStream_t stream = nullptr;
     bool ext_stream = false;  // `stream` belongs to the caller (fsim_set_stream): collectives are stream-ordered
     bool sticky_error = false;

@@ -515,10 +515,11 @@ static int conv_launch(fsim_sim *s, const ConvArgs<Real> &a)
     constexpr int CS_J = CT_J + 2 * CH;
     if (s->tm_sums_rows != CS_J) FSIM_TRY(make_sums_tensor_map(s, CS_J));  // the box height is part of the map
     const size_t smem = sizeof(Real) * 4 * CS_J * ConvBox<Real>::W;
-    static bool attr = false;
-    if (!attr) {
+    // one bit per (strip, tile height) variant: strips 2, 4, 8, 16 x heights 8, 16, 32 -> bits 8..19
+    constexpr uint32_t bit = 1u << (8 + (CSTRIP == 2 ? 0 : CSTRIP == 4 ? 1 : CSTRIP == 8 ? 2 : 3) * 3 + (CT_J == 8 ? 0 : CT_J == 16 ? 1 : 2));
+    if (!(s->smem_opt_in & bit)) {  // per handle, hence per device: the attribute belongs to the device's context
         FSIM_CUDA(cudaFuncSetAttribute(conv_kernel<Real, CSTRIP, CT_J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        s->smem_opt_in |= bit;
     }
     dim3 block(CT_J / CSTRIP * 4 * 32);
     dim3 grid((s->nr + CT_I - 1) / CT_I, (s->own_rows + CT_J - 1) / CT_J);

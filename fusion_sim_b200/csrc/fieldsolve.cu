@@ -260,10 +260,10 @@ static int relax_launch(fsim_sim *s, Real omega)
     a.nr = s->nr; a.rows = s->rows; a.pitch = s->pitch;
     a.omega = omega; a.one_m = (Real)1.0 - omega;
     const size_t smem = sizeof(Real) * 3 * RB_H * RB_W;
-    static bool attr = false;
-    if (!attr) {
+    constexpr uint32_t bit = 1u << T;  // per handle, hence per device: the attribute belongs to the device's context
+    if (!(s->smem_opt_in & bit)) {
         FSIM_CUDA(cudaFuncSetAttribute(relax_kernel<Real, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        s->smem_opt_in |= bit;
     }
     dim3 grid((s->nr + RT_I - 1) / RT_I, (s->rows + RT_J - 1) / RT_J);
     Bracket b(s, T == 4 ? "relax4" : (T == 3 ? "relax3" : (T == 2 ? "relax2" : "relax1")));
