@@ -222,6 +222,11 @@ def run_ours(args):
     local = env_int("LOCAL_RANK", 0)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries ONE JSON line: everything else a library writes to file descriptor 1 (NCCL prints its
+        # version banner there) is sent to stderr; the line itself goes to the saved descriptor
+        sys.stdout.flush()
+        args.real_stdout = os.dup(1)
+        os.dup2(2, 1)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from fusion_sim_b200 import makeCylindricalParticlePusher
@@ -409,7 +414,12 @@ def run_ours(args):
             "push_only_pushes_per_s": halves * n_local * world / (push_ms * 1e-3),
             "extension_field_solve": ext,
         }
-        print(json.dumps(line), flush=True)
+        text = json.dumps(line) + "\n"
+        if getattr(args, "real_stdout", None) is not None:
+            os.write(args.real_stdout, text.encode())
+        else:
+            sys.stdout.write(text)
+            sys.stdout.flush()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
