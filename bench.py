@@ -5,17 +5,21 @@
                     [--workload c5|c3|c2|c1] [--precision f64|f32]
 
 One "step" = one frame of the reference's loop (fusionsim.js:172-174): simulation.step() (two
-leap-frog half-steps, empic.js:1436-1469) + simulation.density() (empic.js:1471-1495) over the
-whole synthetic plasma; 1 push = one half-step of one particle, so a frame is 2*N pushes
-(SURVEY.md section 8d).  Default workload: BASELINE.json configs[4], the weak-scaling shape the
-metric is quoted on -- 64 Mi particles and an 8192 x 2048 slab of cells per GPU.
+leap-frog half-steps, empic.js:1436-1469) + simulation.density() (empic.js:1471-1505: deposit,
+normalise, running average AND the two canvas draws) over the whole synthetic plasma; 1 push = one
+half-step of one particle, so a frame is 2*N pushes.  Default workload:
+BASELINE.json configs[4], the weak-scaling shape the metric is quoted on -- 64 Mi particles and an
+8192 x 2048 slab of cells per GPU.  `--workload c4` is BASELINE configs[3]: 256 Mi particles on
+8192 x 8192 cells, STRONG scaling over 2/4/8 GPUs.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the engine's stream)
 with the state resident in HBM; `e2e` is the same metric through the public host API with host
 buffers: set(position, velocity) from pinned host memory, K frames, and a canvas read-back per
-frame, all inside the timed region.  `--impl reference` times the CPU restatement of the
-reference's shader arithmetic (oracle/, OpenMP, all host threads) on a bounded sample -- the
-reference itself is WebGL and cannot run headless.
+frame, all inside the timed region.  `check` holds run invariants reduced over all ranks (no particle
+lost or duplicated; every in-range particle deposited once) and, at N > 1, a reduced scene on which
+the slab run must equal a single-GPU run bit for bit.  `--impl reference` times the CPU restatement
+of the reference's shader arithmetic (oracle/, OpenMP, all host threads) on the SAME per-GPU
+configuration -- the reference itself is WebGL and cannot run headless.
 """
 from __future__ import annotations
 
@@ -37,10 +41,25 @@ UNIT = "pushes/s"
 WORKLOADS = {
     # name: (particles per GPU, nr, nz per GPU, description)
     "c5": (1 << 26, 8192, 2048, "C5 weak scaling: 64Mi particles + 8192x2048-cell slab per GPU"),
+    "c4": (1 << 28, 8192, 8192, "C4 strong scaling: 256Mi particles, 8192x8192 grid, slab-decomposed"),  # TOTALS
     "c3": (1 << 24, 2048, 2048, "C3: 16Mi particles, 2048x2048 grid"),
     "c2": (1 << 20, 512, 512, "C2: 1Mi particles, 512x512 grid"),
     "c1": (160000, 400, 800, "C1: default demo scene, 160000 particles, 400x800 grid"),
 }
+DEFAULT_STEPS = {"c5": 20, "c4": 20, "c3": 200, "c2": 2000, "c1": 3000}  # timed region >= 0.1 s: the clock sampler sees it
+
+
+def per_gpu_shape(workload, world):
+    """(particles per GPU, nr, grid rows per GPU): C4 is strong scaling (totals divided), the rest weak."""
+    n, nr, nz, _ = WORKLOADS[workload]
+    if workload == "c4":
+        return n // world, nr, nz // world
+    return n, nr, nz
+
+
+def xor_upto(m: int) -> int:
+    """XOR of 0..m."""
+    return [m, 1, m + 1, 0][m % 4] if m >= 0 else 0
 
 
 def env_int(name, default):
@@ -104,13 +123,18 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
-def push_algorithmic_bytes(n, ncell, precision):
+def push_algorithmic_bytes(n, ncell, precision, halves=2):
     """Bytes one sweep of the step kernel must move (per GPU): SURVEY.md section 8d with this
-    build's cell record (8 reals + 1 sink byte per cell instead of the survey's 12 + 1):
-    particle state read + written once (10 reals + 1 flag byte each way), the cell table, the
-    entropy table (4 reals x 1024^2) and the inverse-cdf table (2 reals x 512^2) once."""
+    build's cell record (8 reals per cell instead of the survey's 12, sink mask 1 bit per cell):
+    particle state read + written once (10 reals + 1 flag byte each way); the cell table, the
+    entropy table (4 reals x 1024^2) and the inverse-cdf table (2 reals x 512^2) once -- but never
+    more than the sweep can TOUCH (one texel / record per particle and half-step): the demo scene's
+    160 000 particles touch a third of the entropy table and 4 % of the cells."""
     rs = 8 if precision == "f64" else 4
-    return (2 * (10 * rs + 1)) * float(n) + (8 * rs + 1) * float(ncell) + rs * (4 * 1024 * 1024 + 2 * 512 * 512)
+    touches = float(halves) * float(n)
+    cells = min(float(ncell), touches)
+    return ((2 * (10 * rs + 1)) * float(n) + 8 * rs * cells + float(ncell) / 8
+            + rs * (4 * min(1024.0 * 1024, touches) + 2 * min(512.0 * 512, touches)))
 
 
 def build_scene(workload, rank, world, seed=2026):
@@ -118,7 +142,7 @@ def build_scene(workload, rank, world, seed=2026):
     rank owns rows [rank*nz, (rank+1)*nz) with the particles inside them."""
     from fusion_sim_b200.scenes import (c1_scene, c1_sink_source, plasma_particles, scaled_loops,
                                         scaled_spec)
-    n, nr, nz_local, _ = WORKLOADS[workload]
+    n, nr, nz_local = per_gpu_shape(workload, world)
     if workload == "c1":
         assert world == 1, "C1 is a single-GPU scene"
         return c1_scene(seed)
@@ -140,36 +164,50 @@ def pinned_copy(a):
     return out, t
 
 
-def cpu_baseline(workload, precision, steps, target_s=12.0, threads=None):
-    """CPU restatement of the reference's shader arithmetic (oracle/, kind "port"), timed on the
-    host cores on a bounded sample: a 1/32 z-slab of the workload (same cell size, same particles
-    per cell)."""
-    from fusion_sim_b200.scenes import apply_scene, c1_scene, c1_sink_source, plasma_particles, scaled_loops, scaled_spec
+def make_config(workload, world, precision, n_total, nr, nz, field_sweeps=0, decomposition="slab"):
+    n_local = n_total // world
+    return {"workload": WORKLOADS[workload][3], "particles_total": n_total, "grid": [nr, nz],
+            "precision": precision,
+            "frame": "step()+density() = 2 half-steps + deposit + normalise + running average + the two canvas draws "
+                     "(empic.js:1436-1505)" + (" + solveFields(%d sweeps) [EXTENSION]" % field_sweeps if field_sweeps else ""),
+            "l2": "inputs larger than L2 (particle state %.1f GB per GPU)" % (n_local * (81 if precision == "f64" else 41) / 1e9),
+            "parallelism": ("replicated%d" if decomposition == "replicated" and world > 1 else "slab%d") % world}
+
+
+def cpu_baseline(workload, precision, steps, target_s=12.0, threads=None, scene=None, one_thread=True):
+    """CPU restatement of the reference's shader arithmetic (oracle/, kind "port"), timed on the host
+    cores on the WHOLE per-GPU configuration of the workload (C5: 64 Mi particles on 8192 x 2048 cells;
+    C4: the 8-GPU share), a bounded number of frames."""
+    from fusion_sim_b200.scenes import apply_scene, c1_scene, c1_sink_source, entropy_table, plasma_particles, scaled_loops, scaled_spec
     from oracle.oracle import OraclePusher
     threads = threads or (os.cpu_count() or 1)
-    n, nr, nz, _ = WORKLOADS[workload]
+    n, nr, nz = per_gpu_shape(workload, 8 if workload == "c4" else 1)
     if workload == "c1":
         sc = c1_scene(2026)
         sc["spec"]["precision"] = precision
         sample = "whole C1 scene (160000 particles, 400x800 grid)"
     else:
-        frac = 32 if n >= (1 << 24) else (4 if n >= (1 << 20) else 1)
-        ns, nzs = n // frac, max(16, nz // frac)
-        spec = scaled_spec(nr, nzs, ns, precision=precision)
-        pos, vel = plasma_particles(spec, ns, 99)
-        sink, source = c1_sink_source(nr, nzs)
+        spec = scaled_spec(nr, nz, n, precision=precision)
+        if scene is not None and len(scene["position"]) == n and scene["spec"]["nz"] == nz:
+            pos, vel = scene["position"], scene["velocity"]  # the very arrays the GPU arm uploads
+        else:
+            pos, vel = plasma_particles(spec, n, 2026, z_lo=0.02, z_hi=0.98)
+        sink, source = c1_sink_source(nr, nz)
         sc = dict(spec=spec, position=pos, velocity=vel, sink_mask=sink, source_pdf=source, loops=scaled_loops(spec))
-        sample = f"1/{frac} z-slab of the workload: {nr}x{nzs} cells, {ns} particles (same particles per cell)"
+        sample = f"whole per-GPU workload: {nr}x{nz} cells, {n} particles"
+        if workload == "c4":
+            sample += " (the 8-GPU share of C4)"
     o = OraclePusher(sc["spec"], nthreads=threads)
     rng = np.random.Generator(np.random.PCG64(5))
     sc["rand"] = rng.random((o.n, 4))
-    from fusion_sim_b200.scenes import entropy_table
     sc["entropy"] = entropy_table(rng)
     apply_scene(o, sc)
+    del sc
 
     def frame():
         o.step()
         o.density(timing_mt=True)
+        o.canvas  # noqa: B018 -- the two canvas draws are part of the reference's density()
 
     frame()  # warm-up (page faults, OpenMP pool)
     t0 = time.perf_counter()
@@ -180,18 +218,20 @@ def cpu_baseline(workload, precision, steps, target_s=12.0, threads=None):
     for _ in range(k):
         frame()
     dt = time.perf_counter() - t0
-    # the same sample on ONE host thread (SURVEY.md section 8d asks for both), a few frames only
+    # the same configuration on ONE host thread (SURVEY.md section 8d asks for both): one or a few frames,
+    # only when that stays within ~25 s
     one = None
-    if threads > 1 and not steps:
+    est1 = t1 * threads * 0.7
+    if one_thread and threads > 1 and est1 < 25.0:
         o.nthreads = 1
-        k1 = max(2, min(k, int(4.0 / max(t1 * threads * 0.6, 1e-6))))
+        k1 = max(1, min(k, int(6.0 / max(est1, 1e-6))))
         t0 = time.perf_counter()
         for _ in range(k1):
             frame()
         one = 2.0 * o.n * k1 / (time.perf_counter() - t0)
         o.nthreads = threads
     return {"value": 2.0 * o.n * k / dt, "unit": UNIT, "cores": threads, "kind": "port", "value_1_thread": one,
-            "sample": sample + f", {k} frames in {dt:.1f} s",
+            "sample": sample + f", {k} frames in {dt:.1f} s", "sample_fraction": 1.0,
             "what": "CPU restatement of the reference's shader arithmetic (C, OpenMP); the reference "
                     "itself is WebGL and has no CPU path"}, dt / k * 1e3, k
 
@@ -201,19 +241,72 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    cb, ms, k = cpu_baseline(args.workload, args.precision, args.steps if args.steps_given else 0, threads=threads)
-    n, nr, nz, desc = WORKLOADS[args.workload]
+    # the driver passes the steps of the GPU arm; a CPU frame of the full configuration costs about a
+    # second, so the count is capped to keep the run within a few minutes
+    want = min(args.steps, 12) if args.steps_given else 0
+    cb, ms, k = cpu_baseline(args.workload, args.precision, want, threads=threads, one_thread=False)
+    world = max(1, args.gpus)
+    n, nr, nz = per_gpu_shape(args.workload, world)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": k, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": desc, "precision": args.precision, "frame": "step()+density()",
-                   "sample": cb["sample"]},
+        "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": args.precision,
+        "data": "synthetic",
+        "config": make_config(args.workload, world, args.precision, n * world, nr, nz * world),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "one CPU host whatever N is: the sample is the per-GPU configuration (at N = 1 that IS the "
+                "GPU arm's configuration); a rate, so comparable per GPU",
     }
     print(json.dumps(line), flush=True)
+
+
+def reduced_slab_check(rank, world, local, precision):
+    """At N > 1: a reduced scene (2^17 particles and a 256 x 64 slab per rank, plasma right up to the
+    walls so that particles are absorbed and respawn into other slabs) run twice on this GPU's rank --
+    as one slab of the N-rank run and, whole, as a single-GPU run.  After 4 frames this rank's particles
+    (by global id) and its rows of per-cell counts and running average must be equal bit for bit."""
+    import ctypes as C
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200._lib import check, lib
+    from fusion_sim_b200.dist import SlabPusher, slab_bounds
+    from fusion_sim_b200.scenes import apply_scene, c1_sink_source, entropy_table, plasma_particles, scaled_loops, scaled_spec
+    nr, nz, n = 256, 64 * world, (1 << 17) * world
+    spec = scaled_spec(nr, nz, n, precision=precision, device=local)
+    pos, vel = plasma_particles(spec, n, 4242, z_lo=0.0005, z_hi=0.9995, r_lo=0.0005, r_hi=0.9995)
+    vel *= 8.0  # several rows per frame: drift across the slab boundaries, not only respawns
+    sink, source = c1_sink_source(nr, nz)
+    rng = np.random.Generator(np.random.PCG64(77))
+    sc = dict(spec=spec, position=pos, velocity=vel, sink_mask=sink, source_pdf=source, rand=rng.random((n, 4)),
+              entropy=entropy_table(rng), loops=scaled_loops(spec))
+    single = makeCylindricalParticlePusher(spec)
+    apply_scene(single, sc)
+    b = slab_bounds(nz, world)
+    row = np.clip(np.floor(pos[:, 2] / spec["height"] * nz).astype(np.int64), 0, nz - 1)
+    sel = np.nonzero((row >= b[rank]) & (row < b[rank + 1]))[0]
+    loc = dict(sc)
+    for k in ("position", "velocity", "rand"):
+        loc[k] = sc[k][sel]
+    slab = SlabPusher(dict(spec), loc, rank, world, halo_rows=16, cap_neighbour=16384, cap_far=8192)
+    gid = np.ascontiguousarray(sel.astype(np.uint64))
+    check(lib().fsim_set_ids(slab.sim.handle, gid.ctypes.data_as(C.c_void_p)))
+    for _ in range(4):
+        single.step(); single.density()
+        slab.step(); slab.density()
+    slab.sync(); single.sync()
+    ids = slab.sim.getIds().astype(np.int64)
+    same = lambda x, y: bool(((x == y) | (np.isnan(x) & np.isnan(y))).all())
+    ok = same(single.getPosition()[ids], slab.sim.getPosition()) and same(single.getVelocity()[ids], slab.sim.getVelocity()) \
+        and same(single.getRand()[ids], slab.sim.getRand())
+    row0 = max(0, b[rank] - 16)
+    lo, hi = (b[rank] - row0) * nr, (b[rank + 1] - row0) * nr
+    glo, ghi = b[rank] * nr, b[rank + 1] * nr
+    ok = ok and same(single.getField("moments01_avg")[glo:ghi], slab.sim.getField("moments01_avg")[lo:hi])
+    ok = ok and bool((single.getField("cell_count")[glo:ghi] == slab.sim.getField("cell_count")[lo:hi]).all())
+    moved = slab.migrated
+    slab.sim.destroy(); single.destroy()
+    return ok, moved
 
 
 def run_ours(args):
@@ -232,6 +325,32 @@ def run_ours(args):
     from fusion_sim_b200 import makeCylindricalParticlePusher
     from fusion_sim_b200.scenes import apply_scene
 
+    def all_ranks(values, op="sum"):
+        """Reduce a list of Python ints over the ranks (exact: gathered, combined on the host)."""
+        if world == 1:
+            return list(values)
+        import torch.distributed as dist
+        t = torch.tensor([int(v) & 0x7fffffffffffffff for v in values] + [int(v) >> 63 for v in values],
+                         dtype=torch.int64, device="cuda")
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        k = len(values)
+        res = [0] * k
+        for o in out:
+            o = o.tolist()
+            for i in range(k):
+                v = o[i] | (o[k + i] << 63)
+                res[i] = (res[i] ^ v) if op == "xor" else ((res[i] + v) & 0xffffffffffffffff)
+        return res
+
+    reduced = None
+    if world > 1 and args.decomposition == "slab" and not args.no_reduced_check:
+        ok, moved = reduced_slab_check(rank, world, local, args.precision)
+        okall, movedall = all_ranks([0 if ok else 1, moved])
+        reduced = {"slab_equals_single_gpu": okall == 0, "records_migrated": movedall,
+                   "what": "reduced scene (2^17 particles + 256x64 cells per rank, walls reached), 4 frames: every rank's "
+                           "particles by global id, per-cell counts and running average bit-equal to a single-GPU run"}
+
     sc = build_scene(args.workload, rank, world)
     spec = dict(sc["spec"])
     spec.update(precision=args.precision, device=local)
@@ -244,17 +363,18 @@ def run_ours(args):
         sim = ReplicatedPusher(spec, sc, rank, world)  # measured alternative: no migration, all-reduce of the sums
     elif world > 1:
         from fusion_sim_b200.dist import SlabPusher
-        sim = SlabPusher(spec, sc, rank, world)
+        sim = SlabPusher(spec, sc, rank, world, exchange=args.exchange)
     else:
         sim = makeCylindricalParticlePusher(spec)
         apply_scene(sim, sc)
     nr, nz = int(spec["nr"]), int(spec["nz"])
     ncell_local = sim.ncell_local
-    # two host images for the e2e leg: frame k's read-back overlaps frame k+1 (slab ranks fill
-    # only their rows of the full-size image, so only those pages are touched)
-    _keep3 = [torch.empty((nz, nr, 4), dtype=torch.uint8, pin_memory=(world == 1)) for _ in range(2)]
+    slab_mode = world > 1 and args.decomposition == "slab"
+    own_rows = nz // world if slab_mode else nz  # replicated: every rank renders the whole canvas
+    # two pinned host images for the e2e leg: frame k's read-back overlaps frame k+1.  A slab rank reads
+    # back its own rows only (its share of the canvas).
+    _keep3 = [torch.empty((own_rows, nr, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     canvases = [t.numpy() for t in _keep3]
-    canvas = canvases[0]
 
     solve = {"macro_weight": 1.0e6, "sweeps": args.field_sweeps, "omega": 1.0} if args.field_sweeps > 0 else None
 
@@ -263,6 +383,7 @@ def run_ours(args):
         sim.density()
         if solve:  # EXTENSION: the self-consistent frame; off by default (the reference has none)
             sim.solveFields(solve)
+        sim.draw_canvas()  # the two canvas draws of the reference's density() (empic.js:1497-1504), device-resident
 
     def barrier():
         sim.sync()
@@ -288,10 +409,12 @@ def run_ours(args):
     barrier()
     sampler.recording = True
     l0 = sim.launch_count
+    t_host0 = time.perf_counter()
     sim.mark(0)
     for _ in range(args.steps):
         frame()
     sim.mark(1)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     ms_total = sim.elapsed_ms(0, 1)
     sampler.recording = False
     barrier()
@@ -302,19 +425,54 @@ def run_ours(args):
     n_total = n_local * world
     value = 2.0 * n_total * args.steps / (ms_total * 1e-3)
 
-    # ---- per-kernel device times over K more frames (CUDA events around every launch) ----
+    # ---- run invariants, reduced over the ranks: nothing lost, nothing duplicated, everything deposited ----
+    dg = sim.check_digest()
+    tot = all_ranks([dg["particles"], dg["id_sum"], dg["deposited"]])
+    (xr,) = all_ranks([dg["id_xor"]], op="xor")
+    want_sum = (n_total * (n_total - 1) // 2) & 0xffffffffffffffff
+    check_line = {"particles_total": tot[0], "id_xor": xr, "id_sum": tot[1], "deposited": tot[2],
+                  "sum_alpha": reduce_max(dg["sum_alpha"]) if world == 1 else None,
+                  "expected": {"particles_total": n_total, "id_xor": xor_upto(n_total - 1), "id_sum": want_sum},
+                  "ok": tot[0] == n_total and xr == xor_upto(n_total - 1) and tot[1] == want_sum and tot[2] <= n_total
+                        and tot[2] > 0.98 * n_total}
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dg["sum_alpha"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        check_line["sum_alpha"] = float(t.item())
+    if args.decomposition == "replicated" and world > 1:  # every rank deposits every particle there
+        check_line["ok"] = tot[0] == n_total and xr == xor_upto(n_total - 1) and tot[1] == want_sum
+    if reduced is not None:
+        check_line["reduced_scene"] = reduced
+        check_line["ok"] = check_line["ok"] and reduced["slab_equals_single_gpu"]
+
+    # ---- per-kernel device times over K more frames (CUDA events around every launch), and the exchanges ----
     sim.timing(True)
     sim.timing_reset()
+    if slab_mode:
+        sim.comm_timing = True
+        sim.comm_ms()
     for _ in range(args.steps):
         frame()
     kern = {}
     for nm in ("push", "push2", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_warp", "cellsum_heavy", "conv",
-               "migrate_pack", "migrate_unpack", "charge_source", "relax4", "relax2", "relax1", "efield", "precalc"):
+               "render", "migrate_pack", "migrate_unpack", "charge_source", "relax4", "relax2", "relax1", "efield", "precalc"):
         ms, cnt = sim.timing_get(nm)
         if cnt:
             kern[nm] = {"ms_per_launch": ms / cnt, "launches_per_step": cnt / args.steps,
                         "ms_per_step": ms / args.steps}
     sim.timing(False)
+    comm = None
+    if slab_mode:
+        c = sim.comm_ms()
+        sim.comm_timing = False
+        comm = {k: reduce_max(v / args.steps) for k, v in c.items()}
+        comm["what"] = ("max over ranks, ms per frame, CUDA events on the frame's stream: migrate_exchange = the all-to-all of "
+                        "the fixed-size record regions (includes waiting for the slowest peer); halo_exchange_exposed = what "
+                        "is left of the 5-row halo exchange after the interior stencil ran under it; host_wait = host time "
+                        "blocked in synchronisations inside the frame (none with the fixed-region exchange)")
+        comm["exchange"] = args.exchange
+        comm["host_enqueue_ms_per_step"] = reduce_max(host_enqueue_ms / args.steps)
     peak, peak_kind = measured_peak()
     # dominant kernel: the fused step sweep (both half-steps of step() in one pass over HBM,
     # push.cu NH=2).  Its algorithmic bytes are those of ONE sweep: particle state read + written
@@ -322,7 +480,7 @@ def run_ours(args):
     pk = "push2" if "push2" in kern else "push"
     halves = 2 if pk == "push2" else 1
     push_ms = kern[pk]["ms_per_launch"]
-    alg = push_algorithmic_bytes(n_local, ncell_local, args.precision)
+    alg = push_algorithmic_bytes(n_local, ncell_local, args.precision, halves)
     achieved = alg / (push_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "push_traffic.json")
@@ -339,21 +497,32 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": push_ms, "traffic": traffic,
                 "achieved_per_push_formula": halves * alg / (push_ms * 1e-3) / 1e9,
                 "frac_of_nominal_8000": achieved / 8000.0, "kernels_ms_per_step": kern}
+    # whole frame against the roofline: algorithmic bytes of the sweep + the deposit chain (SURVEY 8d:
+    # 128 bytes per cell in fp64, the particle part being fused into the sweep)
+    rs = 8 if args.precision == "f64" else 4
+    frame_alg = alg + 16.0 * rs * ncell_local
+    roofline["frame"] = {"algorithmic_bytes": frame_alg, "achieved": frame_alg / (ms_total / args.steps * 1e-3) / 1e9,
+                         "frac": frame_alg / (ms_total / args.steps * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the public host API with host buffers ----
     # set(position, velocity) from pinned host arrays, then K frames each followed by the read-back
     # of the canvas (this rank's rows) into pinned host memory; all inside the timed region.
     from fusion_sim_b200._lib import check, lib
     base = sim.sim if world > 1 else sim
-    own_rows = nz if args.decomposition == "replicated" else nz // world  # replicated: every rank renders the whole canvas
     h2d = 2 * pos_h.nbytes
     d2h = 4 * nr * own_rows
     def e2e_pass(frames):
         check(lib().fsim_set_particle_count(base.handle, n_local))
         base.set({"position": pos_h, "velocity": vel_h})
         for k in range(frames):
-            frame()
-            sim.render_async(canvases[k & 1])
+            sim.step()
+            sim.density()
+            if solve:
+                sim.solveFields(solve)
+            if slab_mode:
+                sim.render_rows_async(canvases[k & 1])
+            else:
+                sim.render_async(canvases[k & 1])
 
     e2e_pass(2)  # untimed warm-up of exactly this path: first use of the copy stream, canvas buffers, pinned pages
     barrier()
@@ -373,7 +542,7 @@ def run_ours(args):
     # ---- EXTENSION row N4, reported beside the headline (never inside it unless --field-sweeps is given):
     # device time of one solveFields() of 8 sweeps and of its kernels on this workload's grid
     ext = None
-    if world == 1 and not solve:
+    if world == 1 and not solve and not args.no_extension_probe:
         probe = {"macro_weight": 1.0e6, "sweeps": 8, "omega": 1.0}
         sim.solveFields(probe)  # allocation + warm-up
         sim.timing(True)
@@ -385,7 +554,6 @@ def run_ours(args):
         ext = {"what": "solveFields(8 weighted-Jacobi sweeps) = charge source + 2 x relax4 (TMA-staged, 4 sweeps per "
                        "launch) + E = -grad(phi) + precalc; EXTENSION, no reference counterpart",
                "ms_per_solve": sim.elapsed_ms(4, 5) / 5, "kernels_ms_per_launch": {}}
-        rs = 8 if args.precision == "f64" else 4
         for nm, nbytes in (("charge_source", 2 * rs), ("relax4", 3 * rs), ("efield", 4 * rs), ("precalc", 14 * rs)):
             ms, cnt = sim.timing_get(nm)
             if cnt:
@@ -394,23 +562,19 @@ def run_ours(args):
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, _, _ = cpu_baseline(args.workload, args.precision, 0)
+        if hasattr(sim, "destroy"):
+            sim.destroy()  # the CPU leg needs the host memory bandwidth to itself
+        cb, _, _ = cpu_baseline(args.workload, args.precision, 0, scene=sc)
 
     if rank == 0:
-        n, nr_, nz_, desc = WORKLOADS[args.workload]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": desc, "particles_total": n_total, "grid": [nr, nz],
-                       "precision": args.precision,
-                       "frame": "step()+density() = 2 half-steps + deposit" + (
-                           " + solveFields(%d sweeps) [EXTENSION]" % args.field_sweeps if solve else ""),
-                       "l2": "inputs larger than L2 (particle state %.1f GB per GPU)" % (
-                           n_local * (81 if args.precision == "f64" else 41) / 1e9),
-                       "parallelism": ("replicated%d" if args.decomposition == "replicated" and world > 1 else "slab%d") % world},
+            "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": args.precision,
+            "data": "synthetic",
+            "config": make_config(args.workload, world, args.precision, n_total, nr, nz, args.field_sweeps, args.decomposition),
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cb,
+            "roofline": roofline, "cpu_baseline": cb, "check": check_line, "comm_ms_per_step": comm,
             "push_only_pushes_per_s": halves * n_local * world / (push_ms * 1e-3),
             "extension_field_solve": ext,
         }
@@ -423,6 +587,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    if not check_line["ok"]:
+        sys.stderr.write("bench.py: run invariants violated: %s\n" % json.dumps(check_line))
+        sys.exit(3)
 
 
 def main():
@@ -432,6 +599,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--exchange", default="fixed", choices=["fixed", "exact"],
+                    help="slab runs: fixed-capacity regions with device-side counts (no host round trip) or the exact "
+                         "all-to-all-v with counts read back to the host")
+    ap.add_argument("--no-reduced-check", action="store_true", help="skip the reduced-scene slab == single-GPU check")
+    ap.add_argument("--no-extension-probe", action="store_true")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decomposition", default="slab", choices=["slab", "replicated"],
@@ -441,7 +613,7 @@ def main():
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:
-        args.steps = 20
+        args.steps = DEFAULT_STEPS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

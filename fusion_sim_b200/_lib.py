@@ -64,6 +64,8 @@ _SIGS = {
     "fsim_density": (C.c_int, [_P]),
     "fsim_render_rgba8": (C.c_int, [_P, _P]),
     "fsim_render_rgba8_async": (C.c_int, [_P, _P]),
+    "fsim_render_rows_async": (C.c_int, [_P, _P]),
+    "fsim_draw_canvas": (C.c_int, [_P]),
     "fsim_sort": (C.c_int, [_P]),
     "fsim_sync": (C.c_int, [_P]),
     "fsim_particle_count": (C.c_int64, [_P]),
@@ -105,6 +107,12 @@ _SIGS = {
     "fsim_solve_fields_stage": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_field_rows": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fsim_cellsum_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "fsim_migrate_setup": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(_P), C.POINTER(_P), _P, _P]),
+    "fsim_migrate_begin": (C.c_int, [_P]),
+    "fsim_migrate_end": (C.c_int, [_P]),
+    "fsim_migrate_stats": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "fsim_density_interior": (C.c_int, [_P]),
+    "fsim_check_digest": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "fsim_density_begin": (C.c_int, [_P]),
     "fsim_density_end": (C.c_int, [_P]),
 }

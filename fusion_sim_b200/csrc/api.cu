@@ -196,13 +196,77 @@ __global__ void planar_out_kernel(const Real *__restrict__ in, double *__restric
     for (int q = 0; q < 4; ++q) out[4 * c + q] = (double)in[q * plane + o];
 }
 
-// value.sink_mask [nr][nz] -> 1 byte per global cell i + j*nr; the shader tests .r > 0.5 (:719)
-__global__ void sink_in_kernel(const double *__restrict__ in, uint8_t *__restrict__ out, int nr, int nz)
+// ---- run invariants (fsim_check_digest): particle ids and the deposit, reduced on the device ----------
+// d[0] ^= id, d[1] += id over the live slots; d[2] += count over the owned cells (u64 atomics: exact, order-free)
+__global__ void __launch_bounds__(256)
+digest_ids_kernel(const uint32_t *__restrict__ id, int64_t n_host, const uint32_t *__restrict__ n_dev, unsigned long long *d)
+{
+    const int64_t n = live_count(n_dev, n_host);
+    unsigned long long x = 0, sum = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        x ^= id[p];
+        sum += id[p];
+    }
+    for (int o = 16; o; o >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicXor(d, x);
+        atomicAdd(d + 1, sum);
+    }
+}
+// counts and the weight channel of the per-cell sums over the owned rows; the floating-point partial sums
+// are formed in a fixed order (one per block, tree inside the block) and added in block order by the host
+template <typename Real>
+__global__ void __launch_bounds__(256)
+digest_cells_kernel(const uint32_t *__restrict__ count, const Real *__restrict__ alpha, int nr, int pitch, int row_lo,
+                    int nrows, unsigned long long *d, double *partial)
+{
+    __shared__ double sh[8];
+    __shared__ unsigned long long shc[8];
+    const int64_t ncell = (int64_t)nr * nrows;
+    const int64_t per = (ncell + gridDim.x - 1) / gridDim.x;
+    const int64_t c0 = (int64_t)blockIdx.x * per, c1 = min(ncell, c0 + per);
+    double a = 0.0;
+    unsigned long long cnt = 0;
+    for (int64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+        const int64_t j = row_lo + c / nr, i = c % nr;
+        cnt += count[j * nr + i];
+        a += (double)alpha[j * pitch + i];
+    }
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = a; shc[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        unsigned long long tc = 0;
+        for (int w = 0; w < 8; ++w) { t += sh[w]; tc += shc[w]; }
+        partial[blockIdx.x] = t;
+        atomicAdd(d + 2, tc);
+    }
+}
+
+// value.sink_mask [nr][nz] -> 1 bit per global cell i + j*nr; the shader tests .r > 0.5 (:719).
+// One warp per 32-cell word (ballot): 2 MB instead of 16.7 MB at 8192 x 2048, resident in L2 for good.
+__global__ void sink_in_kernel(const double *__restrict__ in, uint32_t *__restrict__ out, int nr, int nz)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim is a multiple of 32
+    bool keep = false;
+    if (c < (int64_t)nr * nz) {
+        const int i = (int)(c % nr), j = (int)(c / nr);
+        keep = in[(size_t)i * nz + j] > 0.5;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0 && c < (int64_t)nr * nz) out[c >> 5] = word;
+}
+__global__ void sink_out_kernel(const uint32_t *__restrict__ in, uint8_t *__restrict__ out, int64_t ncell)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= (int64_t)nr * nz) return;
-    const int i = (int)(c % nr), j = (int)(c / nr);
-    out[c] = in[(size_t)i * nz + j] > 0.5 ? 1 : 0;
+    if (c < ncell) out[c] = (in[c >> 5] >> (c & 31)) & 1u;
 }
 
 // ---- host-side restatement of the source_pdf -> inverse-cdf table build (empic.js:1268-1339) --
@@ -275,13 +339,21 @@ static void build_shape(double *out, bool as_f32)
     }
 }
 
-static int check(fsim_sim *s)
+int check_handle(fsim_sim *s)
 {
     if (!s) return fail(FSIM_ERR_INVALID, "null simulation handle");
     if (s->sticky_error) return fail(FSIM_ERR_CUDA, "handle is in a sticky CUDA error state: " + g_last_error);
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
     return FSIM_OK;
+}
+static int check(fsim_sim *s) { return check_handle(s); }
+// entry points that address particles by count: the asynchronous slab exchange keeps the exact count on
+// the device (settle_count synchronises and refreshes fsim_sim::n)
+static int check_n(fsim_sim *s)
+{
+    FSIM_TRY(check_handle(s));
+    return settle_count(s);
 }
 
 static int finish(fsim_sim *s, int rc)
@@ -290,19 +362,22 @@ static int finish(fsim_sim *s, int rc)
     return rc;
 }
 
+// allocations are zeroed ON THE HANDLE'S STREAM (a cudaStreamNonBlocking stream is not ordered after
+// the legacy default stream a plain cudaMemset runs on)
+static thread_local cudaStream_t g_alloc_stream = nullptr;
 template <typename T>
 static int dalloc(T **p, size_t count, bool zero = true)
 {
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     FSIM_CUDA(cudaMalloc((void **)p, bytes));
-    if (zero) FSIM_CUDA(cudaMemset(*p, 0, bytes));
+    if (zero) FSIM_CUDA(cudaMemsetAsync(*p, 0, bytes, g_alloc_stream));
     return FSIM_OK;
 }
 static int dalloc_bytes(void **p, size_t bytes, bool zero = true)
 {
     bytes = std::max<size_t>(bytes, 16);
     FSIM_CUDA(cudaMalloc(p, bytes));
-    if (zero) FSIM_CUDA(cudaMemset(*p, 0, bytes));
+    if (zero) FSIM_CUDA(cudaMemsetAsync(*p, 0, bytes, g_alloc_stream));
     return FSIM_OK;
 }
 
@@ -334,6 +409,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_CUDA(cudaSetDevice(s->device));
     FSIM_CUDA(cudaDeviceGetAttribute(&s->nsm, cudaDevAttrMultiProcessorCount, s->device));
     FSIM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    g_alloc_stream = s->stream;
 
     s->nr = (int)sp->nr;
     s->nz = (int)sp->nz;
@@ -383,7 +459,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_TRY(dalloc_bytes(&s->cellrec, s->rs * RECSTRIDE * s->ncell_local));
     FSIM_TRY(dalloc_bytes(&s->E, s->rs * 3 * s->ncell_local));
     FSIM_TRY(dalloc_bytes(&s->B, s->rs * 3 * s->ncell_local));
-    FSIM_TRY(dalloc(&s->sink, s->ncell_global));
+    FSIM_TRY(dalloc(&s->sink, (s->ncell_global + 31) / 32));
     FSIM_TRY(dalloc_bytes(&s->entropy, s->rs * 4 * FSIM_N_ENTROPY * FSIM_N_ENTROPY));
     FSIM_TRY(dalloc_bytes(&s->invcdf, s->rs * 2 * FSIM_N_INVCDF * FSIM_N_INVCDF));
     FSIM_TRY(dalloc_bytes(&s->cellsum, s->rs * 4 * s->plane));
@@ -398,7 +474,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_TRY(dalloc(&s->medium_list, s->cap / 16 + 2));
     FSIM_TRY(dalloc(&s->heavy_n, 2));
     FSIM_TRY(dalloc(&s->oob, 1));
-    FSIM_TRY(dalloc(&s->mscratch, 2 * 64 + 8));
+    FSIM_TRY(dalloc(&s->mscratch, MC_WORDS));
     FSIM_TRY(dalloc(&s->hole_flag, s->cap));
 
     // host-computed constant tables (libm): deposit footprint and quadrature cosines
@@ -449,6 +525,10 @@ static void free_all(fsim_sim *s)
                     s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf};
     for (void *p : ptrs) cudaFree(p);
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef);
+    cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);
+    if (s->n_pinned) cudaFreeHost(s->n_pinned);
+    for (auto &e : s->n_event)
+        if (e) cudaEventDestroy(e);
     for (auto &kv : s->timers)
         for (auto &pe : kv.second.pending) {
             cudaEventDestroy(pe.first);
@@ -588,7 +668,13 @@ int fsim_create(const fsim_spec *sp, fsim_sim **out)
     if (bad(sp->particle_mass) || sp->particle_mass == 0) return fail(FSIM_ERR_INVALID, ".particle_mass <- must be a finite non-zero number");
     if (bad(sp->particle_charge)) return fail(FSIM_ERR_INVALID, ".particle_charge <- must be a finite number");
     if (sp->precision != FSIM_F64 && sp->precision != FSIM_F32) return fail(FSIM_ERR_INVALID, ".precision <- must be FSIM_F64 or FSIM_F32");
-    if (sp->nparticles_total < 0 || sp->nparticles_total > 0xfffffff0ll) return fail(FSIM_ERR_INVALID, ".nparticles_total <- out of range");
+    // slot indices travel with a flag in bit 31 (perm[], key[]) and particle ids are 32-bit: keep both below 2^31 / 2^32
+    const int64_t n_req = sp->nparticles_total > 0 ? sp->nparticles_total : sp->nparticles * sp->nparticles;
+    const int64_t slots = std::max<int64_t>(n_req, sp->capacity);
+    if (sp->nparticles_total < 0 || sp->capacity < 0 || slots > 0x7fffffffll - 4096)
+        return fail(FSIM_ERR_INVALID, ".nparticles_total <- particle slots per handle must stay below 2^31");
+    if (sp->id_base > 0xffffffffull || sp->id_base + (uint64_t)slots > 0xffffffffull)
+        return fail(FSIM_ERR_INVALID, ".id_base <- id_base + particle slots must stay below 2^32 (ids are 32-bit)");
     if (sp->slab_rows < 0 || sp->slab_row0 < 0 || sp->slab_row0 + sp->slab_rows > sp->nz)
         return fail(FSIM_ERR_INVALID, ".slab_rows <- slab outside the grid");
     if (sp->slab_rows > 0 && sp->halo_rows < FSIM_SHAPE_MID)
@@ -626,7 +712,7 @@ int fsim_set_B(fsim_sim *s, const double *B)
 }
 int fsim_set_position(fsim_sim *s, const double *pos)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     s->binned = false;
     s->keys_valid = false;
     s->have_leavers = false;
@@ -635,7 +721,7 @@ int fsim_set_position(fsim_sim *s, const double *pos)
 }
 int fsim_set_velocity(fsim_sim *s, const double *vel)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     return finish(s, particles_in3(s, vel, AVX, s->factor_r, s->factor_r, s->factor_z, false));
 }
 int fsim_set_sink_mask(fsim_sim *s, const double *mask)
@@ -669,7 +755,7 @@ int fsim_set_entropy(fsim_sim *s, const double *entropy)
 }
 int fsim_set_rand(fsim_sim *s, const double *rnd)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     if (!rnd) return fail(FSIM_ERR_INVALID, "null array");
     if (s->n == 0) return FSIM_OK;
     FSIM_TRY(finish(s, stage_in(s, rnd, sizeof(double) * 4 * s->n)));
@@ -689,7 +775,7 @@ int fsim_set_rand(fsim_sim *s, const double *rnd)
 // from a state no set() call can express (particles that were "just respawned").
 int fsim_set_state(fsim_sim *s, const double *pos4, const double *vel3, const double *rand4)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     if (s->n == 0) return FSIM_OK;
     if (pos4) {
         FSIM_TRY(finish(s, stage_in(s, pos4, sizeof(double) * 4 * s->n)));
@@ -744,6 +830,11 @@ int fsim_set_particle_count(fsim_sim *s, int64_t n)
     FSIM_TRY(check(s));
     if (n < 0 || n > s->cap - 1024) return fail(FSIM_ERR_RANGE, "particle count exceeds capacity");
     s->n = n;
+    if (s->n_async) {  // the device-resident count follows (pageable source: staged before the call returns)
+        const uint32_t n32 = (uint32_t)n;
+        FSIM_CUDA(cudaMemcpyAsync(s->mscratch + MC_NLIVE, &n32, sizeof n32, cudaMemcpyHostToDevice, s->stream));
+        s->n_inflight[0] = s->n_inflight[1] = false;
+    }
     s->binned = false;
     s->keys_valid = false;
     s->have_leavers = false;
@@ -757,7 +848,7 @@ int fsim_set_particle_count(fsim_sim *s, int64_t n)
 }
 int fsim_set_ids(fsim_sim *s, const uint64_t *ids)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     if (!ids) return fail(FSIM_ERR_INVALID, "null array");
     std::vector<uint32_t> tmp((size_t)s->n);
     for (int64_t k = 0; k < s->n; ++k) {
@@ -963,17 +1054,29 @@ int fsim_density_begin(fsim_sim *s)
         FSIM_TRY(finish(s, launch_cellsum_atomic(s)));  // measured alternative, not bit-reproducible
     else
         FSIM_TRY(finish(s, launch_cellsum(s)));
+    if (s->slab) FSIM_TRY(finish(s, launch_halo_pack(s)));  // own boundary rows -> send buffers (the caller's exchange starts here)
     // the deposit is done with the index list; now, every sort_interval frames, put the storage
     // itself into cell order for the pushes that follow
     if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) FSIM_TRY(finish(s, launch_apply_perm(s)));
-    if (s->slab) FSIM_TRY(finish(s, launch_halo_pack(s)));  // own boundary rows -> send buffers
+    s->conv_interior_done = false;
+    return FSIM_OK;
+}
+// slab mode: the stencil on the rows that need no halo row, to run WHILE the halo exchange is in flight
+int fsim_density_interior(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    if (!s->slab) return FSIM_OK;
+    FSIM_TRY(finish(s, launch_conv_rows(s, 1)));
+    s->conv_interior_done = true;
     return FSIM_OK;
 }
 int fsim_density_end(fsim_sim *s)
 {
     FSIM_TRY(check(s));
     if (s->slab) FSIM_TRY(finish(s, launch_halo_unpack(s)));  // neighbours' boundary rows -> halo rows of the sums
-    return finish(s, launch_conv(s));
+    const int part = s->conv_interior_done ? 2 : 0;
+    s->conv_interior_done = false;
+    return finish(s, launch_conv_rows(s, part));
 }
 // device addresses of the per-cell sums (planar, 4 planes of rows x pitch reals) and the per-cell
 // counts -- for a caller that reduces them across ranks between fsim_density_begin and _end
@@ -1011,10 +1114,9 @@ int fsim_render_rgba8(fsim_sim *s, uint8_t *rgba)
     return FSIM_OK;
 }
 
-int fsim_render_rgba8_async(fsim_sim *s, uint8_t *rgba)
+// two device images alternate; the copy of image k (if any) runs on the copy stream under the next frame
+static int canvas_draw(fsim_sim *s, uint8_t *host, bool own_rows_only)
 {
-    FSIM_TRY(check(s));
-    if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
     const size_t bytes = 4 * (size_t)s->ncell_global;
     if (!s->copy_stream) {
         FSIM_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
@@ -1026,15 +1128,38 @@ int fsim_render_rgba8_async(fsim_sim *s, uint8_t *rgba)
     }
     const int k = (s->canvas_slot ^= 1);
     if (s->copy_pending[k]) FSIM_CUDA(cudaEventSynchronize(s->copy_done[k]));  // image k is free again
+    s->copy_pending[k] = false;
     FSIM_TRY(finish(s, launch_render(s, s->canvas_dev[k])));
+    if (!host) return FSIM_OK;
     FSIM_CUDA(cudaEventRecord(s->render_done[k], s->stream));
     FSIM_CUDA(cudaStreamWaitEvent(s->copy_stream, s->render_done[k], 0));
     const size_t off = 4 * (size_t)s->nr * (size_t)(s->nz - s->own0 - s->own_rows);
     const size_t len = 4 * (size_t)s->nr * (size_t)s->own_rows;
-    FSIM_CUDA(cudaMemcpyAsync(rgba + off, s->canvas_dev[k] + off, len, cudaMemcpyDeviceToHost, s->copy_stream));
+    FSIM_CUDA(cudaMemcpyAsync(host + (own_rows_only ? 0 : off), s->canvas_dev[k] + off, len, cudaMemcpyDeviceToHost, s->copy_stream));
     FSIM_CUDA(cudaEventRecord(s->copy_done[k], s->copy_stream));
     s->copy_pending[k] = true;
     return FSIM_OK;
+}
+
+int fsim_render_rgba8_async(fsim_sim *s, uint8_t *rgba)
+{
+    FSIM_TRY(check(s));
+    if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
+    return canvas_draw(s, rgba, false);
+}
+// slab mode: `rows` holds only this rank's rows [own_rows][nr][4] (top row first) -- small enough to pin
+int fsim_render_rows_async(fsim_sim *s, uint8_t *rows)
+{
+    FSIM_TRY(check(s));
+    if (!rows) return fail(FSIM_ERR_INVALID, "null array");
+    return canvas_draw(s, rows, true);
+}
+// the two canvas draws of out.density (programBMag + programDensity, empic.js:1497-1504) into the
+// device-resident canvas, without a read-back: where the reference leaves its canvas, too
+int fsim_draw_canvas(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    return canvas_draw(s, nullptr, false);
 }
 
 int fsim_sync(fsim_sim *s)
@@ -1045,10 +1170,21 @@ int fsim_sync(fsim_sim *s)
         FSIM_CUDA(cudaStreamSynchronize(s->copy_stream));
         s->copy_pending[0] = s->copy_pending[1] = false;
     }
-    uint32_t oob = 0;
-    FSIM_CUDA(cudaMemcpy(&oob, s->oob, sizeof oob, cudaMemcpyDeviceToHost));
+    uint32_t oob = 0, merr = 0;
+    FSIM_CUDA(cudaMemcpyAsync(&oob, s->oob, sizeof oob, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaMemcpyAsync(&merr, s->mscratch + MC_ERR, sizeof merr, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    FSIM_TRY(settle_count(s));
+    if (merr) {
+        FSIM_CUDA(cudaMemsetAsync(s->mscratch + MC_ERR, 0, sizeof merr, s->stream));
+        return fail(FSIM_ERR_RANGE, std::string("slab exchange: ") +
+                    ((merr & MERR_SEND_OVERFLOW) ? "more particles left for one rank in a frame than its send region holds "
+                                                   "(raise the exchange capacity, or use the exact exchange); " : "") +
+                    ((merr & MERR_CAPACITY) ? "arrivals exceed the particle capacity of this rank; " : "") +
+                    "the particle state is no longer valid");
+    }
     if (oob) {
-        cudaMemset(s->oob, 0, sizeof oob);
+        FSIM_CUDA(cudaMemsetAsync(s->oob, 0, sizeof oob, s->stream));  // ordered before the next push by the stream
         char buf[256];
         snprintf(buf, sizeof buf, "%u particle pushes gathered outside the local slab table (halo_rows too small "
                  "or migration overdue)", oob);
@@ -1057,7 +1193,22 @@ int fsim_sync(fsim_sim *s)
     return FSIM_OK;
 }
 
-int64_t fsim_particle_count(const fsim_sim *s) { return s ? s->n : -1; }
+#ifdef FSIM_TUNE
+// tuning build only (make EXTRA=-DFSIM_TUNE; not declared in include/fusionsim.h, not in the product)
+int fsim_tune_set(int push_variant, int conv_variant)
+{
+    fsim::g_push_variant = push_variant;
+    fsim::g_conv_variant = conv_variant;
+    return FSIM_OK;
+}
+#endif
+
+int64_t fsim_particle_count(const fsim_sim *s)
+{
+    if (!s) return -1;
+    if (s->n_async && settle_count(const_cast<fsim_sim *>(s)) != FSIM_OK) return -1;
+    return s->n;
+}
 int64_t fsim_local_cells(const fsim_sim *s) { return s ? s->ncell_local : -1; }
 int64_t fsim_launch_count(const fsim_sim *s) { return s ? s->launches : -1; }
 
@@ -1083,22 +1234,22 @@ static int part_out(fsim_sim *s, double *out, int width, int a0, bool with_alive
 
 int fsim_get_position(fsim_sim *s, double *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     return finish(s, part_out(s, out, 4, AX, true));
 }
 int fsim_get_velocity(fsim_sim *s, double *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     return finish(s, part_out(s, out, 3, AVX, false));
 }
 int fsim_get_rand(fsim_sim *s, double *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     return finish(s, part_out(s, out, 4, AQ0, false));
 }
 int fsim_get_ids(fsim_sim *s, uint64_t *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     std::vector<uint32_t> tmp((size_t)s->n);
     FSIM_CUDA(cudaMemcpyAsync(tmp.data(), s->pid[s->cur], sizeof(uint32_t) * s->n, cudaMemcpyDeviceToHost, s->stream));
@@ -1108,7 +1259,7 @@ int fsim_get_ids(fsim_sim *s, uint64_t *out)
 }
 int fsim_get_cells(fsim_sim *s, int64_t *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_n(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     if (s->n == 0) return FSIM_OK;
     FSIM_TRY(finish(s, ensure_stage(s, sizeof(int64_t) * s->n)));
@@ -1130,6 +1281,7 @@ int fsim_get_field(fsim_sim *s, const char *name, double *out)
 {
     FSIM_TRY(check(s));
     if (!name) return fail(FSIM_ERR_INVALID, "null field name");
+    if (!out) return fail(FSIM_ERR_INVALID, "null array");
     const std::string n(name);
     const int64_t nc = s->ncell_local;
     if (n == "E") return finish(s, table_out(s, s->E, out, 3 * nc));
@@ -1172,8 +1324,48 @@ int fsim_get_sink_mask(fsim_sim *s, uint8_t *out)
 {
     FSIM_TRY(check(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
-    FSIM_CUDA(cudaMemcpyAsync(out, s->sink, (size_t)s->ncell_global, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_TRY(finish(s, ensure_stage(s, (size_t)s->ncell_global)));
+    sink_out_kernel<<<grid_for(s->ncell_global, 256), 256, 0, s->stream>>>(s->sink, (uint8_t *)s->stage, s->ncell_global);
+    FSIM_CUDA(cudaGetLastError());
+    s->launches++;
+    return finish(s, stage_out(s, out, (size_t)s->ncell_global));
+}
+
+// Invariants of a run, reduced on the device (extension; bench.py prints them with every line):
+// out[0] live particles, out[1] XOR of their ids, out[2] sum of their ids (mod 2^64), out[3] particles the
+// last density() deposited on the owned rows; *sum_alpha = sum of the weight channel of the per-cell sums
+// over the owned rows (= 0.001 * out[3] up to rounding).  Over all ranks of a slab run the first three
+// must equal those of ids 0..N-1: no particle lost or duplicated by the migration.
+int fsim_check_digest(fsim_sim *s, uint64_t *out, double *sum_alpha)
+{
+    FSIM_TRY(check_n(s));
+    if (!out) return fail(FSIM_ERR_INVALID, "null array");
+    constexpr int NB = 256;
+    FSIM_TRY(finish(s, ensure_stage(s, 4 * sizeof(unsigned long long) + NB * sizeof(double))));
+    unsigned long long *d = (unsigned long long *)s->stage;
+    double *partial = (double *)(d + 4);
+    FSIM_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long) + NB * sizeof(double), s->stream));
+    if (s->n) digest_ids_kernel<<<s->nsm * 4, 256, 0, s->stream>>>(s->pid[s->cur], s->n, nullptr, d);
+    const int lo = s->own0 - s->row0;
+    FSIM_TRY(finish(s, dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        digest_cells_kernel<Real><<<NB, 256, 0, s->stream>>>(s->cellcount, (const Real *)s->cellsum + 3 * s->plane, s->nr,
+                                                              s->pitch, lo, s->own_rows, d, partial);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches += 2;
+        return (int)FSIM_OK;
+    })));
+    unsigned long long hd[4];
+    double hp[NB];
+    FSIM_CUDA(cudaMemcpyAsync(hd, d, sizeof hd, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaMemcpyAsync(hp, partial, sizeof hp, cudaMemcpyDeviceToHost, s->stream));
     FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    out[0] = (uint64_t)s->n; out[1] = hd[0]; out[2] = hd[1]; out[3] = hd[2];
+    if (sum_alpha) {
+        double t = 0.0;
+        for (int k = 0; k < NB; ++k) t += hp[k];
+        *sum_alpha = t;
+    }
     return FSIM_OK;
 }
 

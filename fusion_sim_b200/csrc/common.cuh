@@ -3,9 +3,9 @@
 // The engine behind the C ABI of include/fusionsim.h.  Data layout in HBM:
 //   particles : structure of arrays, 10 reals + 1 alive byte + 1 u32 id per particle,
 //               two copies (the counting sort is out of place);
-//   cell table: array of 12-real records R1.xyz R2.xyz R3.xyz A.xyz, index i + j*nr
+//   cell table: array of 8-real records B.xyz f one_m A.xyz (below), index i + j*nr
 //               (empic.js:1162), rows [row0, row0+rows) of the global grid;
-//   sink mask : 1 byte per GLOBAL cell; entropy 1024^2 x 4 reals; inv_cdf 512^2 x 2 reals.
+//   sink mask : 1 BIT per GLOBAL cell; entropy 1024^2 x 4 reals; inv_cdf 512^2 x 2 reals.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -28,6 +28,41 @@ constexpr int NPART_ARRAYS = 10;  // x y z vx vy vz q0 q1 q2 q3
 // ~33 cheap fp64 operations instead of gathering 96 bytes: the gather, not the fp64 pipe, is what
 // limits the step kernel on B200.  Same expressions, same order => same bits as a stored table.
 constexpr int RECSTRIDE = 8;
+
+// ---- multi-GPU slab exchange (migrate.cu) ---------------------------------------------------------
+constexpr int MAX_RANKS = 64;
+// words of the small device counter block fsim_sim::mscratch
+enum {
+    MC_NLEAVERS = 0,  // length of the leaver list the push (or find_leavers) wrote into perm[]
+    MC_NHOLES,        // slots vacated by packed leavers (list in MigratePlan::holes / perm[])
+    MC_NTARGETS, MC_NSOURCES,  // compaction lists
+    MC_NRECV,         // arrivals of this frame (sum of the received region headers)
+    MC_NOLD, MC_NNEW, // live slots before / after this frame's migration
+    MC_ERR,           // sticky error bits MERR_* (read by fsim_sync)
+    MC_SENT_LO, MC_SENT_HI,  // 64-bit running total of packed records (statistics)
+    MC_NLIVE,         // device-resident particle count (asynchronous exchange: fsim_sim::n is an upper bound)
+    MC_CURSOR = 16,                        // [MAX_RANKS] records packed for each destination
+    MC_PREFIX = MC_CURSOR + MAX_RANKS,     // [MAX_RANKS + 1] exclusive prefix of the received counts
+    MC_COUNTS = MC_PREFIX + MAX_RANKS + 1, // [MAX_RANKS] destination counts (exact exchange)
+    MC_WORDS = MC_COUNTS + MAX_RANKS
+};
+constexpr uint32_t MERR_SEND_OVERFLOW = 1u;  // more leavers for one destination than its send region holds
+constexpr uint32_t MERR_CAPACITY = 2u;       // arrivals exceed the particle capacity of this rank
+constexpr int MIGRATE_HEADER_BYTES = 16;     // every exchange region starts with its record count (u32) + padding
+
+// Fixed-capacity exchange plan (fsim_migrate_setup): region k of the send buffer goes to rank k, region k
+// of the receive buffer comes from rank k; sizes are known to the host of both sides, the record counts
+// travel in the region headers -- no host round trip in the frame.
+struct MigratePlan {
+    int nranks = 0, self = 0;
+    int lo[MAX_RANKS + 1] = {};            // rank k owns rows [lo[k], lo[k+1])
+    uint32_t send_cap[MAX_RANKS] = {}, recv_cap[MAX_RANKS] = {};  // records
+    uint64_t send_off[MAX_RANKS + 1] = {}, recv_off[MAX_RANKS + 1] = {};  // byte offsets of the regions
+    uint32_t recv_slot0[MAX_RANKS + 1] = {};  // exclusive prefix of recv_cap (thread -> region mapping)
+    uint32_t send_total = 0, recv_total = 0;  // sums of the capacities
+    unsigned char *send = nullptr, *recv = nullptr;
+    uint32_t *holes = nullptr, *targets = nullptr, *sources = nullptr;  // [send_total] each
+};
 enum { REC_BX = 0, REC_BY, REC_BZ, REC_F, REC_ONEM, REC_AX, REC_AY, REC_AZ };
 enum { AX = 0, AY, AZ, AVX, AVY, AVZ, AQ0, AQ1, AQ2, AQ3 };
 
@@ -108,9 +143,9 @@ struct fsim_sim {
     int steps_since_sort = 0;     // step() calls since the last physical sort
 
     // tables
-    void *cellrec = nullptr;   // [ncell_local][12]
+    void *cellrec = nullptr;   // [ncell_local][RECSTRIDE]
     void *E = nullptr, *B = nullptr;  // [ncell_local][3]
-    uint8_t *sink = nullptr;   // [ncell_global]
+    uint32_t *sink = nullptr;  // [(ncell_global + 31) / 32] bit c = 1: cell c keeps the particle (sink_mask.r > 0.5)
     void *entropy = nullptr;   // [1024*1024][4]
     void *invcdf = nullptr;    // [512*512][2]
     bool have_precalc = false;
@@ -138,10 +173,18 @@ struct fsim_sim {
     size_t stage_bytes = 0;
     void *migr = nullptr;          // packed migration records (send side)
     size_t migr_bytes = 0;
-    uint32_t *mscratch = nullptr;  // small counters of the migration kernels
+    uint32_t *mscratch = nullptr;  // [MC_WORDS] small counters of the migration kernels (enum MC_*)
     uint8_t *hole_flag = nullptr;  // [cap] 1 = slot vacated by a leaver
     uint32_t nholes_host = 0;
+    fsim::MigratePlan plan;        // asynchronous fixed-capacity exchange (fsim_migrate_setup)
+    bool n_async = false;          // the exact particle count lives in mscratch[MC_NLIVE]; `n` is an upper bound
+    uint32_t *n_pinned = nullptr;  // [2] pinned host copies of MC_NLIVE, read back without waiting
+    cudaEvent_t n_event[2] = {};
+    int64_t n_pending_bound[2] = {};  // arrivals that may have been added after read-back k was taken
+    bool n_inflight[2] = {false, false};
+    int n_slot = 0;
     void *halo_buf = nullptr;      // slab mode: [send_lo | send_hi | recv_lo | recv_hi], each 4 x 5 x nr reals
+    bool conv_interior_done = false;  // fsim_density_interior ran: fsim_density_end convolves only the boundary tiles
     bool have_leavers = false;     // perm[0..*nleavers) lists the slots whose row left the slab (emitted by the push)
 
     // measurement
@@ -278,7 +321,19 @@ __device__ __forceinline__ void warp_runs(uint32_t key, int lane, int &leader, u
     rank = (uint32_t)(lane - leader);
 }
 
+#ifdef FSIM_TUNE
+extern int g_push_variant, g_conv_variant;  // tuning build only (fsim_tune_set)
+#endif
+
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// exact particle count inside a kernel: the device word when the exchange is asynchronous, else the host's n
+__device__ __forceinline__ int64_t live_count(const uint32_t *n_dev, int64_t n_host)
+{
+    if (!n_dev) return n_host;
+    const int64_t d = (int64_t)*n_dev;
+    return d < n_host ? d : n_host;
+}
 
 // kernels / host stages implemented in the other translation units
 int launch_push(fsim_sim *s, bool with_hist, int nhalf);  // nhalf half-steps in one sweep
@@ -287,10 +342,12 @@ int launch_bin(fsim_sim *s);       // scan + index scatter -> starts[], perm[]
 int launch_apply_perm(fsim_sim *s);  // physical re-sort: storage <- storage[perm]
 int launch_cellsum(fsim_sim *s);
 int launch_cellsum_atomic(fsim_sim *s);
-int launch_conv(fsim_sim *s);
 int make_sums_tensor_map(fsim_sim *s, int box_rows);
 int launch_halo_pack(fsim_sim *s);
 int launch_halo_unpack(fsim_sim *s);
+int launch_conv_rows(fsim_sim *s, int part);  // part 0: all owned rows, 1: rows that need no halo, 2: the rest
+int settle_count(fsim_sim *s);               // asynchronous exchange: make fsim_sim::n exact again (synchronises)
+int check_handle(fsim_sim *s);               // sticky-error / device check of every entry point
 int launch_precalc(fsim_sim *s);
 int launch_expand_records(fsim_sim *s, double *dev_out);  // [cells][12] R1 R2 R3 A as doubles
 int launch_add_loop(fsim_sim *s, double R, double Z, double I);

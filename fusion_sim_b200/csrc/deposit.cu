@@ -14,12 +14,15 @@
 //             (empic.js:1053-1056), programAvgMoments (avg_frag :274-277, ratio :1083) and the
 //             avgA -> avgB copy (:1490-1495).
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "sortnet.cuh"
 
 namespace fsim {
+
+#ifdef FSIM_TUNE
+int g_conv_variant = 0;
+#endif
 
 constexpr int THREAD_CELL_MAX = 16;   // up to here: one thread per cell, (id, slot) pairs sorted in registers
 constexpr int WARP_CELL_MAX = 256;    // up to here: one warp per cell; larger cells: one block per cell
@@ -330,7 +333,7 @@ int launch_cellsum(fsim_sim *s)
 // are formed once per window (18 adds per column offset for 8 outputs) and shared, ~82 fp64
 // operations per cell and channel instead of 107 (162 without the symmetry); the 40 taps that are
 // exactly zero are removed at compile time.  With the two IEEE divisions of the normalisation the
-// kernel is bound by the fp64 pipe.  Measured on B200 at C5 fp64 (FSIM_CONV_VARIANT, tools/tune.py): 8-row strips on
+// kernel is bound by the fp64 pipe.  Measured on B200 at C5 fp64 (tuning build, tools/tune.py): 8-row strips on
 // 32 x 8 tiles 0.65 ms, 8-row strips on 32 x 16 tiles 0.69, 4-row strips on 32 x 16 tiles 0.86,
 // 16-row strips 0.88-0.90, 2-row strips 1.50 -- longer strips need fewer shared-memory loads per
 // output, small tiles put more blocks on an SM to hide the single TMA wait of each.
@@ -339,7 +342,7 @@ constexpr int CH = FSIM_SHAPE_MID;              // halo = 5
 // TMA needs the box START (innermost coordinate x element size) 16-byte aligned, and the box width
 // a multiple of 16 bytes: the box therefore begins CXOFF >= 5 cells left of the tile, CXOFF a
 // multiple of 2 reals (fp64) / 4 reals (fp32), and is CBOXW >= CXOFF + 32 + 5 wide.  (A start at
-// -5 cells is an "illegal instruction" fault: measured, tools/scratch/tma_test2.cu.)
+// -5 cells is an "illegal instruction" fault: measured on B200.)
 template <typename Real> struct ConvBox;
 template <> struct ConvBox<double> { static constexpr int XOFF = 6, W = 44; };
 template <> struct ConvBox<float> { static constexpr int XOFF = 8, W = 48; };
@@ -364,6 +367,8 @@ struct ConvArgs {
     int nr, pitch;
     int64_t plane;
     int j0, j1;               // output rows [j0, j1) (owned rows, local index)
+    int tile0;                // first tile row of this launch (blockIdx.y + tile0)
+    int skip0, skip1;         // tile rows [skip0, skip1) are left out (boundary-only launch); empty when skip0 >= skip1
 };
 
 // CSTRIP = output rows per thread (window of CSTRIP + 10 values per column offset), CT_J = tile height
@@ -376,7 +381,9 @@ conv_kernel(const __grid_constant__ CUtensorMap tmS, const ConvArgs<Real> a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Real *sm = reinterpret_cast<Real *>(smem_raw);  // [4][CS_J][CBOXW], written by the TMA unit
     __shared__ __align__(8) unsigned long long bar;
-    const int i0 = blockIdx.x * CT_I, jb = a.j0 + blockIdx.y * CT_J;
+    int ty = (int)blockIdx.y + a.tile0;
+    if (ty >= a.skip0) ty += a.skip1 - a.skip0;  // boundary launch: jump over the interior tile rows
+    const int i0 = blockIdx.x * CT_I, jb = a.j0 + ty * CT_J;
     const int tid = threadIdx.x;
     constexpr uint32_t kBytes = 4u * CS_J * CBOXW * sizeof(Real);
     if (tid == 0) {
@@ -509,8 +516,11 @@ int upload_shape(const double *shape64, const double *shape32)
     return FSIM_OK;
 }
 
+// part 0: every tile row; 1: the tile rows whose 5-row halo lies inside the owned rows (no received halo row
+// is read); 2: the others (first tile row, last one or two).  Parts 1 and 2 are disjoint and cover part 0:
+// the running average is updated in place, so every cell must be visited exactly once per density().
 template <typename Real, int CSTRIP, int CT_J>
-static int conv_launch(fsim_sim *s, const ConvArgs<Real> &a)
+static int conv_launch(fsim_sim *s, ConvArgs<Real> a, int part)
 {
     constexpr int CS_J = CT_J + 2 * CH;
     if (s->tm_sums_rows != CS_J) FSIM_TRY(make_sums_tensor_map(s, CS_J));  // the box height is part of the map
@@ -522,13 +532,22 @@ static int conv_launch(fsim_sim *s, const ConvArgs<Real> &a)
         s->smem_opt_in |= bit;
     }
     dim3 block(CT_J / CSTRIP * 4 * 32);
-    dim3 grid((s->nr + CT_I - 1) / CT_I, (s->own_rows + CT_J - 1) / CT_J);
+    const int ntile = (s->own_rows + CT_J - 1) / CT_J;
+    // tile row t reads sums rows [t*CT_J - 5, t*CT_J + CT_J + 5) of the owned block: interior if that stays inside it
+    const int in0 = std::min(ntile, (CH + CT_J - 1) / CT_J);
+    const int in1 = std::max(in0, (s->own_rows - CH) / CT_J);  // tiles t < in1 end at (t+1)*CT_J <= own_rows - 5
+    a.tile0 = 0; a.skip0 = a.skip1 = 1 << 30;
+    int rows_of_tiles = ntile;
+    if (part == 1) { a.tile0 = in0; rows_of_tiles = in1 - in0; }
+    if (part == 2) { a.skip0 = in0; a.skip1 = in1; rows_of_tiles = ntile - (in1 - in0); }
+    if (rows_of_tiles <= 0) return FSIM_OK;
+    dim3 grid((s->nr + CT_I - 1) / CT_I, rows_of_tiles);
     conv_kernel<Real, CSTRIP, CT_J><<<grid, block, smem, s->stream>>>(*reinterpret_cast<const CUtensorMap *>(s->tm_sums), a);
     FSIM_CUDA(cudaGetLastError());
     return FSIM_OK;
 }
 
-int launch_conv(fsim_sim *s)
+int launch_conv_rows(fsim_sim *s, int part)
 {
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
@@ -537,17 +556,19 @@ int launch_conv(fsim_sim *s)
         a.nr = s->nr; a.pitch = s->pitch; a.plane = s->plane;
         a.j0 = s->own0 - s->row0; a.j1 = a.j0 + s->own_rows;
         Bracket b(s, "conv");
-        const char *e = getenv("FSIM_CONV_VARIANT");  // tuning (tools/tune.py); default measured fastest on B200
-        switch (e ? atoi(e) : 0) {
-        case 1: return conv_launch<Real, 8, 16>(s, a);
-        case 2: return conv_launch<Real, 8, 32>(s, a);
-        case 3: return conv_launch<Real, 4, 32>(s, a);
-        case 4: return conv_launch<Real, 2, 16>(s, a);
-        case 5: return conv_launch<Real, 16, 16>(s, a);
-        case 6: return conv_launch<Real, 16, 32>(s, a);
-        case 8: return conv_launch<Real, 4, 16>(s, a);
-        default: return conv_launch<Real, 8, 8>(s, a);  // 0.65 ms at C5 fp64 against 0.86 for <4,16>, 0.69 <8,16>, 0.88 <16,32>
+#ifdef FSIM_TUNE
+        switch (g_conv_variant) {  // tuning build only (tools/tune.py)
+        case 1: return conv_launch<Real, 8, 16>(s, a, part);
+        case 2: return conv_launch<Real, 8, 32>(s, a, part);
+        case 3: return conv_launch<Real, 4, 32>(s, a, part);
+        case 4: return conv_launch<Real, 2, 16>(s, a, part);
+        case 5: return conv_launch<Real, 16, 16>(s, a, part);
+        case 6: return conv_launch<Real, 16, 32>(s, a, part);
+        case 8: return conv_launch<Real, 4, 16>(s, a, part);
+        default: break;
         }
+#endif
+        return conv_launch<Real, 8, 8>(s, a, part);  // 0.65 ms at C5 fp64 against 0.86 for <4,16>, 0.69 <8,16>, 0.88 <16,32>
     });
 }
 

@@ -375,9 +375,12 @@ int fsim_jacobi_solve(fsim_jacobi *j, double tolerance, int32_t substep, int32_t
     int it = 0;
     const int sub_n = substep > 0 ? substep : 1;  // params.substep || 1
     const bool literal = (j->flags & FSIM_JACOBI_LITERAL) != 0;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
+    struct EventPair {  // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+        ~EventPair() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    } ev;
+    const cudaEvent_t e0 = ev.a, e1 = ev.b;
     while (it < max_iterations && diff > tolerance) {
         for (int s = 0; s < sub_n; ++s) {
             // programSet: x_guess <- x_result (:649-652), then x_result <- R x_guess + C (:655)
@@ -418,8 +421,6 @@ int fsim_jacobi_solve(fsim_jacobi *j, double tolerance, int32_t substep, int32_t
         diff = 2 * Ld * max_diff / (fabs(x1) + fabs(x2));                                    // :687
         it++;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (correlation) *correlation = corr;
     if (diff_out) *diff_out = diff;
     if (iterations) *iterations = it;

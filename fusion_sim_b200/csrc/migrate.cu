@@ -16,8 +16,6 @@
 
 namespace fsim {
 
-constexpr int MAX_RANKS = 64;
-
 struct RankBounds {
     int n;
     int self;
@@ -36,11 +34,11 @@ __device__ __forceinline__ int dest_rank(const RankBounds &rb, Real z, int nz)
 // fallback when the push did not emit the list: scan all particles for rows that are not owned
 template <typename Real>
 __global__ void __launch_bounds__(256)
-find_leavers_kernel(const Real *__restrict__ z, int64_t n, int nz, int own0, int own_rows,
-                    uint32_t *__restrict__ list, uint32_t *__restrict__ nlist)
+find_leavers_kernel(const Real *__restrict__ z, int64_t n, const uint32_t *__restrict__ n_dev, int nz, int own0,
+                    int own_rows, uint32_t *__restrict__ list, uint32_t *__restrict__ nlist)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    if (p >= live_count(n_dev, n)) return;
     const int gj = tex_idx(z[p], nz);
     if (gj < own0 || gj >= own0 + own_rows) list[atomicAdd(nlist, 1u)] = (uint32_t)p;
 }
@@ -190,6 +188,214 @@ __global__ void __launch_bounds__(256) compact_move_kernel(const MoveArgs<Real> 
     }
 }
 
+
+// ---- asynchronous fixed-capacity exchange: every count stays on the device ----------------------------
+struct PlanDev {  // the part of MigratePlan the kernels need (by value: ~1.3 KB of kernel parameters)
+    int nranks, self;
+    int lo[MAX_RANKS + 1];
+    uint32_t send_cap[MAX_RANKS], recv_cap[MAX_RANKS], recv_slot0[MAX_RANKS + 1];
+    uint64_t send_off[MAX_RANKS], recv_off[MAX_RANKS];
+};
+
+template <typename Real>
+__device__ __forceinline__ int dest_rank_plan(const PlanDev &pl, Real z, int nz)
+{
+    const int row = tex_idx(z, nz);
+    int d = 0;
+    while (d + 1 < pl.nranks && row >= pl.lo[d + 1]) ++d;
+    return d;
+}
+
+template <typename Real>
+struct PackFixedArgs {
+    const Real *src[NPART_ARRAYS];
+    const uint8_t *alive;
+    const uint32_t *id;
+    unsigned char *send;     // regions of PlanDev::send_off, each: 16-byte header + records
+    const uint32_t *list;    // leaver list (perm[]), length ctr[MC_NLEAVERS]
+    uint32_t *holes;         // packed leavers' slots
+    uint8_t *hole_flag;
+    uint32_t *ctr;           // mscratch
+    const uint32_t *key;     // non-null: keep the sort histogram consistent
+    uint32_t *counts;
+    int nz;
+};
+
+// grid-stride over the leaver list whose length is read on the device
+template <typename Real>
+__global__ void __launch_bounds__(256) migrate_pack_fixed_kernel(const PackFixedArgs<Real> a, const PlanDev pl)
+{
+    constexpr size_t REC = NPART_ARRAYS * sizeof(Real) + 8;
+    const uint32_t nlist = a.ctr[MC_NLEAVERS];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nlist; t += gridDim.x * blockDim.x) {
+        const size_t p = a.list[t];
+        const int d = dest_rank_plan(pl, a.src[AZ][p], a.nz);
+        const uint32_t slot = atomicAdd(a.ctr + MC_CURSOR + d, 1u);
+        if (d == pl.self || slot >= pl.send_cap[d]) {  // region full: the particle stays, the run is flagged invalid
+            atomicOr(a.ctr + MC_ERR, MERR_SEND_OVERFLOW);
+            continue;
+        }
+        unsigned char *rec = a.send + pl.send_off[d] + MIGRATE_HEADER_BYTES + (size_t)slot * REC;
+        Real *r = reinterpret_cast<Real *>(rec);
+#pragma unroll
+        for (int k = 0; k < NPART_ARRAYS; ++k) r[k] = a.src[k][p];
+        uint32_t *u = reinterpret_cast<uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
+        u[0] = a.id[p];
+        u[1] = a.alive[p];
+        a.holes[atomicAdd(a.ctr + MC_NHOLES, 1u)] = (uint32_t)p;
+        a.hole_flag[p] = 1;
+        if (a.key) atomicSub(a.counts + (a.key[p] & KEY_MASK), 1u);
+    }
+}
+
+// one block: record counts into the send headers, statistics
+__global__ void __launch_bounds__(64) migrate_send_headers_kernel(unsigned char *send, uint32_t *ctr, const PlanDev pl)
+{
+    const int d = threadIdx.x;
+    uint32_t c = 0;
+    if (d < pl.nranks) {
+        c = min(ctr[MC_CURSOR + d], pl.send_cap[d]);
+        if (d == pl.self) c = 0;
+        uint32_t *h = reinterpret_cast<uint32_t *>(send + pl.send_off[d]);
+        h[0] = c; h[1] = 0; h[2] = 0; h[3] = 0;
+    }
+    // total packed (64-bit counter in two words; single block, so a plain read-modify-write)
+    uint32_t tot = c;
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __shared__ uint32_t part[2];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t old = ((uint64_t)ctr[MC_SENT_HI] << 32) | ctr[MC_SENT_LO];
+        const uint64_t now = old + part[0] + part[1];
+        ctr[MC_SENT_LO] = (uint32_t)now;
+        ctr[MC_SENT_HI] = (uint32_t)(now >> 32);
+    }
+}
+
+// one block: prefix of the received counts, new particle count, capacity check
+__global__ void __launch_bounds__(64)
+migrate_recv_headers_kernel(const unsigned char *recv, uint32_t *ctr, const PlanDev pl, uint32_t max_live)
+{
+    if (threadIdx.x != 0) return;
+    uint32_t run = 0;
+    for (int k = 0; k < pl.nranks; ++k) {
+        ctr[MC_PREFIX + k] = run;
+        uint32_t c = (k == pl.self) ? 0u : reinterpret_cast<const uint32_t *>(recv + pl.recv_off[k])[0];
+        run += min(c, pl.recv_cap[k]);
+    }
+    ctr[MC_PREFIX + pl.nranks] = run;
+    const uint32_t n_old = ctr[MC_NLIVE], nholes = ctr[MC_NHOLES];
+    uint32_t nrecv = run;
+    if ((uint64_t)n_old - nholes + nrecv > max_live) {  // does not fit: drop the excess, flag the run invalid
+        atomicOr(ctr + MC_ERR, MERR_CAPACITY);
+        nrecv = max_live - (n_old - nholes);
+    }
+    ctr[MC_NRECV] = nrecv;
+    ctr[MC_NOLD] = n_old;
+    ctr[MC_NNEW] = n_old - nholes + nrecv;
+    ctr[MC_NTARGETS] = 0;
+    ctr[MC_NSOURCES] = 0;
+}
+
+template <typename Real>
+struct UnpackFixedArgs {
+    Real *dst[NPART_ARRAYS];
+    uint8_t *alive;
+    uint32_t *id;
+    const unsigned char *recv;
+    const uint32_t *holes;
+    uint8_t *hole_flag;
+    const uint32_t *ctr;
+    uint32_t *key, *counts;  // non-null key: arrivals get their deposit prepass here
+    Real *dcol[2];
+    int nr, nz, row0, rows, own_lo, own_hi;
+};
+
+// one thread per receive SLOT (sum of the capacities, known to the host); arrival i goes into hole i
+// while holes last, then to the end of the storage
+template <typename Real>
+__global__ void __launch_bounds__(256) migrate_unpack_fixed_kernel(const UnpackFixedArgs<Real> a, const PlanDev pl)
+{
+    constexpr size_t REC = NPART_ARRAYS * sizeof(Real) + 8;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pl.recv_slot0[pl.nranks]) return;
+    int k = 0;
+    while (t >= pl.recv_slot0[k + 1]) ++k;
+    const uint32_t j = t - pl.recv_slot0[k];
+    if (j >= a.ctr[MC_PREFIX + k + 1] - a.ctr[MC_PREFIX + k]) return;
+    const uint32_t i = a.ctr[MC_PREFIX + k] + j;
+    if (i >= a.ctr[MC_NRECV]) return;  // capacity overflow (flagged)
+    const uint32_t nholes = a.ctr[MC_NHOLES];
+    size_t slot;
+    if (i < nholes) {
+        slot = a.holes[i];
+        a.hole_flag[slot] = 0;
+    } else {
+        slot = (size_t)a.ctr[MC_NOLD] + (i - nholes);
+    }
+    const unsigned char *rec = a.recv + pl.recv_off[k] + MIGRATE_HEADER_BYTES + (size_t)j * REC;
+    const Real *r = reinterpret_cast<const Real *>(rec);
+    Real v[NPART_ARRAYS];
+#pragma unroll
+    for (int q = 0; q < NPART_ARRAYS; ++q) {
+        v[q] = r[q];
+        a.dst[q][slot] = v[q];
+    }
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
+    a.id[slot] = u[0];
+    a.alive[slot] = (uint8_t)u[1];
+    if (a.key) {
+        const Real rr = fsqrt(v[AX] * v[AX] + v[AY] * v[AY]);
+        Real c0, c1, c2;
+        const uint32_t key = sprite_key_colour<Real>(v[AX], v[AY], v[AZ], rr, v[AVX], v[AVY], v[AVZ], a.nr, a.nz,
+                                                     a.row0, a.rows, a.own_lo, a.own_hi, c0, c1, c2);
+        a.key[slot] = key;
+        a.dcol[0][slot] = c0; a.dcol[1][slot] = c1;
+        (void)c2;
+        atomicAdd(a.counts + (key & KEY_MASK), 1u);
+    }
+}
+
+// more leavers than arrivals: the storage shrinks to n_new; one thread per possible hole
+__global__ void __launch_bounds__(256)
+compact_lists_fixed_kernel(const uint32_t *__restrict__ holes, const uint8_t *__restrict__ hole_flag, uint32_t *ctr,
+                           uint32_t *__restrict__ targets, uint32_t *__restrict__ sources, uint32_t span_max)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nholes = ctr[MC_NHOLES], nrecv = ctr[MC_NRECV];
+    if (nholes <= nrecv || t >= span_max) return;
+    const int64_t n_new = ctr[MC_NNEW], n_old = ctr[MC_NOLD];
+    if (t < nholes - nrecv) {
+        const uint32_t slot = holes[nrecv + t];
+        if ((int64_t)slot < n_new) targets[atomicAdd(ctr + MC_NTARGETS, 1u)] = slot;
+    }
+    const int64_t q = n_new + t;
+    if (q < n_old && !hole_flag[q]) sources[atomicAdd(ctr + MC_NSOURCES, 1u)] = (uint32_t)q;
+}
+
+// clear the flags of the vacated slots, publish the new count, reset the per-frame counters
+__global__ void __launch_bounds__(256)
+migrate_finish_kernel(const uint32_t *__restrict__ holes, uint8_t *__restrict__ hole_flag, uint32_t *ctr, uint32_t span_max)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ctr[MC_NHOLES] && t < span_max) hole_flag[holes[t]] = 0;
+}
+__global__ void migrate_publish_kernel(uint32_t *ctr, int nranks)
+{
+    if (threadIdx.x == 0) {
+        ctr[MC_NLIVE] = ctr[MC_NNEW];
+        ctr[MC_NHOLES] = 0;
+        ctr[MC_NLEAVERS] = 0;
+    }
+    if ((int)threadIdx.x < nranks) ctr[MC_CURSOR + threadIdx.x] = 0;
+}
+
+__global__ void set_words_kernel(uint32_t *p, uint32_t v, int n)
+{
+    if ((int)threadIdx.x < n) p[threadIdx.x] = v;
+}
+
 static int ensure_migr(fsim_sim *s, size_t bytes)
 {
     if (bytes <= s->migr_bytes) return FSIM_OK;
@@ -225,16 +431,19 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
         set_error("fsim_migrate_pack: row_bounds[self] does not match the slab of this handle");
         return FSIM_ERR_INVALID;
     }
-    FSIM_CUDA(cudaSetDevice(s->device));
+    FSIM_TRY(check_handle(s));
+    if (s->n_async) {
+        set_error("fsim_migrate_pack: this handle uses the asynchronous exchange (fsim_migrate_setup)");
+        return FSIM_ERR_STATE;
+    }
     RankBounds rb;
     rb.n = nranks;
     rb.self = self;
     for (int k = 0; k <= nranks; ++k) rb.lo[k] = (int)row_bounds[k];
-    // scratch: counts[MAX_RANKS] | cursor[MAX_RANKS] | nleavers | ntargets | nsources
-    uint32_t *scr = s->mscratch;
-    uint32_t *nlist_d = scr + 2 * MAX_RANKS;
-    FSIM_CUDA(cudaMemsetAsync(scr, 0, sizeof(uint32_t) * 2 * MAX_RANKS, s->stream));
-    FSIM_CUDA(cudaMemsetAsync(scr + 2 * MAX_RANKS + 1, 0, sizeof(uint32_t) * 2, s->stream));
+    uint32_t *scr = s->mscratch;  // layout: enum MC_* (common.cuh)
+    uint32_t *nlist_d = scr + MC_NLEAVERS;
+    FSIM_CUDA(cudaMemsetAsync(scr + MC_CURSOR, 0, sizeof(uint32_t) * (MC_WORDS - MC_CURSOR), s->stream));
+    FSIM_CUDA(cudaMemsetAsync(scr + MC_NTARGETS, 0, sizeof(uint32_t) * 2, s->stream));
     for (int k = 0; k < nranks; ++k) send_counts[k] = 0;
     *send_buf_dev = nullptr;
     s->nholes_host = 0;
@@ -247,24 +456,24 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
         if (!s->have_leavers) {  // the push did not emit the list: scan the positions
             FSIM_CUDA(cudaMemsetAsync(nlist_d, 0, sizeof(uint32_t), s->stream));
             find_leavers_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
-                (const Real *)s->part[c][AZ], s->n, s->nz, s->own0, s->own_rows, s->perm, nlist_d);
+                (const Real *)s->part[c][AZ], s->n, nullptr, s->nz, s->own0, s->own_rows, s->perm, nlist_d);
             FSIM_CUDA(cudaGetLastError());
             s->launches++;
         }
         s->have_leavers = false;
         // destination counts of the leavers and the list length: ONE read-back per frame
         migrate_count_kernel<Real><<<s->nsm * 2, 256, 0, s->stream>>>((const Real *)s->part[c][AZ], s->perm, nlist_d, s->nz, rb,
-                                                                   scr);
+                                                                   scr + MC_COUNTS);
         FSIM_CUDA(cudaGetLastError());
         s->launches++;
         uint32_t nlist = 0;
         uint32_t hc[MAX_RANKS] = {}, off[MAX_RANKS] = {};
         FSIM_CUDA(cudaMemcpyAsync(&nlist, nlist_d, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-        FSIM_CUDA(cudaMemcpyAsync(hc, scr, sizeof(uint32_t) * nranks, cudaMemcpyDeviceToHost, s->stream));
+        FSIM_CUDA(cudaMemcpyAsync(hc, scr + MC_COUNTS, sizeof(uint32_t) * nranks, cudaMemcpyDeviceToHost, s->stream));
         FSIM_CUDA(cudaStreamSynchronize(s->stream));
         if (nlist == 0) return (int)FSIM_OK;
-        if ((int64_t)nlist > s->cap / 2) {
-            set_error("fsim_migrate_pack: more than half of the particle slots leave the slab at once");
+        if ((int64_t)nlist > s->cap / 4) {  // the compaction lists of fsim_migrate_unpack hold cap/4 entries each
+            set_error("fsim_migrate_pack: more than a quarter of the particle slots leave the slab at once");
             return (int)FSIM_ERR_RANGE;
         }
         int64_t total = 0;
@@ -274,13 +483,13 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
             total += hc[k];
         }
         FSIM_TRY(ensure_migr(s, (size_t)total * (NPART_ARRAYS * sizeof(Real) + 8) + 16));
-        FSIM_CUDA(cudaMemcpyAsync(scr + MAX_RANKS, off, sizeof(uint32_t) * nranks, cudaMemcpyHostToDevice, s->stream));
+        FSIM_CUDA(cudaMemcpyAsync(scr + MC_CURSOR, off, sizeof(uint32_t) * nranks, cudaMemcpyHostToDevice, s->stream));
         PackArgs<Real> a;
         for (int k = 0; k < NPART_ARRAYS; ++k) a.src[k] = (const Real *)s->part[c][k];
         a.alive = s->alive[c];
         a.id = s->pid[c];
         a.buf = (unsigned char *)s->migr;
-        a.cursor = scr + MAX_RANKS;
+        a.cursor = scr + MC_CURSOR;
         a.list = s->perm; a.nlist = nlist;
         a.hole_flag = s->hole_flag;
         a.key = keys ? s->key : nullptr;
@@ -305,7 +514,7 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
         set_error("fsim_migrate_unpack: bad argument");
         return FSIM_ERR_INVALID;
     }
-    FSIM_CUDA(cudaSetDevice(s->device));
+    FSIM_TRY(check_handle(s));
     const int64_t nholes = s->nholes_host;
     const int64_t n_old = s->n;
     const int64_t n_new = n_old - nholes + nrecv;
@@ -339,11 +548,11 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
             uint32_t *targets = s->perm + s->cap / 2, *sources = s->perm + s->cap / 2 + s->cap / 4;
             compact_lists_kernel<<<grid_for(span, 256), 256, 0, s->stream>>>(
                 s->perm, (uint32_t)nholes, (uint32_t)nrecv, s->hole_flag, n_new, n_old, targets,
-                scr + 2 * MAX_RANKS + 1, sources, scr + 2 * MAX_RANKS + 2);
+                scr + MC_NTARGETS, sources, scr + MC_NSOURCES);
             MoveArgs<Real> m;
             for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k] = (Real *)s->part[c][k];
             m.alive = s->alive[c]; m.id = s->pid[c];
-            m.targets = targets; m.sources = sources; m.ntargets = scr + 2 * MAX_RANKS + 1;
+            m.targets = targets; m.sources = sources; m.ntargets = scr + MC_NTARGETS;
             m.key = s->keys_valid ? s->key : nullptr;
             for (int q = 0; q < 2; ++q) m.dcol[q] = (Real *)s->dcol[q];
             compact_move_kernel<Real><<<grid_for(nholes - nrecv, 256), 256, 0, s->stream>>>(m);
@@ -362,17 +571,224 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
     return FSIM_OK;
 }
 
+
+// ---- asynchronous exchange: fixed-capacity regions, counts in the region headers ----------------------
+static PlanDev plan_dev(const MigratePlan &p)
+{
+    PlanDev d;
+    d.nranks = p.nranks; d.self = p.self;
+    for (int k = 0; k <= MAX_RANKS; ++k) { d.lo[k] = p.lo[k]; d.recv_slot0[k] = p.recv_slot0[k]; }
+    for (int k = 0; k < MAX_RANKS; ++k) {
+        d.send_cap[k] = p.send_cap[k]; d.recv_cap[k] = p.recv_cap[k];
+        d.send_off[k] = p.send_off[k]; d.recv_off[k] = p.recv_off[k];
+    }
+    return d;
+}
+
+int fsim_migrate_setup(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, int32_t self, const int64_t *send_caps,
+                       const int64_t *recv_caps, void **send_buf_dev, void **recv_buf_dev, int64_t *send_region_bytes,
+                       int64_t *recv_region_bytes)
+{
+    FSIM_TRY(check_handle(s));
+    if (!row_bounds || !send_caps || !recv_caps || !send_buf_dev || !recv_buf_dev || !send_region_bytes || !recv_region_bytes) {
+        set_error("fsim_migrate_setup: null argument");
+        return FSIM_ERR_INVALID;
+    }
+    if (!s->slab || nranks < 1 || nranks > MAX_RANKS || self < 0 || self >= nranks ||
+        row_bounds[self] != s->own0 || row_bounds[self + 1] != s->own0 + s->own_rows) {
+        set_error("fsim_migrate_setup: rank arguments do not match the slab of this handle");
+        return FSIM_ERR_INVALID;
+    }
+    FSIM_TRY(settle_count(s));
+    MigratePlan &p = s->plan;
+    for (void *q : {(void *)p.send, (void *)p.recv, (void *)p.holes, (void *)p.targets, (void *)p.sources})
+        if (q) FSIM_CUDA(cudaFree(q));
+    p = MigratePlan();
+    p.nranks = nranks; p.self = self;
+    for (int k = 0; k <= nranks; ++k) p.lo[k] = (int)row_bounds[k];
+    const size_t rec = NPART_ARRAYS * s->rs + 8;
+    auto region = [&](int64_t cap) { return (uint64_t)((MIGRATE_HEADER_BYTES + (size_t)cap * rec + 15) / 16 * 16); };
+    for (int k = 0; k < nranks; ++k) {
+        if (send_caps[k] < 0 || recv_caps[k] < 0 || send_caps[k] > (1 << 28) || recv_caps[k] > (1 << 28)) {
+            set_error("fsim_migrate_setup: capacity out of range");
+            return FSIM_ERR_INVALID;
+        }
+        p.send_cap[k] = k == self ? 0u : (uint32_t)send_caps[k];
+        p.recv_cap[k] = k == self ? 0u : (uint32_t)recv_caps[k];
+        p.send_off[k + 1] = p.send_off[k] + region(p.send_cap[k]);
+        p.recv_off[k + 1] = p.recv_off[k] + region(p.recv_cap[k]);
+        p.recv_slot0[k + 1] = p.recv_slot0[k] + p.recv_cap[k];
+        p.send_total += p.send_cap[k];
+        p.recv_total += p.recv_cap[k];
+        send_region_bytes[k] = (int64_t)(p.send_off[k + 1] - p.send_off[k]);
+        recv_region_bytes[k] = (int64_t)(p.recv_off[k + 1] - p.recv_off[k]);
+    }
+    FSIM_CUDA(cudaMalloc((void **)&p.send, p.send_off[nranks]));
+    FSIM_CUDA(cudaMalloc((void **)&p.recv, p.recv_off[nranks]));
+    FSIM_CUDA(cudaMemsetAsync(p.send, 0, p.send_off[nranks], s->stream));
+    FSIM_CUDA(cudaMemsetAsync(p.recv, 0, p.recv_off[nranks], s->stream));
+    const size_t nl = std::max<size_t>(p.send_total, 1);
+    FSIM_CUDA(cudaMalloc((void **)&p.holes, sizeof(uint32_t) * nl));
+    FSIM_CUDA(cudaMalloc((void **)&p.targets, sizeof(uint32_t) * nl));
+    FSIM_CUDA(cudaMalloc((void **)&p.sources, sizeof(uint32_t) * nl));
+    if (!s->n_pinned) {
+        FSIM_CUDA(cudaMallocHost((void **)&s->n_pinned, 2 * sizeof(uint32_t)));
+        for (int k = 0; k < 2; ++k) FSIM_CUDA(cudaEventCreateWithFlags(&s->n_event[k], cudaEventDisableTiming));
+    }
+    // from here on the exact particle count lives on the device
+    FSIM_CUDA(cudaMemsetAsync(s->mscratch, 0, sizeof(uint32_t) * MC_WORDS, s->stream));
+    set_words_kernel<<<1, 32, 0, s->stream>>>(s->mscratch + MC_NLIVE, (uint32_t)s->n, 1);
+    FSIM_CUDA(cudaGetLastError());
+    s->n_async = true;
+    s->n_inflight[0] = s->n_inflight[1] = false;
+    s->have_leavers = false;
+    *send_buf_dev = p.send;
+    *recv_buf_dev = p.recv;
+    return FSIM_OK;
+}
+
+// Leavers -> send regions (headers carry the counts).  Nothing is read back: the caller enqueues its
+// all-to-all of the (fixed-size) regions on the same stream and then calls fsim_migrate_end.
+int fsim_migrate_begin(fsim_sim *s)
+{
+    FSIM_TRY(check_handle(s));
+    if (!s->n_async) {
+        set_error("fsim_migrate_begin: call fsim_migrate_setup first");
+        return FSIM_ERR_STATE;
+    }
+    const MigratePlan &p = s->plan;
+    uint32_t *ctr = s->mscratch;
+    s->binned = false;
+    const bool keys = s->keys_valid;
+    return dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        const int c = s->cur;
+        if (!s->have_leavers) {  // the push did not emit the list: scan the positions
+            FSIM_CUDA(cudaMemsetAsync(ctr + MC_NLEAVERS, 0, sizeof(uint32_t), s->stream));
+            if (s->n) {
+                find_leavers_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
+                    (const Real *)s->part[c][AZ], s->n, ctr + MC_NLIVE, s->nz, s->own0, s->own_rows, s->perm, ctr + MC_NLEAVERS);
+                FSIM_CUDA(cudaGetLastError());
+                s->launches++;
+            }
+        }
+        s->have_leavers = false;
+        const PlanDev pd = plan_dev(p);
+        PackFixedArgs<Real> a;
+        for (int k = 0; k < NPART_ARRAYS; ++k) a.src[k] = (const Real *)s->part[c][k];
+        a.alive = s->alive[c]; a.id = s->pid[c];
+        a.send = p.send; a.list = s->perm; a.holes = p.holes; a.hole_flag = s->hole_flag;
+        a.ctr = ctr;
+        a.key = keys ? s->key : nullptr;
+        a.counts = s->counts;
+        a.nz = s->nz;
+        {
+            Bracket b(s, "migrate_pack");
+            migrate_pack_fixed_kernel<Real><<<s->nsm * 2, 256, 0, s->stream>>>(a, pd);
+            migrate_send_headers_kernel<<<1, 64, 0, s->stream>>>(p.send, ctr, pd);
+            FSIM_CUDA(cudaGetLastError());
+            s->launches++;
+        }
+        return (int)FSIM_OK;
+    });
+}
+
+// Arrivals (receive regions) -> holes / end of the storage, compaction, new count -- all from device-side counts.
+int fsim_migrate_end(fsim_sim *s)
+{
+    FSIM_TRY(check_handle(s));
+    if (!s->n_async) {
+        set_error("fsim_migrate_end: call fsim_migrate_setup first");
+        return FSIM_ERR_STATE;
+    }
+    const MigratePlan &p = s->plan;
+    uint32_t *ctr = s->mscratch;
+    const uint32_t max_live = (uint32_t)(s->cap - 1024);
+    int rc = dispatch(s, [&](auto tag) {
+        using Real = decltype(tag);
+        const int c = s->cur;
+        const PlanDev pd = plan_dev(p);
+        Bracket b(s, "migrate_unpack");
+        migrate_recv_headers_kernel<<<1, 64, 0, s->stream>>>(p.recv, ctr, pd, max_live);
+        if (p.recv_total) {
+            UnpackFixedArgs<Real> a;
+            for (int k = 0; k < NPART_ARRAYS; ++k) a.dst[k] = (Real *)s->part[c][k];
+            a.alive = s->alive[c]; a.id = s->pid[c];
+            a.recv = p.recv; a.holes = p.holes; a.hole_flag = s->hole_flag; a.ctr = ctr;
+            a.key = s->keys_valid ? s->key : nullptr;
+            a.counts = s->counts;
+            for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
+            a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
+            a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
+            migrate_unpack_fixed_kernel<Real><<<grid_for(p.recv_total, 256), 256, 0, s->stream>>>(a, pd);
+        }
+        if (p.send_total) {  // shrink when more left than arrived (decided on the device)
+            compact_lists_fixed_kernel<<<grid_for(p.send_total, 256), 256, 0, s->stream>>>(
+                p.holes, s->hole_flag, ctr, p.targets, p.sources, p.send_total);
+            MoveArgs<Real> m;
+            for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k] = (Real *)s->part[c][k];
+            m.alive = s->alive[c]; m.id = s->pid[c];
+            m.targets = p.targets; m.sources = p.sources; m.ntargets = ctr + MC_NTARGETS;
+            m.key = s->keys_valid ? s->key : nullptr;
+            for (int q = 0; q < 2; ++q) m.dcol[q] = (Real *)s->dcol[q];
+            compact_move_kernel<Real><<<grid_for(p.send_total, 256), 256, 0, s->stream>>>(m);
+            migrate_finish_kernel<<<grid_for(p.send_total, 256), 256, 0, s->stream>>>(p.holes, s->hole_flag, ctr, p.send_total);
+        }
+        migrate_publish_kernel<<<1, 64, 0, s->stream>>>(ctr, p.nranks);
+        FSIM_CUDA(cudaGetLastError());
+        s->launches += 5;
+        return (int)FSIM_OK;
+    });
+    FSIM_TRY(rc);
+    // Host-side UPPER bound of the live slots (grid sizes): the newest read-back that has arrived plus
+    // everything that may have come in since; the read-back of this frame's count is queued, never awaited.
+    for (int k = 0; k < 2; ++k)
+        if (s->n_inflight[k]) s->n_pending_bound[k] += p.recv_total;
+    int64_t bound = std::min<int64_t>(s->n + (int64_t)p.recv_total, s->cap - 1024);
+    for (int k = 0; k < 2; ++k)
+        if (s->n_inflight[k] && cudaEventQuery(s->n_event[k]) == cudaSuccess) {
+            bound = std::min<int64_t>(bound, (int64_t)s->n_pinned[k] + s->n_pending_bound[k]);
+            s->n_inflight[k] = false;
+        }
+    s->n = bound;
+    const int slot = s->n_slot ^= 1;
+    if (!s->n_inflight[slot]) {
+        FSIM_CUDA(cudaMemcpyAsync(s->n_pinned + slot, ctr + MC_NLIVE, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        FSIM_CUDA(cudaEventRecord(s->n_event[slot], s->stream));
+        s->n_inflight[slot] = true;
+        s->n_pending_bound[slot] = 0;
+    }
+    s->ids_identity = false;
+    s->binned = false;  // keys_valid is kept: the kernels above maintained key[], dcol[] and counts[]
+    return FSIM_OK;
+}
+
+// records packed so far (statistics; synchronises)
+int fsim_migrate_stats(fsim_sim *s, int64_t *sent_total)
+{
+    FSIM_TRY(check_handle(s));
+    if (!sent_total) {
+        set_error("fsim_migrate_stats: null argument");
+        return FSIM_ERR_INVALID;
+    }
+    uint32_t w[2] = {0, 0};
+    FSIM_CUDA(cudaMemcpyAsync(w, s->mscratch + MC_SENT_LO, sizeof w, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    *sent_total = (int64_t)(((uint64_t)w[1] << 32) | w[0]);
+    return FSIM_OK;
+}
+
 int fsim_halo_ptrs(fsim_sim *s, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, int64_t *bytes_each)
 {
     if (!s || !send_lo || !send_hi || !recv_lo || !recv_hi || !bytes_each) {
         set_error("fsim_halo_ptrs: null argument");
         return FSIM_ERR_INVALID;
     }
-    FSIM_CUDA(cudaSetDevice(s->device));
+    FSIM_TRY(check_handle(s));
     const size_t each = (size_t)4 * FSIM_SHAPE_MID * s->nr * s->rs;
     if (!s->halo_buf) {
         FSIM_CUDA(cudaMalloc(&s->halo_buf, 4 * each));
-        FSIM_CUDA(cudaMemset(s->halo_buf, 0, 4 * each));
+        FSIM_CUDA(cudaMemsetAsync(s->halo_buf, 0, 4 * each, s->stream));  // ordered before the first halo pack by the stream
     }
     unsigned char *b = (unsigned char *)s->halo_buf;
     const int o0 = s->own0 - s->row0;  // first owned row, local index
@@ -436,6 +852,18 @@ int launch_halo_unpack(fsim_sim *s)
     const int o0 = s->own0 - s->row0;
     if (p[2]) FSIM_TRY(halo_copy(s, 2, o0 - FSIM_SHAPE_MID, 0));        // recv_lo -> 5 rows below the slab
     if (p[3]) FSIM_TRY(halo_copy(s, 3, o0 + s->own_rows, 0));           // recv_hi -> 5 rows above the slab
+    return FSIM_OK;
+}
+
+// asynchronous exchange: the host's n is an upper bound between synchronisation points; make it exact
+int settle_count(fsim_sim *s)
+{
+    if (!s->n_async) return FSIM_OK;
+    uint32_t n = 0;
+    FSIM_CUDA(cudaMemcpyAsync(&n, s->mscratch + MC_NLIVE, sizeof n, cudaMemcpyDeviceToHost, s->stream));
+    FSIM_CUDA(cudaStreamSynchronize(s->stream));
+    s->n = (int64_t)n;
+    s->n_inflight[0] = s->n_inflight[1] = false;
     return FSIM_OK;
 }
 

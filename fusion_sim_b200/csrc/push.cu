@@ -8,12 +8,12 @@
 // position shader reads the old position with the new velocity (:847-848), so the fusion is
 // exact and the update can be done in place (a particle touches only its own state).
 //
-// HBM-bound: 10 reals + 1 byte read and written per particle, streamed with 128-bit loads and
-// stores (ld.global.cs / st.global.cs keep the 126 MB L2 for the entropy and cell tables);
+// HBM-bound: 10 reals + 1 byte read and written per particle, streamed with vector loads and
+// stores (ld.global.cs / st.global.cs keep the 126 MB L2 for the entropy and cell tables): 64-bit
+// per lane (fp64: one particle per thread at 64 registers, 32 warps per SM -- measured 12 % faster
+// than 128-bit loads, which need 128 registers and halve the occupancy: profiles/r2_push_variants.md);
 // tables come through the read-only path.  Arithmetic is IEEE, left to right as the GLSL is
 // written, compiled with -fmad=false so it rounds exactly like the CPU oracle.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace fsim {
@@ -24,7 +24,7 @@ struct PushArgs {
     uint8_t *alive;
     const Real *__restrict__ ent;
     const Real *__restrict__ cellrec;
-    const uint8_t *__restrict__ sink;
+    const uint32_t *__restrict__ sink;  // 1 bit per GLOBAL cell (2 MB at 8192 x 2048: stays in L2)
     const Real *__restrict__ invcdf;
     uint32_t *key;      // optional deposit prepass: sort key, sprite colour, histogram
     Real *dcol[2];
@@ -32,7 +32,8 @@ struct PushArgs {
     uint32_t *oob;
     uint32_t *leavers, *nleavers;  // slab mode: slots whose new row is not owned (migration list)
     int own0, own_rows;
-    int64_t n;
+    int64_t n;              // live slots (an upper bound when n_dev is set)
+    const uint32_t *n_dev;  // asynchronous slab exchange: the exact count lives on the device
     int nr, nz, row0, rows, own_lo, own_hi;
     Real sf, h, k13, k31;
 };
@@ -116,7 +117,7 @@ struct Slots {
 // NH = 2 performs the B-pass and the A-pass of empic.js:1438-1467 in one sweep over HBM: state
 // read once, written once.  Same operations in the same order, hence the same bits.
 template <typename Real, int V, int NH>
-__device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p0, Slots<Real, V> &t)
+__device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p0, const int64_t n, Slots<Real, V> &t)
 {
     Real (&x)[V] = t.x, (&y)[V] = t.y, (&z)[V] = t.z, (&vx)[V] = t.vx, (&vy)[V] = t.vy, (&vz)[V] = t.vz;
     Real (&q0)[V] = t.q0, (&q1)[V] = t.q1, (&q2)[V] = t.q2, (&q3)[V] = t.q3, (&rcur)[V] = t.rcur;
@@ -141,7 +142,9 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
             const int ci = tex_idx(r, a.nr);
             int cj = tex_idx(z[k], a.nz) - a.row0;
             if (cj < 0 || cj >= a.rows) {  // slab mode: particle outside the local table
-                if (p0 + k < a.n) atomicAdd(a.oob, 1u);
+                // counted only if the record is USED: a particle respawned in the previous half-step
+                // (al = 0) gets a fresh random velocity (:772) and may sit anywhere in the global domain
+                if (al[k] && p0 + k < n) atomicAdd(a.oob, 1u);
                 cj = cj < 0 ? 0 : a.rows - 1;
             }
             ld_rec(a.cellrec + RECSTRIDE * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
@@ -186,8 +189,10 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
             const Real nzp = z[k] + a.sf * nvz;
             const Real rn = fsqrt(nx * nx + ny * ny);
             bool keep = false;
-            if (rn == rn && nzp == nzp)  // NaN position => absorbed (documented rule)
-                keep = __ldg(a.sink + ((size_t)tex_idx(rn, a.nr) + (size_t)tex_idx(nzp, a.nz) * a.nr)) != 0;
+            if (rn == rn && nzp == nzp) {  // NaN position => absorbed (documented rule)
+                const uint32_t gc = (uint32_t)tex_idx(rn, a.nr) + (uint32_t)tex_idx(nzp, a.nz) * (uint32_t)a.nr;
+                keep = (__ldg(a.sink + (gc >> 5)) >> (gc & 31u)) & 1u;
+            }
             if (keep) {
                 x[k] = nx; y[k] = ny; z[k] = nzp; al[k] = 1;
                 rcur[k] = rn;
@@ -206,7 +211,7 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
 // Deposit prepass on the NEW state (what density() will see): sort key, sprite colour and the
 // warp-aggregated histogram of the counting sort.  Whole warps must call this converged.
 template <typename Real, int V>
-__device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int64_t p0, const Slots<Real, V> &t)
+__device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int64_t p0, const int64_t n, const Slots<Real, V> &t)
 {
     const int lane = threadIdx.x & 31;
     uint32_t newcell[V];
@@ -219,7 +224,7 @@ __device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int6
     for (int q = 0; q < 2; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);  // 0.001 v_z is formed by the per-cell pass from v_z itself
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-        const bool valid = p0 + k < a.n;
+        const bool valid = p0 + k < n;
         const uint32_t c = valid ? (newcell[k] & KEY_MASK) : 0xffffffffu;
         if (valid) a.key[p0 + k] = newcell[k];
         if (valid && a.leavers) {
@@ -261,6 +266,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
     // no early exit: the arrays are padded past n (common.cuh), the whole warp stays converged for
     // the warp-aggregated histogram; side effects of slots >= n are masked.
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    const int64_t n = live_count(a.n_dev, a.n);
     Slots<Real, V> t;
     ld_stream<Real, V>(a.a[AQ2] + p0, t.q2);
     ld_stream<Real, V>(a.a[AQ3] + p0, t.q3);
@@ -274,9 +280,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
     ld_stream<Real, V>(a.a[AVZ] + p0, t.vz);
 #pragma unroll
     for (int k = 0; k < V; ++k) t.al[k] = a.alive[p0 + k];
-    advance<Real, V, NH>(a, p0, t);
+    advance<Real, V, NH>(a, p0, n, t);
     store_slots<Real, V>(a, p0, t);
-    if (a.key) emit_prepass<Real, V>(a, p0, t);
+    if (a.key) emit_prepass<Real, V>(a, p0, n, t);
 }
 
 template <typename Real>
@@ -294,9 +300,10 @@ static PushArgs<Real> make_args(fsim_sim *s, bool with_hist)
     a.counts = s->counts;
     a.oob = s->oob;
     a.leavers = (with_hist && s->slab) ? s->perm : nullptr;
-    a.nleavers = s->mscratch + 2 * 64;
+    a.nleavers = s->mscratch + MC_NLEAVERS;
     a.own0 = s->own0; a.own_rows = s->own_rows;
     a.n = s->n;
+    a.n_dev = s->n_async ? s->mscratch + MC_NLIVE : nullptr;
     a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
     a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
     a.sf = (Real)s->step_factor;
@@ -316,13 +323,11 @@ static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf)
     return FSIM_OK;
 }
 
-// Tuning variants (vector width, block size, register cap); FSIM_PUSH_VARIANT selects one at run
-// time for measurement, the default is the one measured fastest on B200 (profiles/).
-static int push_variant()
-{
-    const char *e = getenv("FSIM_PUSH_VARIANT");  // read per launch: tools/tune.py sweeps it in-process
-    return e ? atoi(e) : 4;  // 4: 64-bit loads, 256 threads x 4 blocks per SM -- measured fastest on B200 for fp64
-}
+#ifdef FSIM_TUNE
+// Tuning build only (make EXTRA=-DFSIM_TUNE, tools/tune.py): vector width / block size / register cap
+// variants selectable at run time through fsim_tune_set().  The product compiles ONE variant per precision.
+int g_push_variant = 0;
+#endif
 
 int launch_push(fsim_sim *s, bool with_hist, int nhalf)
 {
@@ -330,22 +335,28 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf)
         FSIM_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (s->ncell_local + 1), s->stream));
         s->counts_dirty = false;
     }
-    if (with_hist && s->slab) FSIM_CUDA(cudaMemsetAsync(s->mscratch + 2 * 64, 0, sizeof(uint32_t), s->stream));
+    if (with_hist && s->slab) FSIM_CUDA(cudaMemsetAsync(s->mscratch + MC_NLEAVERS, 0, sizeof(uint32_t), s->stream));
     int rc = dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
-        constexpr int V = 16 / sizeof(Real);  // 128-bit loads and stores
+        constexpr int V = 16 / sizeof(Real);  // particles per 128 bits
         if (s->n == 0) return (int)FSIM_OK;
         const PushArgs<Real> a = make_args<Real>(s, with_hist);
         Bracket b(s, nhalf == 2 ? "push2" : "push");
-        switch (push_variant()) {
+#ifdef FSIM_TUNE
+        switch (g_push_variant) {
         case 1: return push_impl<Real, V, 128, 4>(s, a, nhalf);
         case 2: return push_impl<Real, V, 256, 3>(s, a, nhalf);
         case 3: return push_impl<Real, V / 2, 256, 3>(s, a, nhalf);
+        case 4: return push_impl<Real, V / 2, 256, 4>(s, a, nhalf);
         case 5: return push_impl<Real, V / 2, 128, 6>(s, a, nhalf);
         case 6: return push_impl<Real, V / 2, 512, 2>(s, a, nhalf);
         case 7: return push_impl<Real, V, 256, 2>(s, a, nhalf);
-        default: return push_impl<Real, V / 2, 256, 4>(s, a, nhalf);
+        default: break;
         }
+#endif
+        // measured fastest on B200 (profiles/r2_push_variants.md): fp64 one particle per thread (64-bit
+        // streams), fp32 two (64-bit streams); 256 threads x 4 blocks per SM = 64 registers per thread
+        return push_impl<Real, V / 2, 256, 4>(s, a, nhalf);
     });
     s->binned = false;
     s->keys_valid = with_hist;

@@ -25,6 +25,7 @@ struct PrepassArgs {
     uint32_t *key, *counts;
     Real *dcol[2];
     int64_t n;
+    const uint32_t *n_dev;
     int nr, nz, row0, rows, own_lo, own_hi;
 };
 
@@ -32,7 +33,7 @@ template <typename Real>
 __global__ void __launch_bounds__(256) prepass_kernel(const PrepassArgs<Real> a)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < a.n;
+    const bool valid = p < live_count(a.n_dev, a.n);
     uint32_t c = 0xffffffffu;  // lanes past the end form their own (ignored) group
     if (valid) {
         const Real xx = a.x[p], yy = a.y[p];
@@ -184,13 +185,14 @@ struct PermuteArgs {
     uint32_t *id_dst;
     const uint32_t *perm;
     int64_t n;
+    const uint32_t *n_dev;
 };
 
 template <typename Real>
 __global__ void __launch_bounds__(256) apply_perm_kernel(const PermuteArgs<Real> a)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.n) return;
+    if (j >= live_count(a.n_dev, a.n)) return;
     const size_t p = a.perm[j] & KEY_MASK;
     Real v[NPART_ARRAYS];
 #pragma unroll
@@ -209,8 +211,9 @@ constexpr int IDX_ITEMS = 4;  // 32-particle chunks per warp: their atomics' rou
 
 __global__ void __launch_bounds__(256)
 index_scatter_kernel(const uint32_t *__restrict__ key, uint32_t *__restrict__ cursor,
-                     uint32_t *__restrict__ perm, int64_t n)
+                     uint32_t *__restrict__ perm, int64_t n_host, const uint32_t *__restrict__ n_dev)
 {
+    const int64_t n = live_count(n_dev, n_host);
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t p0 = warp * (32 * IDX_ITEMS) + lane;
@@ -256,6 +259,7 @@ int launch_keys(fsim_sim *s)
             a.key = s->key; a.counts = s->counts;
             for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
             a.n = s->n; a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
+            a.n_dev = s->n_async ? s->mscratch + MC_NLIVE : nullptr;
             a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
             Bracket b(s, "prepass");
             prepass_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
@@ -285,8 +289,8 @@ int launch_bin(fsim_sim *s)
     s->counts_dirty = false;  // scan_final zeroed counts[]
     if (s->n) {
         Bracket b(s, "index_scatter");
-        index_scatter_kernel<<<grid_for((s->n + IDX_ITEMS - 1) / IDX_ITEMS, 256), 256, 0, s->stream>>>(s->key, s->cursor,
-                                                                                                      s->perm, s->n);
+        index_scatter_kernel<<<grid_for((s->n + IDX_ITEMS - 1) / IDX_ITEMS, 256), 256, 0, s->stream>>>(
+            s->key, s->cursor, s->perm, s->n, s->n_async ? s->mscratch + MC_NLIVE : nullptr);
         FSIM_CUDA(cudaGetLastError());
     }
     s->binned = true;
@@ -309,6 +313,7 @@ int launch_apply_perm(fsim_sim *s)
             a.alive_src = s->alive[src]; a.alive_dst = s->alive[dst];
             a.id_src = s->pid[src]; a.id_dst = s->pid[dst];
             a.perm = s->perm; a.n = s->n;
+            a.n_dev = s->n_async ? s->mscratch + MC_NLIVE : nullptr;
             Bracket b(s, "permute");
             apply_perm_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(a);
             FSIM_CUDA(cudaGetLastError());

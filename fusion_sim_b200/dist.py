@@ -6,10 +6,14 @@ Per frame:
   step()     every rank pushes its own particles (no communication: the gather is nearest-grid-
              point, `halo_rows` rows of cell table beyond the slab cover the drift of a frame);
   density()  1. particles whose row left the slab (drift, or respawn anywhere in the domain) are
-                packed by destination and moved with an all-to-all-v; records carry the global id;
+                packed by destination rank into FIXED-CAPACITY regions whose headers carry the record
+                counts, and moved with one all-to-all of host-known sizes; records carry the global id.
+                No count is read back: the frame has no host round trip (exchange="exact" keeps the
+                host-synchronising all-to-all-v for arbitrary volumes);
              2. sort + per-cell sums of the owned rows (id order => same bits as on one GPU);
-             3. the 5 boundary rows of per-cell sums go to each neighbour (send/recv);
-             4. 11x11 stencil + normalise + running average on the owned rows.
+             3. the 5 boundary rows of per-cell sums go to each neighbour (send/recv) WHILE the stencil
+                runs on the rows that need no halo row;
+             4. 11x11 stencil + normalise + running average on the remaining (boundary) rows.
 
 The exchange functions work on any backend object with the small interface used below, so the
 host logic is tested on CPU (gloo, world_size 2) against the single-process oracle.
@@ -48,8 +52,30 @@ def exchange_records(send: torch.Tensor, send_counts, record_bytes: int, group=N
     return recv, sum(rc_l)
 
 
-def exchange_halo(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, group=None):
-    """Boundary rows of the per-cell sums: send_lo -> rank-1 (its recv_hi), send_hi -> rank+1."""
+HEADER_BYTES = 16  # every exchange region: record count (u32) + padding, then the records
+
+
+def region_capacities(rank: int, world: int, cap_neighbour: int, cap_far: int):
+    """Records the region between `rank` and every other rank holds: drift only reaches the two
+    neighbours, a respawn can land anywhere (the source pdf is global).  Symmetric in the two ranks,
+    so the sender's and the receiver's host agree on every size without talking."""
+    return [0 if k == rank else (int(cap_neighbour) if abs(k - rank) == 1 else int(cap_far)) for k in range(world)]
+
+
+def region_bytes(cap: int, record_bytes: int) -> int:
+    return (HEADER_BYTES + cap * record_bytes + 15) // 16 * 16
+
+
+def exchange_regions(send: torch.Tensor, send_bytes, recv: torch.Tensor, recv_bytes, group=None):
+    """All-to-all of fixed-size regions: region k of `send` goes to rank k, region k of `recv` comes
+    from rank k.  Sizes are known to both hosts in advance; the record counts travel in the headers."""
+    dist.all_to_all_single(recv, send, output_split_sizes=[int(b) for b in recv_bytes],
+                           input_split_sizes=[int(b) for b in send_bytes], group=group)
+
+
+def exchange_halo_begin(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, group=None):
+    """Boundary rows of the per-cell sums: send_lo -> rank-1 (its recv_hi), send_hi -> rank+1.
+    Returns the pending work objects (wait with exchange_halo_finish)."""
     ops = []
     if rank > 0:
         ops.append(dist.P2POp(dist.isend, send_lo, rank - 1, group))
@@ -57,9 +83,16 @@ def exchange_halo(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, gro
     if rank < world - 1:
         ops.append(dist.P2POp(dist.isend, send_hi, rank + 1, group))
         ops.append(dist.P2POp(dist.irecv, recv_hi, rank + 1, group))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+def exchange_halo_finish(works):
+    for w in works:
+        w.wait()  # NCCL: the current stream waits, the host does not
+
+
+def exchange_halo(send_lo, send_hi, recv_lo, recv_hi, rank: int, world: int, group=None):
+    exchange_halo_finish(exchange_halo_begin(send_lo, send_hi, recv_lo, recv_hi, rank, world, group))
 
 
 HALO_RELAX = 4  # rows of potential a relaxation launch may consume (most sweeps per launch)
@@ -100,9 +133,15 @@ def _dev_tensor(ptr: int, nbytes: int, device) -> torch.Tensor:
 
 
 class SlabPusher:
-    """One rank of a slab-decomposed simulation; same member names as the single-GPU object."""
+    """One rank of a slab-decomposed simulation; same member names as the single-GPU object.
 
-    def __init__(self, spec: dict, scene: dict, rank: int, world: int, halo_rows: int = 16, slack: float = 0.25):
+    exchange="fixed" (default): fixed-capacity exchange regions, every count stays on the device, no host
+    round trip in the frame; `cap_neighbour` / `cap_far` are the records a region to a neighbouring / any
+    other rank holds per frame (an overflow is reported by sync()).  exchange="exact": all-to-all-v sized
+    by counts read back to the host (two host waits per frame, any volume)."""
+
+    def __init__(self, spec: dict, scene: dict, rank: int, world: int, halo_rows: int = 16, slack: float = 0.25,
+                 exchange: str = "fixed", cap_neighbour: int | None = None, cap_far: int | None = None):
         from . import _lib
         from .pusher import CylindricalParticlePusher
         from .scenes import apply_scene
@@ -118,46 +157,118 @@ class SlabPusher:
         self.sim = CylindricalParticlePusher(lspec)
         apply_scene(self.sim, scene)
         self._lib = _lib
+        L, h = _lib.lib(), self.sim.handle
         # one stream for the engine's kernels AND the NCCL collectives: torch orders a collective after
         # the current stream's work and makes the current stream wait for it, so no host
         # synchronisation is needed between a kernel and the exchange that consumes its output
         self.stream = torch.cuda.Stream(self.device)
         self.sim.sync()
-        _lib.check(_lib.lib().fsim_set_stream(self.sim.handle, C.c_void_p(self.stream.cuda_stream)))
-        self.record_bytes = int(_lib.lib().fsim_migrate_record_bytes(self.sim.handle))
+        _lib.check(L.fsim_set_stream(h, C.c_void_p(self.stream.cuda_stream)))
+        self.record_bytes = int(L.fsim_migrate_record_bytes(h))
         self.ncell_local = self.sim.ncell_local
         self._bounds_c = (C.c_int64 * (world + 1))(*self.bounds)
-        self.migrated = 0
-        self.t_migrate = self.t_halo = 0.0
+        self.exchange = exchange
+        self._sent_exact = 0
+        self.host_wait_s = 0.0
+        self.comm_timing = False
+        self._ev = {"migrate_exchange": [], "halo_exchange_exposed": []}
+        if exchange == "fixed":
+            nb = int(cap_neighbour) if cap_neighbour else max(4096, n_local // 1024)
+            far = int(cap_far) if cap_far else max(1024, n_local // 16384)
+            caps = region_capacities(rank, world, nb, far)
+            caps_c = (C.c_int64 * world)(*caps)
+            sb, rb = (C.c_int64 * world)(), (C.c_int64 * world)()
+            sp, rp = C.c_void_p(), C.c_void_p()
+            _lib.check(L.fsim_migrate_setup(h, self._bounds_c, world, rank, caps_c, caps_c, C.byref(sp), C.byref(rp), sb, rb))
+            self._send_bytes, self._recv_bytes = list(sb), list(rb)
+            assert self._send_bytes == [region_bytes(c, self.record_bytes) for c in caps]
+            with torch.cuda.stream(self.stream):
+                self._send = _dev_tensor(sp.value, sum(self._send_bytes), self.device)
+                self._recv = _dev_tensor(rp.value, sum(self._recv_bytes), self.device)
+            self.capacities = caps
+        elif exchange != "exact":
+            raise ValueError("exchange: 'fixed' or 'exact'")
+        ptrs = [C.c_void_p() for _ in range(4)]
+        nbytes = C.c_int64()
+        _lib.check(L.fsim_halo_ptrs(h, *[C.byref(p) for p in ptrs], C.byref(nbytes)))
+        with torch.cuda.stream(self.stream):
+            self._halo = [_dev_tensor(p.value or 0, nbytes.value if p.value else 0, self.device) for p in ptrs]
 
     # -- frame --------------------------------------------------------------------------------
     def step(self):
         self.sim.step()
 
+    def _mark(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(self.stream)
+        return e
+
     def migrate(self):
         L, h = self._lib.lib(), self.sim.handle
+        if self.exchange == "fixed":
+            self._lib.check(L.fsim_migrate_begin(h))
+            with torch.cuda.stream(self.stream):
+                e0 = self._mark() if self.comm_timing else None
+                exchange_regions(self._send, self._send_bytes, self._recv, self._recv_bytes)
+                if e0 is not None:
+                    self._ev["migrate_exchange"].append((e0, self._mark()))
+            self._lib.check(L.fsim_migrate_end(h))
+            return
+        import time
         counts = (C.c_int64 * self.world)()
         buf = C.c_void_p()
-        self._lib.check(L.fsim_migrate_pack(h, self._bounds_c, self.world, self.rank, counts, C.byref(buf)))
+        t0 = time.perf_counter()
+        self._lib.check(L.fsim_migrate_pack(h, self._bounds_c, self.world, self.rank, counts, C.byref(buf)))  # reads counts back
+        self.host_wait_s += time.perf_counter() - t0
         sc = list(counts)
         with torch.cuda.stream(self.stream):
             send = _dev_tensor(buf.value or 0, sum(sc) * self.record_bytes, self.device)
-            recv, nrecv = exchange_records(send, sc, self.record_bytes)  # the count exchange is the frame's one host wait
+            e0 = self._mark() if self.comm_timing else None
+            t0 = time.perf_counter()
+            recv, nrecv = exchange_records(send, sc, self.record_bytes)  # the count exchange is a host wait
+            self.host_wait_s += time.perf_counter() - t0
+            if e0 is not None:
+                self._ev["migrate_exchange"].append((e0, self._mark()))
             self._lib.check(L.fsim_migrate_unpack(h, C.c_void_p(recv.data_ptr() if nrecv else 0), nrecv))
             del recv  # allocated on self.stream: the caching allocator reuses it in stream order
-        self.migrated += sum(sc)
+        self._sent_exact += sum(sc)
+
+    @property
+    def migrated(self) -> int:
+        """Records this rank has sent so far (synchronises)."""
+        if self.exchange != "fixed":
+            return self._sent_exact
+        v = C.c_int64()
+        self._lib.check(self._lib.lib().fsim_migrate_stats(self.sim.handle, C.byref(v)))
+        return int(v.value)
 
     def density(self):
         L, h = self._lib.lib(), self.sim.handle
         self.migrate()
-        self._lib.check(L.fsim_density_begin(h))
-        ptrs = [C.c_void_p() for _ in range(4)]
-        nbytes = C.c_int64()
-        self._lib.check(L.fsim_halo_ptrs(h, *[C.byref(p) for p in ptrs], C.byref(nbytes)))
+        self._lib.check(L.fsim_density_begin(h))     # ... per-cell sums, boundary rows -> send buffers
+        t = self._halo
         with torch.cuda.stream(self.stream):
-            t = [_dev_tensor(p.value or 0, nbytes.value if p.value else 0, self.device) for p in ptrs]
-            exchange_halo(t[0], t[1], t[2], t[3], self.rank, self.world)
-        self._lib.check(L.fsim_density_end(h))
+            works = exchange_halo_begin(t[0], t[1], t[2], t[3], self.rank, self.world)
+        self._lib.check(L.fsim_density_interior(h))  # stencil on the rows that read no halo row, under the exchange
+        with torch.cuda.stream(self.stream):
+            e0 = self._mark() if self.comm_timing else None
+            exchange_halo_finish(works)
+            if e0 is not None:
+                self._ev["halo_exchange_exposed"].append((e0, self._mark()))
+        self._lib.check(L.fsim_density_end(h))       # halo rows in, stencil on the boundary tiles
+
+    def comm_ms(self, reset: bool = True) -> dict:
+        """Device time (ms, CUDA events on the frame's stream) spent in the exchanges since the last
+        call: the migration all-to-all (it waits for the slowest peer) and the part of the halo
+        exchange the interior stencil did not hide; plus the host time blocked in synchronisations."""
+        self.sim.sync()
+        out = {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in self._ev.items()}
+        out["host_wait"] = self.host_wait_s * 1e3
+        if reset:
+            for v in self._ev.values():
+                v.clear()
+            self.host_wait_s = 0.0
+        return out
 
     # -- EXTENSION: self-consistent field solve on the slab -------------------------------------------
     def solveFields(self, value: dict):
@@ -211,8 +322,17 @@ class SlabPusher:
     def render(self, out):
         return self.sim.render(out)
 
+    def check_digest(self):
+        return self.sim.check_digest()
+
     def render_async(self, out):
         return self.sim.render_async(out)
+
+    def render_rows_async(self, out):
+        return self.sim.render_rows_async(out)
+
+    def draw_canvas(self):
+        self.sim.draw_canvas()
 
     def set(self, value):
         self.sim.set(value)

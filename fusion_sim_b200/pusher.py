@@ -174,6 +174,15 @@ class CylindricalParticlePusher:
         check(lib().fsim_render_rgba8_async(self._h, ptr(out)))
         return out
 
+    def render_rows_async(self, out: np.ndarray) -> np.ndarray:
+        """A slab rank's own rows of the image, [slab_rows][nr][4], into `out` (pinned) on the copy stream."""
+        check(lib().fsim_render_rows_async(self._h, ptr(out)))
+        return out
+
+    def draw_canvas(self):
+        """The two canvas draws of out.density (empic.js:1497-1504) into the device-resident canvas."""
+        check(lib().fsim_draw_canvas(self._h))
+
     @property
     def canvas(self) -> np.ndarray:
         """RGBA8 image [nz][nr][4], top row first: what `drawImage(simulation.canvas)` shows."""
@@ -276,6 +285,15 @@ class CylindricalParticlePusher:
         ms = C.c_double()
         check(lib().fsim_elapsed_ms(self._h, a, b, C.byref(ms)))
         return ms.value
+
+    def check_digest(self) -> dict:
+        """Run invariants reduced on the device (fsim_check_digest): live particles, XOR and sum of
+        their ids, particles deposited on the owned rows, sum of the weight channel."""
+        out = np.zeros(4, np.uint64)
+        a = C.c_double()
+        check(lib().fsim_check_digest(self._h, ptr(out), C.byref(a)))
+        return {"particles": int(out[0]), "id_xor": int(out[1]), "id_sum": int(out[2]),
+                "deposited": int(out[3]), "sum_alpha": a.value}
 
     @property
     def launch_count(self) -> int:

@@ -19,6 +19,12 @@
  * Accessors return the NORMALISED device state (r in [0,1], z in [0,1]).
  * Device textures are addressed texel (i,j) -> i + j*nr (empic.js:1162): cell-indexed
  * accessors use that order.
+ *
+ * Lifetime of input arrays: every setter enqueues its host->device copy on the handle's stream and
+ * returns.  Arrays in pageable memory may be reused as soon as the call returns (the driver stages
+ * them); arrays in page-locked (pinned) memory are read asynchronously and must stay unchanged until
+ * the next fsim_sync() or accessor call.  Limits: particle slots per handle < 2^31, id_base + slots
+ * < 2^32, nr*nz < 2^31.
  */
 #ifndef FUSIONSIM_H
 #define FUSIONSIM_H
@@ -64,7 +70,9 @@ typedef struct fsim_spec {
     int32_t precision;      /* FSIM_F64 (default) | FSIM_F32 (mirrors RGBA32F storage)    */
     int32_t device;         /* CUDA device ordinal                                        */
     uint32_t flags;         /* FSIM_FLAG_*                                                */
-    int32_t sort_interval;  /* re-sort particles by cell every k step() calls, 0 = only in density() */
+    int32_t sort_interval;  /* physical re-sort of the particle storage by cell: density() does it every
+                             * k-th frame (0 = the default, 8); a loop of step() calls without density()
+                             * re-sorts after 4*k steps                                                */
     int64_t nparticles_total; /* if > 0: particle count, overrides nparticles^2           */
     int64_t capacity;       /* particle slots to allocate (>= count; 0 = count)           */
     int64_t slab_row0;      /* multi-GPU slab: first grid row (z index) owned             */
@@ -111,6 +119,10 @@ int fsim_render_rgba8(fsim_sim *sim, uint8_t *rgba); /* out.canvas :60 after :14
  * frame; `rgba` (pinned memory for a truly asynchronous copy) is complete after the next fsim_sync()
  * or after two further fsim_render_rgba8_async() calls (two device buffers alternate).           */
 int fsim_render_rgba8_async(fsim_sim *sim, uint8_t *rgba);
+int fsim_render_rows_async(fsim_sim *sim, uint8_t *rows); /* same, but `rows` holds only the owned rows
+                                                            * [slab_rows][nr][4] (a slab rank's share)      */
+int fsim_draw_canvas(fsim_sim *sim); /* the two canvas draws of out.density (:1497-1504) into the device-
+                                      * resident canvas, no read-back (the reference's canvas stays on the GPU) */
 int fsim_sort(fsim_sim *sim);      /* extension: re-sort particle storage by cell now          */
 int fsim_sync(fsim_sim *sim);      /* wait for the handle's stream                             */
 
@@ -165,6 +177,13 @@ int fsim_get_field(fsim_sim *sim, const char *name, double *out);
 int fsim_get_cell_count(fsim_sim *sim, uint32_t *out); /* [cells] particles deposited per cell   */
 int fsim_get_sink_mask(fsim_sim *sim, uint8_t *out);   /* [nr*nz] 1 = keep, 0 = absorb           */
 
+/* ---- run invariants (extension): reduced on the device, printed by bench.py with every line ---------
+ * out[0] live particles, out[1] XOR of their ids, out[2] sum of their ids mod 2^64, out[3] particles the
+ * last density() deposited on the owned rows; *sum_alpha (may be NULL) = sum of the weight channel of the
+ * per-cell sums over the owned rows.  Over all ranks of a slab run out[0..2] must equal those of the ids
+ * 0..N-1: the migration neither lost nor duplicated a particle.                                          */
+int fsim_check_digest(fsim_sim *sim, uint64_t *out /* [4] */, double *sum_alpha);
+
 /* ---- measurement hooks (extension) ----------------------------------------------------------- */
 /* Per-kernel device time (ms, CUDA events on the handle's stream) accumulated since the last
  * reset, and launch counts.  names: "push","hist","scan","scatter","cellsum","conv","render".   */
@@ -188,14 +207,34 @@ int64_t fsim_migrate_record_bytes(const fsim_sim *sim);
 int fsim_migrate_pack(fsim_sim *sim, const int64_t *row_bounds, int32_t nranks, int32_t self,
                       int64_t *send_counts /* host [nranks] */, void **send_buf_dev);
 int fsim_migrate_unpack(fsim_sim *sim, const void *recv_buf_dev, int64_t nrecv);
+/* ASYNCHRONOUS exchange (no host round trip in the frame).  fsim_migrate_setup fixes, once, the capacity in
+ * records of the region this rank sends to / receives from every other rank and returns the two device
+ * buffers and the byte size of every region (16-byte header holding the record count, then the records);
+ * region k of the send buffer goes to rank k, region k of the receive buffer comes from rank k.  From then
+ * on the handle keeps the exact particle count on the device.  Per frame: fsim_migrate_begin (pack; nothing
+ * is read back), the caller's all-to-all of the fixed-size regions on the handle's stream,
+ * fsim_migrate_end (arrivals fill the holes, compaction, new count: all from device-side counts).
+ * A region too small for a frame's leavers, or arrivals beyond the particle capacity, are reported by the
+ * next fsim_sync() as FSIM_ERR_RANGE (the state is then invalid; fsim_migrate_pack/_unpack is the exact,
+ * host-synchronising alternative for arbitrary volumes).                                               */
+int fsim_migrate_setup(fsim_sim *sim, const int64_t *row_bounds, int32_t nranks, int32_t self,
+                       const int64_t *send_caps /* [nranks] records */, const int64_t *recv_caps,
+                       void **send_buf_dev, void **recv_buf_dev,
+                       int64_t *send_region_bytes /* out [nranks] */, int64_t *recv_region_bytes);
+int fsim_migrate_begin(fsim_sim *sim);
+int fsim_migrate_end(fsim_sim *sim);
+int fsim_migrate_stats(fsim_sim *sim, int64_t *sent_total); /* records packed so far (synchronises) */
 /* Halo of the per-cell sums (5 rows each side) for the slab convolution. */
 int fsim_halo_ptrs(fsim_sim *sim, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi,
                    int64_t *bytes_each);
 /* measured alternative (replicated tables, index-sharded particles): the per-cell sums and counts of
  * every rank are added between fsim_density_begin and fsim_density_end; these are their addresses. */
 int fsim_cellsum_ptrs(fsim_sim *sim, void **sums, int64_t *sum_bytes, void **counts, int64_t *count_bytes);
-int fsim_density_begin(fsim_sim *sim); /* sort + per-cell sums (before the halo exchange)        */
-int fsim_density_end(fsim_sim *sim);   /* convolution + normalise + running average              */
+int fsim_density_begin(fsim_sim *sim); /* sort + per-cell sums + halo pack (before the halo exchange) */
+int fsim_density_interior(fsim_sim *sim); /* optional, slab mode: stencil + normalise + running average on the
+                                        * rows that read no halo row -- runs while the exchange is in flight */
+int fsim_density_end(fsim_sim *sim);   /* halo unpack, then the stencil on the remaining rows (all owned rows
+                                        * if fsim_density_interior was not called)                        */
 
 /* ---- dense weighted-Jacobi solver: matrix_webgl.makeSORIterative (matrix_webgl.js:35-711) ------------
  * "next" row N3 of SURVEY.md section 8f.  vec_length L = 4 (2^n_power)^2; A is [L][L] row-major.

@@ -481,10 +481,12 @@ static inline REAL ORC(quant8)(REAL v) /* v in [0,1] -> stored value k/255 */
 {
     return ORC(orc_floor)(v * RC(255.0) + RC(0.5));
 }
-void ORC(orc_render)(int64_t nr, int64_t nz, const REAL *B, const REAL *avg,
-                     uint8_t *rgba)
+void ORC(orc_render_mt)(int64_t nr, int64_t nz, const REAL *B, const REAL *avg,
+                        uint8_t *rgba, int nthreads)
 {
-    for (int64_t j = 0; j < nz; ++j)
+    int64_t j;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (j = 0; j < nz; ++j)
         for (int64_t i = 0; i < nr; ++i) {
             int64_t c = i + j * nr;
             REAL Bx = B[4 * c], By = B[4 * c + 1], Bz = B[4 * c + 2];
@@ -508,6 +510,11 @@ void ORC(orc_render)(int64_t nr, int64_t nz, const REAL *B, const REAL *avg,
                 o[q] = (uint8_t)ORC(quant8)(ORC(clamp01)(out));
             }
         }
+}
+
+void ORC(orc_render)(int64_t nr, int64_t nz, const REAL *B, const REAL *avg, uint8_t *rgba)
+{
+    ORC(orc_render_mt)(nr, nz, B, avg, rgba, 1);
 }
 
 #undef ORC_CAT2

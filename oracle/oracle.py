@@ -276,8 +276,8 @@ class OraclePusher:
     @property
     def canvas(self) -> np.ndarray:
         out = np.empty((self.nz, self.nr, 4), np.uint8)
-        self._f("orc_render")(C.c_int64(self.nr), C.c_int64(self.nz), _p(self.B),
-                              _p(self.moments01_avg), _p(out))
+        self._f("orc_render_mt")(C.c_int64(self.nr), C.c_int64(self.nz), _p(self.B),
+                                 _p(self.moments01_avg), _p(out), C.c_int(self.nthreads))
         return out
 
     # -- accessors (extension; same names as the product) --------------------------------

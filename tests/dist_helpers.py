@@ -43,8 +43,9 @@ def split_scene(sc, rank, world):
 class OracleSlab:
     """Numpy/oracle emulation of one slab rank, driven through dist.exchange_records/halo."""
 
-    def __init__(self, sc, rank, world):
+    def __init__(self, sc, rank, world, exchange="fixed"):
         from fusion_sim_b200.dist import slab_bounds
+        self.exchange = exchange
         from fusion_sim_b200.scenes import apply_scene
         from oracle.oracle import OraclePusher
         self.rank, self.world = rank, world
@@ -67,7 +68,8 @@ class OracleSlab:
         self.o.step()
 
     def migrate(self):
-        from fusion_sim_b200.dist import exchange_records
+        from fusion_sim_b200.dist import (HEADER_BYTES, exchange_records, exchange_regions, region_bytes,
+                                          region_capacities)
         from oracle.numpy_ref import tex
         o = self.o
         row = tex(o.position[:, 2].astype(np.float64), o.nz)
@@ -83,15 +85,39 @@ class OracleSlab:
         rec["id"] = self.ids[idx]
         rec["alive"] = o.position[idx, 3].astype(np.uint32)
         counts = [int((dest[leave] == k).sum()) for k in range(self.world)]
-        send = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy())
-        recv, nrecv = exchange_records(send, counts, REC.itemsize)
-        got = recv.numpy().view(REC)
+        if self.exchange == "exact":  # all-to-all-v sized by exchanged counts
+            send = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy())
+            recv, nrecv = exchange_records(send, counts, REC.itemsize)
+            got = recv.numpy().view(REC)
+        else:  # the wire format of the CUDA SlabPusher: fixed-capacity regions, counts in the headers
+            caps = region_capacities(self.rank, self.world, 4096, 1024)
+            nbytes = [region_bytes(c, REC.itemsize) for c in caps]
+            send = np.zeros(sum(nbytes), np.uint8)
+            off = first = 0
+            for k in range(self.world):
+                assert counts[k] <= caps[k], "test scene overflows the exchange region"
+                send[off:off + 4].view(np.uint32)[0] = counts[k]
+                body = rec[first:first + counts[k]].view(np.uint8).reshape(-1)
+                send[off + HEADER_BYTES:off + HEADER_BYTES + body.size] = body
+                off += nbytes[k]
+                first += counts[k]
+            recv = torch.zeros(sum(nbytes), dtype=torch.uint8)
+            exchange_regions(torch.from_numpy(send), nbytes, recv, nbytes)
+            buf, parts, off = recv.numpy(), [], 0
+            for k in range(self.world):
+                c = int(buf[off:off + 4].view(np.uint32)[0])
+                parts.append(buf[off + HEADER_BYTES:off + HEADER_BYTES + c * REC.itemsize].view(REC))
+                off += nbytes[k]
+            got = np.concatenate(parts)
+            nrecv = len(got)
         keep = ~leave
         pos = np.concatenate([o.position[keep], np.c_[got["state"][:, 0:3], got["alive"].astype(np.float64)]])
         vel = np.concatenate([o.velocity[keep], np.c_[got["state"][:, 3:6], np.ones(nrecv)]])
         rnd = np.concatenate([o.rand[keep], got["state"][:, 6:10]])
         ids = np.concatenate([self.ids[keep], got["id"]])
         self._resize(np.ascontiguousarray(pos), np.ascontiguousarray(vel), np.ascontiguousarray(rnd), ids)
+        self.sent = getattr(self, "sent", 0) + sum(counts)
+        self.sent_far = getattr(self, "sent_far", 0) + sum(c for k, c in enumerate(counts) if abs(k - self.rank) > 1)
         return sum(counts)
 
     def density(self):
@@ -186,22 +212,19 @@ def _gather(rank, world, parts):
 SOLVE = {"macro_weight": 5e11, "sweeps": 7, "omega": 0.9}  # per-frame field solve of the self-consistent tests
 
 
-def cpu_worker(rank, world, port, frames, result_path, solve=False):
+def cpu_worker(rank, world, port, frames, result_path, solve=False, exchange="fixed"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         sc = scene_for_dist()
-        s = OracleSlab(sc, rank, world)
-        moved = 0
+        s = OracleSlab(sc, rank, world, exchange)
         for _ in range(frames):
             s.step()
-            n0 = len(s.ids)
             s.density()
-            moved += abs(len(s.ids) - n0)
             if solve:
                 s.solveFields(SOLVE)
         parts = dict(ids=s.ids, pos=s.o.position, vel=s.o.velocity, rnd=s.o.rand,
-                     avg=s.owned(s.o.moments01_avg), cnt=s.owned(s.o.cell_count), moved=moved)
+                     avg=s.owned(s.o.moments01_avg), cnt=s.owned(s.o.cell_count), moved=s.sent, far=s.sent_far)
         if solve:
             parts.update(phi=s.owned(s.o.phi).reshape(-1), E=s.owned(s.o.E)[:, :3])
         out = _gather(rank, world, parts)
@@ -219,10 +242,10 @@ def assemble(out):
                 vel=np.concatenate([o["vel"] for o in out])[order][:, :3],
                 rnd=np.concatenate([o["rnd"] for o in out])[order],
                 avg=np.concatenate([o["avg"] for o in out]), cnt=np.concatenate([o["cnt"] for o in out]).reshape(-1),
-                moved=sum(o["moved"] for o in out))
+                moved=sum(o["moved"] for o in out), far=sum(o.get("far", 0) for o in out))
 
 
-def gpu_worker(rank, world, port, frames, result_path, solve=False):
+def gpu_worker(rank, world, port, frames, result_path, solve=False, exchange="fixed"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -231,7 +254,7 @@ def gpu_worker(rank, world, port, frames, result_path, solve=False):
         sc = scene_for_dist()
         loc, ids = split_scene(sc, rank, world)
         spec = dict(sc["spec"], device=rank)
-        s = SlabPusher(spec, loc, rank, world, halo_rows=8)
+        s = SlabPusher(spec, loc, rank, world, halo_rows=8, exchange=exchange)
         import ctypes as C
         gid = np.ascontiguousarray(ids.astype(np.uint64))
         s._lib.check(s._lib.lib().fsim_set_ids(s.sim.handle, gid.ctypes.data_as(C.c_void_p)))

@@ -1,8 +1,8 @@
-"""Multi-rank path.  CPU (gloo, world_size 2): the exchange logic of fusion_sim_b200/dist.py --
-slab bounds, all-to-all-v of particle records, 5-row halo of the per-cell sums -- driven with an
-oracle-backed rank, must reproduce the single-process oracle BIT FOR BIT (particles by global id,
-counts and running average by global cell).  GPU (nccl, >= 2 devices): the same check with the
-CUDA SlabPusher."""
+"""Multi-rank path.  CPU (gloo, world_size 2 and 4): the exchange logic of fusion_sim_b200/dist.py --
+slab bounds, the fixed-region all-to-all of particle records (and the exact all-to-all-v), 5-row halo
+of the per-cell sums -- driven with an oracle-backed rank, must reproduce the single-process oracle BIT
+FOR BIT (particles by global id, counts and running average by global cell).  GPU (nccl, 2 / 4 / 8
+devices): the same check with the CUDA SlabPusher."""
 import os
 import socket
 
@@ -48,18 +48,25 @@ def test_slab_bounds():
     assert b[0] == 0 and b[-1] == 10 and all(x < y for x, y in zip(b, b[1:]))
 
 
-def test_two_ranks_gloo_match_single_oracle(tmp_path):
+@pytest.mark.parametrize("world,exchange", [(2, "fixed"), (2, "exact"), (4, "fixed")])
+def test_ranks_gloo_match_single_oracle(tmp_path, world, exchange):
     path = str(tmp_path / "res.npz")
-    mp.spawn(dh.cpu_worker, args=(2, free_port(), FRAMES, path), nprocs=2, join=True)
+    mp.spawn(dh.cpu_worker, args=(world, free_port(), FRAMES, path, False, exchange), nprocs=world, join=True)
     check_against_single(path)
+    if world > 2:  # a respawn crossed more than one slab boundary: the all-to-all is not neighbour-only
+        assert int(np.load(path)["far"]) > 0
 
 
 @pytest.mark.gpu
-def test_two_gpus_nccl_match_single_oracle(tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("world,exchange", [(2, "fixed"), (2, "exact"), (4, "fixed"), (8, "fixed"), (8, "exact")])
+def test_gpus_nccl_match_single_oracle(tmp_path, world, exchange):
+    """world ranks on world GPUs against the single-process oracle, bit for bit.  With 4 and 8 slabs the
+    middle ranks have two neighbours (both halos), the source region (rows 28..36 of 64) lies outside
+    the cell table of the outer ranks, and particles absorbed there respawn into a NON-neighbouring slab."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     path = str(tmp_path / "res.npz")
-    mp.spawn(dh.gpu_worker, args=(2, free_port(), FRAMES, path), nprocs=2, join=True)
+    mp.spawn(dh.gpu_worker, args=(world, free_port(), FRAMES, path, False, exchange), nprocs=world, join=True)
     check_against_single(path)
 
 
@@ -72,11 +79,12 @@ def test_two_ranks_gloo_self_consistent_fields(tmp_path):
 
 
 @pytest.mark.gpu
-def test_two_gpus_nccl_self_consistent_fields(tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 4])
+def test_gpus_nccl_self_consistent_fields(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     path = str(tmp_path / "res.npz")
-    mp.spawn(dh.gpu_worker, args=(2, free_port(), FRAMES, path, True), nprocs=2, join=True)
+    mp.spawn(dh.gpu_worker, args=(world, free_port(), FRAMES, path, True), nprocs=world, join=True)
     check_against_single(path, solve=True)
 
 

@@ -68,7 +68,12 @@ def test_algorithmic_bytes_formula():
     sys.path.insert(0, ROOT)
     import bench
     # SURVEY.md section 8d worked example, C3 fp64: 2.72 GB particle state + cell table + tables;
-    # this build's cell record is 65 B instead of the survey's 97 B => 3.03 GB instead of 3.17 GB
+    # this build's cell record is 64 B + 1 sink BIT instead of the survey's 97 B => 3.02 GB instead of 3.17 GB
     b = bench.push_algorithmic_bytes(1 << 24, 2048 * 2048, "f64")
-    assert abs(b / 1e9 - 3.03) < 0.02
-    assert bench.push_algorithmic_bytes(1000, 0, "f32") == 82 * 1000 + 4 * (4 * 1024 * 1024 + 2 * 512 * 512)
+    assert abs(b / 1e9 - 3.02) < 0.02
+    # tables count at most what the sweep can touch: 1000 particles x 2 half-steps x one texel each
+    assert bench.push_algorithmic_bytes(1000, 0, "f32") == 82 * 1000 + 4 * (4 * 2000 + 2 * 2000)
+    # the demo scene (C1): 160 000 particles touch 320 000 of 1 Mi entropy texels and at most 320 000 cells
+    c1 = bench.push_algorithmic_bytes(160000, 320000, "f64")
+    assert c1 == 162 * 160000 + 64 * 320000 + 320000 / 8 + 8 * (4 * 320000 + 2 * 262144)
+    assert bench.xor_upto(6) == 0 ^ 1 ^ 2 ^ 3 ^ 4 ^ 5 ^ 6 and bench.xor_upto(-1) == 0

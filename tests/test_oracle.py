@@ -297,3 +297,27 @@ def test_canvas_matches_numpy_restatement():
     expect = out.reshape(o.nz, o.nr, 4)[::-1].astype(np.uint8)
     assert_same(img, expect, "canvas")
     assert img[..., 3].min() == 255
+
+
+def test_window_oracle_equals_the_whole_grid_oracle():
+    """tests/window_oracle.py (the checker of the C5-size GPU test) against the whole-grid oracle: counts,
+    per-cell sums and running average of a window at either edge and in the middle, with NaN and
+    out-of-range positions among the particles."""
+    from window_oracle import oracle_window
+    sc = small_scene(n=30000, nr=40, nz=96, speed=0.3, blob=(0.95, 0.99))
+    o = OraclePusher(sc["spec"], nthreads=2)
+    apply_scene(o, sc)
+    for frame in range(3):
+        prev = o.moments01_avg.copy()
+        o.step()
+        o.position[5::97, 2] = np.nan      # what a NaN respawn texel leaves behind
+        o.position[7::101, 2] = 1.25       # beyond the top edge: clipped sprite
+        o.density()
+        gp, gv = o.getPosition(), o.getVelocity()
+        for (w0, w1) in ((0, 16), (40, 56), (80, 96), (0, 96)):
+            a, b = w0 * o.nr, w1 * o.nr
+            cnt, S, avg, nsel = oracle_window(gp, gv, prev[a:b], o.nr, o.nz, w0, w1, threads=2)
+            assert nsel > 100
+            assert_same(cnt, o.cell_count[a:b], f"frame {frame} rows {w0}..{w1} counts")
+            assert_same(S, o.cell_sums[a:b], f"frame {frame} rows {w0}..{w1} sums")
+            assert_same(avg, o.moments01_avg[a:b], f"frame {frame} rows {w0}..{w1} running average")

@@ -1,5 +1,7 @@
 """Kernel tuning sweep on one B200 (not part of the product): builds the bench scene once and
-times frames under each FSIM_PUSH_VARIANT.  Usage: python tools/tune.py [workload] [precision]"""
+times frames under each push variant.  Needs the tuning build of the library:
+    tools/ab_build.sh tune WORK -DFSIM_TUNE
+    FSIM_LIB_PATH=tools/scratch/ab/tune/fusion_sim_b200/csrc/libfusionsim.so python tools/tune.py [workload] [precision] [variants]"""
 import json
 import os
 import sys
@@ -16,11 +18,13 @@ variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else li
 sc = bench.build_scene(workload, 0, 1)
 spec = dict(sc["spec"], precision=precision, flags=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 sim = makeCylindricalParticlePusher(spec)
+import ctypes as _C  # noqa: E402
+_L = _C.CDLL(os.environ["FSIM_LIB_PATH"])  # the tuning build exports fsim_tune_set
 apply_scene(sim, sc)
 names = ("push", "push2", "scan", "permute", "index_scatter", "cellsum", "cellsum_warp", "cellsum_heavy", "conv", "prepass")
 out = {}
 for v in variants:
-    os.environ["FSIM_PUSH_VARIANT"] = str(v)
+    _L.fsim_tune_set(int(v), 0)
     for _ in range(3):
         sim.step(); sim.density()
     sim.sync()
