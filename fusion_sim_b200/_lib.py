@@ -58,6 +58,7 @@ _SIGS = {
     "fsim_add_bz": (C.c_int, [_P, C.c_double]),
     "fsim_add_btheta": (C.c_int, [_P, C.c_double]),
     "fsim_add_spindle_cusp_plasma_field": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
+    "fsim_get_spindle": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "fsim_precalc": (C.c_int, [_P]),
     "fsim_step": (C.c_int, [_P]),
     "fsim_half_step": (C.c_int, [_P]),

@@ -347,7 +347,42 @@ int check_handle(fsim_sim *s)
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
     return FSIM_OK;
 }
-static int check(fsim_sim *s) { return check_handle(s); }
+// Second stream for the stencil and the canvas draws (common.cuh).  Created on first use, one priority level
+// above the main stream: its blocks are scheduled as soon as the sweep's retire.
+cudaStream_t post_begin(fsim_sim *s)
+{
+    if (s->spec.flags & FSIM_FLAG_SERIAL_POST) return s->stream;
+    if (!s->post_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&s->post_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return s->stream;
+        cudaEventCreateWithFlags(&s->post_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->post_done, cudaEventDisableTiming);
+    }
+    cudaEventRecord(s->post_fork, s->stream);
+    cudaStreamWaitEvent(s->post_stream, s->post_fork, 0);
+    return s->post_stream;
+}
+int post_end(fsim_sim *s)
+{
+    if (!s->post_stream || (s->spec.flags & FSIM_FLAG_SERIAL_POST)) return FSIM_OK;
+    FSIM_CUDA(cudaEventRecord(s->post_done, s->post_stream));
+    s->post_pending = true;
+    return FSIM_OK;
+}
+int post_join(fsim_sim *s)
+{
+    if (!s->post_pending) return FSIM_OK;
+    FSIM_CUDA(cudaStreamWaitEvent(s->stream, s->post_done, 0));
+    s->post_pending = false;
+    return FSIM_OK;
+}
+// every entry point except the frame's own (step, density, migrate, canvas draws) first joins the post stream
+static int check(fsim_sim *s)
+{
+    FSIM_TRY(check_handle(s));
+    return post_join(s);
+}
 // entry points that address particles by count: the asynchronous slab exchange keeps the exact count on
 // the device (settle_count synchronises and refreshes fsim_sim::n)
 static int check_n(fsim_sim *s)
@@ -476,6 +511,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     FSIM_TRY(dalloc(&s->oob, 1));
     FSIM_TRY(dalloc(&s->mscratch, MC_WORDS));
     FSIM_TRY(dalloc(&s->hole_flag, s->cap));
+    if (s->slab) FSIM_TRY(dalloc(&s->leavers, s->cap));
 
     // host-computed constant tables (libm): deposit footprint and quadrature cosines
     double shape64[FSIM_NSHAPE * FSIM_NSHAPE], shape32[FSIM_NSHAPE * FSIM_NSHAPE];
@@ -485,11 +521,7 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     // empic.js:317: the argument is formed in the shader's working precision, its cosine is the host libm's
     double costab[FSIM_NQUAD];
     float costab32[FSIM_NQUAD];
-    for (int k = 0; k < FSIM_NQUAD; ++k) {
-        costab[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);
-        const float a = (float)FSIM_PI_GLSL * ((float)k + 0.5f) / 1000.0f;
-        costab32[k] = (float)cos((double)a);
-    }
+    host_cos_tables(costab, costab32);
     FSIM_TRY(upload_costab(costab, costab32));
 
     // ids, default rand / entropy
@@ -522,7 +554,7 @@ static void free_all(fsim_sim *s)
     }
     void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
-                    s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf};
+                    s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf, s->leavers};
     for (void *p : ptrs) cudaFree(p);
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef);
     cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);
@@ -542,6 +574,12 @@ static void free_all(fsim_sim *s)
         if (s->copy_done[k]) cudaEventDestroy(s->copy_done[k]);
     }
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->post_stream) {
+        cudaStreamSynchronize(s->post_stream);
+        cudaStreamDestroy(s->post_stream);
+        cudaEventDestroy(s->post_fork);
+        cudaEventDestroy(s->post_done);
+    }
     if (s->stream && !s->ext_stream) cudaStreamDestroy(s->stream);
 }
 
@@ -628,6 +666,7 @@ static int planar_out(fsim_sim *s, const void *src, double *host)
 
 static int collect_timers(fsim_sim *s)
 {
+    FSIM_TRY(post_join(s));
     FSIM_CUDA(cudaStreamSynchronize(s->stream));
     for (auto &kv : s->timers) {
         for (auto &pe : kv.second.pending) {
@@ -883,12 +922,30 @@ int fsim_add_btheta(fsim_sim *s, double Bt)
     FSIM_TRY(check(s));
     return finish(s, launch_add_uniform(s, 2, Bt));
 }
-int fsim_add_spindle_cusp_plasma_field(fsim_sim *s, double, double, double)
+int fsim_add_spindle_cusp_plasma_field(fsim_sim *s, double r, double B_c, double beta_c)
 {
     FSIM_TRY(check(s));
-    // spindle.makeSpindleCuspPlasmaField references undefined names and a shader that does not
-    // compile (spindle.js:57,328,333,624,643,651): calling it throws in the reference too.
-    return fail(FSIM_ERR_UNSUPPORTED, "addSpindleCuspPlasmaField: spindle.js does not run in the reference");
+    // spindle.makeSpindleCuspPlasmaField does not run in the reference (spindle.js:57,328,333,624,643,651); this is
+    // the boundary solve it was written towards, specified in include/fusionsim.h (spindle.cu)
+    auto bad = [](double v) { return !(v == v) || isinf(v); };
+    if (bad(r) || r <= 0) return fail(FSIM_ERR_INVALID, ".r <- coil radius must be a positive number");
+    if (bad(B_c)) return fail(FSIM_ERR_INVALID, ".B_c <- must be a finite number");
+    if (bad(beta_c) || beta_c < 0 || beta_c > 1) return fail(FSIM_ERR_INVALID, ".beta_c <- must lie in [0, 1]");
+    return finish(s, spindle_solve(s, r, B_c, beta_c));
+}
+// what the last fsim_add_spindle_cusp_plasma_field found: element strengths x [256], node currents [257] (amperes),
+// the solved system A [256][256] and rhs [256]; checks of the solver and its final `diff` (matrix_webgl.js:687)
+int fsim_get_spindle(fsim_sim *s, double *x, double *currents, double *A, double *rhs, int32_t *iterations, double *diff)
+{
+    FSIM_TRY(check(s));
+    if (s->spindle_x.empty()) return fail(FSIM_ERR_STATE, "no spindle-cusp boundary solve on this handle yet");
+    if (x) memcpy(x, s->spindle_x.data(), sizeof(double) * s->spindle_x.size());
+    if (currents) memcpy(currents, s->spindle_currents.data(), sizeof(double) * s->spindle_currents.size());
+    if (A) memcpy(A, s->spindle_A.data(), sizeof(double) * s->spindle_A.size());
+    if (rhs) memcpy(rhs, s->spindle_rhs.data(), sizeof(double) * s->spindle_rhs.size());
+    if (iterations) *iterations = s->spindle_iterations;
+    if (diff) *diff = s->spindle_diff;
+    return FSIM_OK;
 }
 
 int fsim_precalc(fsim_sim *s)
@@ -1006,21 +1063,27 @@ static int physical_sort(fsim_sim *s)
 
 int fsim_half_step(fsim_sim *s)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     return finish(s, launch_push(s, false, 1));
 }
 
 int fsim_step(fsim_sim *s)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     // out.step, empic.js:1436-1469: B-buffers then A-buffers = two half-steps.  The second one also
     // emits the deposit prepass (sort key, sprite colour, histogram) of the new state for the
     // density() that follows.
     // Both are done in ONE sweep over the particle storage (push.cu, NH = 2).
     // After set({position}) the storage order says nothing about the new positions: put the storage into
     // cell order BEFORE the sweep (an unsorted sweep costs 6.8 ms instead of 2.9 at 64 Mi particles).
-    if (s->steps_since_sort >= (1 << 20) && s->n) FSIM_TRY(finish(s, physical_sort(s)));
-    FSIM_TRY(finish(s, launch_push(s, true, 2)));
+    // The sort itself is FUSED into the sweep: the binning leaves the index list, the sweep reads through it and
+    // writes the other copy of the storage in cell order (push.cu, PERM).
+    if (s->steps_since_sort >= (1 << 20) && s->n) {
+        FSIM_TRY(finish(s, bin_particles(s)));
+        s->resort_due = true;
+    }
+    FSIM_TRY(finish(s, launch_push(s, true, 2, s->resort_due)));
+    s->resort_due = false;  // (a binning that no longer matches the positions cannot be used: wait for the next one)
     s->steps_since_sort++;
     if (s->steps_since_sort >= 4 * sort_interval(s))  // push-only loops: keep the gather coherent
         FSIM_TRY(finish(s, physical_sort(s)));
@@ -1048,7 +1111,7 @@ int fsim_sort(fsim_sim *s)
 
 int fsim_density_begin(fsim_sim *s)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     FSIM_TRY(finish(s, bin_particles(s)));
     if (s->spec.flags & FSIM_FLAG_ATOMIC_DEPOSIT)
         FSIM_TRY(finish(s, launch_cellsum_atomic(s)));  // measured alternative, not bit-reproducible
@@ -1057,14 +1120,15 @@ int fsim_density_begin(fsim_sim *s)
     if (s->slab) FSIM_TRY(finish(s, launch_halo_pack(s)));  // own boundary rows -> send buffers (the caller's exchange starts here)
     // the deposit is done with the index list; now, every sort_interval frames, put the storage
     // itself into cell order for the pushes that follow
-    if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) FSIM_TRY(finish(s, launch_apply_perm(s)));
+    // -- fused into the next step()'s sweep, which reads through this frame's index list (no pass of its own)
+    if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) s->resort_due = true;
     s->conv_interior_done = false;
     return FSIM_OK;
 }
 // slab mode: the stencil on the rows that need no halo row, to run WHILE the halo exchange is in flight
 int fsim_density_interior(fsim_sim *s)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     if (!s->slab) return FSIM_OK;
     FSIM_TRY(finish(s, launch_conv_rows(s, 1)));
     s->conv_interior_done = true;
@@ -1072,7 +1136,7 @@ int fsim_density_interior(fsim_sim *s)
 }
 int fsim_density_end(fsim_sim *s)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     if (s->slab) FSIM_TRY(finish(s, launch_halo_unpack(s)));  // neighbours' boundary rows -> halo rows of the sums
     const int part = s->conv_interior_done ? 2 : 0;
     s->conv_interior_done = false;
@@ -1104,7 +1168,7 @@ int fsim_render_rgba8(fsim_sim *s, uint8_t *rgba)
     if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
     const size_t bytes = 4 * (size_t)s->ncell_global;
     FSIM_TRY(finish(s, ensure_stage(s, bytes)));
-    FSIM_TRY(finish(s, launch_render(s, (uint8_t *)s->stage)));
+    FSIM_TRY(finish(s, launch_render(s, (uint8_t *)s->stage, s->stream)));
     // canvas rows run top-down (row nz-1-j): the owned rows [own0, own0+own_rows) are one block;
     // a slab rank fills only its block of the caller's full-size image.
     const size_t off = 4 * (size_t)s->nr * (size_t)(s->nz - s->own0 - s->own_rows);
@@ -1129,9 +1193,11 @@ static int canvas_draw(fsim_sim *s, uint8_t *host, bool own_rows_only)
     const int k = (s->canvas_slot ^= 1);
     if (s->copy_pending[k]) FSIM_CUDA(cudaEventSynchronize(s->copy_done[k]));  // image k is free again
     s->copy_pending[k] = false;
-    FSIM_TRY(finish(s, launch_render(s, s->canvas_dev[k])));
+    const cudaStream_t ps = post_begin(s);  // after the stencil, on its stream: the next sweep does not wait for the image
+    FSIM_TRY(finish(s, launch_render(s, s->canvas_dev[k], ps)));
+    FSIM_TRY(post_end(s));
     if (!host) return FSIM_OK;
-    FSIM_CUDA(cudaEventRecord(s->render_done[k], s->stream));
+    FSIM_CUDA(cudaEventRecord(s->render_done[k], ps));
     FSIM_CUDA(cudaStreamWaitEvent(s->copy_stream, s->render_done[k], 0));
     const size_t off = 4 * (size_t)s->nr * (size_t)(s->nz - s->own0 - s->own_rows);
     const size_t len = 4 * (size_t)s->nr * (size_t)s->own_rows;
@@ -1143,14 +1209,14 @@ static int canvas_draw(fsim_sim *s, uint8_t *host, bool own_rows_only)
 
 int fsim_render_rgba8_async(fsim_sim *s, uint8_t *rgba)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
     return canvas_draw(s, rgba, false);
 }
 // slab mode: `rows` holds only this rank's rows [own_rows][nr][4] (top row first) -- small enough to pin
 int fsim_render_rows_async(fsim_sim *s, uint8_t *rows)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     if (!rows) return fail(FSIM_ERR_INVALID, "null array");
     return canvas_draw(s, rows, true);
 }
@@ -1158,7 +1224,7 @@ int fsim_render_rows_async(fsim_sim *s, uint8_t *rows)
 // device-resident canvas, without a read-back: where the reference leaves its canvas, too
 int fsim_draw_canvas(fsim_sim *s)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_handle(s));
     return canvas_draw(s, nullptr, false);
 }
 

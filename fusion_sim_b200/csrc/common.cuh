@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include <map>
@@ -17,6 +18,18 @@
 
 #include "../../include/fsim_constants.h"
 #include "../../include/fusionsim.h"
+
+// Debug build (make EXTRA=-DFSIM_DEBUG_BOUNDS; tools/ab_build.sh dbg WORK -DFSIM_DEBUG_BOUNDS): every index that
+// is READ FROM MEMORY before it addresses the particle storage or a list (perm[], holes, leavers, targets,
+// sources, cursors) is checked on the device; a violation traps the kernel and the next API call fails with
+// FSIM_ERR_CUDA.  The pool forbids compute-sanitizer, this is its substitute: the GPU test-suite is run once
+// per round against this build (profiles/).  Compiled out of the product.
+#ifdef FSIM_DEBUG_BOUNDS
+#include <assert.h>
+#define FSIM_ASSERT(cond) assert(cond)
+#else
+#define FSIM_ASSERT(cond) ((void)0)
+#endif
 
 namespace fsim {
 
@@ -98,6 +111,13 @@ struct fsim_sim {
     int nsm = 148;            // multiprocessors of the device (grid sizes of the grid-stride kernels)
     uint32_t smem_opt_in = 0; // kernels whose dynamic shared-memory limit was raised ON THIS DEVICE (one bit each)
     cudaStream_t stream = nullptr;
+    // stencil + canvas draws ("post" work: reads the per-cell sums, writes the running average and the canvas)
+    // run on a second, higher-priority stream so that they overlap the NEXT frame's sweep: the sweep is
+    // bound by DRAM, the stencil by the fp64 pipe.  post_begin forks it off the main stream, post_join makes the
+    // main stream wait for it (before anything that reads the average / writes the sums or B).
+    cudaStream_t post_stream = nullptr;
+    cudaEvent_t post_fork = nullptr, post_done = nullptr;
+    bool post_pending = false;
     bool ext_stream = false;  // `stream` belongs to the caller (fsim_set_stream): collectives are stream-ordered
     bool sticky_error = false;
 
@@ -141,6 +161,7 @@ struct fsim_sim {
     bool binned = false;          // starts[] and perm[] match the current positions
     bool ever_sorted = false;
     int steps_since_sort = 0;     // step() calls since the last physical sort
+    bool resort_due = false;      // density() found the storage due for a re-sort: the next step() sweeps through perm[]
 
     // tables
     void *cellrec = nullptr;   // [ncell_local][RECSTRIDE]
@@ -173,6 +194,7 @@ struct fsim_sim {
     size_t stage_bytes = 0;
     void *migr = nullptr;          // packed migration records (send side)
     size_t migr_bytes = 0;
+    uint32_t *leavers = nullptr;   // [cap], slab mode: slots whose row left the slab (written by the sweep), then the hole list
     uint32_t *mscratch = nullptr;  // [MC_WORDS] small counters of the migration kernels (enum MC_*)
     uint8_t *hole_flag = nullptr;  // [cap] 1 = slot vacated by a leaver
     uint32_t nholes_host = 0;
@@ -185,7 +207,12 @@ struct fsim_sim {
     int n_slot = 0;
     void *halo_buf = nullptr;      // slab mode: [send_lo | send_hi | recv_lo | recv_hi], each 4 x 5 x nr reals
     bool conv_interior_done = false;  // fsim_density_interior ran: fsim_density_end convolves only the boundary tiles
-    bool have_leavers = false;     // perm[0..*nleavers) lists the slots whose row left the slab (emitted by the push)
+    bool have_leavers = false;     // leavers[0..*nleavers) lists the slots whose row left the slab (emitted by the push)
+
+    // spindle-cusp boundary solve (spindle.cu): what the last addSpindleCuspPlasmaField() found
+    std::vector<double> spindle_x, spindle_currents, spindle_A, spindle_rhs;
+    int spindle_iterations = 0;
+    double spindle_diff = 0.0;
 
     // measurement
     bool timing = false;
@@ -211,7 +238,8 @@ struct Bracket {
     fsim_sim *s;
     KernelTimer *t = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    Bracket(fsim_sim *sim, const char *name) : s(sim)
+    cudaStream_t st;
+    Bracket(fsim_sim *sim, const char *name, cudaStream_t stream = nullptr) : s(sim), st(stream ? stream : sim->stream)
     {
         s->launches++;
         KernelTimer &kt = s->timers[name];
@@ -220,13 +248,13 @@ struct Bracket {
             t = &kt;
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
-            cudaEventRecord(e0, s->stream);
+            cudaEventRecord(e0, st);
         }
     }
     ~Bracket()
     {
         if (t) {
-            cudaEventRecord(e1, s->stream);
+            cudaEventRecord(e1, st);
             t->pending.emplace_back(e0, e1);
         }
     }
@@ -325,6 +353,16 @@ __device__ __forceinline__ void warp_runs(uint32_t key, int lane, int &leader, u
 extern int g_push_variant, g_conv_variant;  // tuning build only (fsim_tune_set)
 #endif
 
+// empic.js:317: the quadrature angle is formed in the shader's working precision, its cosine is the host libm's
+inline void host_cos_tables(double *c64, float *c32)
+{
+    for (int k = 0; k < FSIM_NQUAD; ++k) {
+        c64[k] = cos(FSIM_PI_GLSL * ((double)k + 0.5) / 1000.0);
+        const float a = (float)FSIM_PI_GLSL * ((float)k + 0.5f) / 1000.0f;
+        c32[k] = (float)cos((double)a);
+    }
+}
+
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // exact particle count inside a kernel: the device word when the exchange is asynchronous, else the host's n
@@ -336,7 +374,7 @@ __device__ __forceinline__ int64_t live_count(const uint32_t *n_dev, int64_t n_h
 }
 
 // kernels / host stages implemented in the other translation units
-int launch_push(fsim_sim *s, bool with_hist, int nhalf);  // nhalf half-steps in one sweep
+int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort = false);  // nhalf half-steps in one sweep (+ fused re-sort)
 int launch_keys(fsim_sim *s);      // deposit prepass from the stored state: key, colour, histogram
 int launch_bin(fsim_sim *s);       // scan + index scatter -> starts[], perm[]
 int launch_apply_perm(fsim_sim *s);  // physical re-sort: storage <- storage[perm]
@@ -347,12 +385,16 @@ int launch_halo_pack(fsim_sim *s);
 int launch_halo_unpack(fsim_sim *s);
 int launch_conv_rows(fsim_sim *s, int part);  // part 0: all owned rows, 1: rows that need no halo, 2: the rest
 int settle_count(fsim_sim *s);               // asynchronous exchange: make fsim_sim::n exact again (synchronises)
-int check_handle(fsim_sim *s);               // sticky-error / device check of every entry point
+int check_handle(fsim_sim *s);               // sticky-error / device check of every entry point (does not join the post stream)
+cudaStream_t post_begin(fsim_sim *s);        // fork: the post stream sees everything enqueued on the main stream so far
+int post_end(fsim_sim *s);                   // marks the end of the post work enqueued since post_begin
+int post_join(fsim_sim *s);                  // the main stream waits for pending post work
 int launch_precalc(fsim_sim *s);
 int launch_expand_records(fsim_sim *s, double *dev_out);  // [cells][12] R1 R2 R3 A as doubles
 int launch_add_loop(fsim_sim *s, double R, double Z, double I);
 int launch_add_uniform(fsim_sim *s, int kind, double val);
-int launch_render(fsim_sim *s, uint8_t *dev_rgba);
+int spindle_solve(fsim_sim *s, double coil_r, double B_c, double beta_c);  // spindle.cu
+int launch_render(fsim_sim *s, uint8_t *dev_rgba, cudaStream_t st);
 int ensure_fieldsolve(fsim_sim *s);
 int launch_charge_source(fsim_sim *s, const void *dens_a, double rho_scale);
 int launch_relax(fsim_sim *s, int sweeps, double omega);  // 1..4 sweeps, one launch

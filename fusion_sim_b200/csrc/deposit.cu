@@ -42,6 +42,7 @@ struct CellSumArgs {
     uint32_t *heavy_list, *heavy_n;   // heavy_n[0]: cells for the block path, heavy_n[1]: for the warp path
     uint32_t *medium_list;
     int64_t ncell;
+    int64_t n;        // live slots (upper bound), for the debug-build index checks
     int nr, nz, row0;
     // scratch of the block-per-cell path (the idle half of the particle double buffer)
     uint32_t *sid, *sidx;
@@ -57,6 +58,8 @@ __device__ __forceinline__ void cell_small(const CellSumArgs<Real> &a, uint32_t 
     uint32_t pp[KR], ii[KR];  // pp: slot | clipped flag (bit 31), as index_scatter stored it
 #pragma unroll
     for (int j = 0; j < KR; ++j) pp[j] = (uint32_t)j < k ? a.perm[s + j] : KEY_CLIPPED;
+#pragma unroll
+    for (int j = 0; j < KR; ++j) FSIM_ASSERT((uint32_t)j >= k || ((int64_t)s + j < a.n && (int64_t)(pp[j] & KEY_MASK) < a.n));
 #pragma unroll
     for (int j = 0; j < KR; ++j) ii[j] = (uint32_t)j < k ? a.id[pp[j] & KEY_MASK] : 0xffffffffu;
 #pragma unroll
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(128) cellsum_warp_kernel(const CellSumArgs<Rea
         for (int q = 0; q < NQ; ++q) {
             const uint32_t j = q * 32 + lane;
             pp[q] = (q * 32 < k && j < k) ? a.perm[(size_t)s + j] : KEY_CLIPPED;
+            FSIM_ASSERT(!(q * 32 < k && j < k) || ((int64_t)s + j < a.n && (int64_t)(pp[q] & KEY_MASK) < a.n));
             ii[q] = (q * 32 < k && j < k) ? a.id[pp[q] & KEY_MASK] : 0xffffffffu;
             rank[q] = 0;
         }
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
     uint32_t *sid = a.sid + s, *sidx = a.sidx + s;
     for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
         const uint32_t pf = a.perm[(size_t)s + j];
+        FSIM_ASSERT((int64_t)s + j < a.n && (int64_t)(pf & KEY_MASK) < a.n);
         sid[j] = a.id[pf & KEY_MASK];
         sidx[j] = j | (pf & KEY_CLIPPED);
     }
@@ -261,6 +266,7 @@ cellsum_atomic_kernel(const uint32_t *__restrict__ key, const Real *__restrict__
 
 int launch_cellsum_atomic(fsim_sim *s)
 {
+    FSIM_TRY(post_join(s));  // the previous frame's stencil reads the sums
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
         FSIM_CUDA(cudaMemsetAsync(s->cellsum, 0, sizeof(Real) * 4 * s->plane, s->stream));
@@ -277,6 +283,7 @@ int launch_cellsum_atomic(fsim_sim *s)
 
 int launch_cellsum(fsim_sim *s)
 {
+    FSIM_TRY(post_join(s));  // the previous frame's stencil (second stream) reads the sums this pass overwrites
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
         const int cur = s->cur, alt = s->cur ^ 1;
@@ -293,6 +300,7 @@ int launch_cellsum(fsim_sim *s)
         a.heavy_list = s->heavy_list; a.heavy_n = s->heavy_n;
         a.medium_list = s->medium_list;
         a.ncell = s->ncell_local;
+        a.n = s->n;
         a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0;
         a.sid = (uint32_t *)s->part[alt][4];
         a.sidx = (uint32_t *)s->part[alt][5];
@@ -520,7 +528,7 @@ int upload_shape(const double *shape64, const double *shape32)
 // is read); 2: the others (first tile row, last one or two).  Parts 1 and 2 are disjoint and cover part 0:
 // the running average is updated in place, so every cell must be visited exactly once per density().
 template <typename Real, int CSTRIP, int CT_J>
-static int conv_launch(fsim_sim *s, ConvArgs<Real> a, int part)
+static int conv_launch(fsim_sim *s, ConvArgs<Real> a, int part, cudaStream_t st)
 {
     constexpr int CS_J = CT_J + 2 * CH;
     if (s->tm_sums_rows != CS_J) FSIM_TRY(make_sums_tensor_map(s, CS_J));  // the box height is part of the map
@@ -542,7 +550,7 @@ static int conv_launch(fsim_sim *s, ConvArgs<Real> a, int part)
     if (part == 2) { a.skip0 = in0; a.skip1 = in1; rows_of_tiles = ntile - (in1 - in0); }
     if (rows_of_tiles <= 0) return FSIM_OK;
     dim3 grid((s->nr + CT_I - 1) / CT_I, rows_of_tiles);
-    conv_kernel<Real, CSTRIP, CT_J><<<grid, block, smem, s->stream>>>(*reinterpret_cast<const CUtensorMap *>(s->tm_sums), a);
+    conv_kernel<Real, CSTRIP, CT_J><<<grid, block, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(s->tm_sums), a);
     FSIM_CUDA(cudaGetLastError());
     return FSIM_OK;
 }
@@ -555,20 +563,23 @@ int launch_conv_rows(fsim_sim *s, int part)
         a.mom = (Real *)s->mom; a.norm = (Real *)s->norm; a.avg = (Real *)s->avg;
         a.nr = s->nr; a.pitch = s->pitch; a.plane = s->plane;
         a.j0 = s->own0 - s->row0; a.j1 = a.j0 + s->own_rows;
-        Bracket b(s, "conv");
+        // on the second stream: overlaps the next frame's sweep (DRAM-bound) with this fp64-bound stencil
+        const cudaStream_t st = post_begin(s);
+        struct End { fsim_sim *s; ~End() { post_end(s); } } end{s};
+        Bracket b(s, "conv", st);
 #ifdef FSIM_TUNE
         switch (g_conv_variant) {  // tuning build only (tools/tune.py)
-        case 1: return conv_launch<Real, 8, 16>(s, a, part);
-        case 2: return conv_launch<Real, 8, 32>(s, a, part);
-        case 3: return conv_launch<Real, 4, 32>(s, a, part);
-        case 4: return conv_launch<Real, 2, 16>(s, a, part);
-        case 5: return conv_launch<Real, 16, 16>(s, a, part);
-        case 6: return conv_launch<Real, 16, 32>(s, a, part);
-        case 8: return conv_launch<Real, 4, 16>(s, a, part);
+        case 1: return conv_launch<Real, 8, 16>(s, a, part, st);
+        case 2: return conv_launch<Real, 8, 32>(s, a, part, st);
+        case 3: return conv_launch<Real, 4, 32>(s, a, part, st);
+        case 4: return conv_launch<Real, 2, 16>(s, a, part, st);
+        case 5: return conv_launch<Real, 16, 16>(s, a, part, st);
+        case 6: return conv_launch<Real, 16, 32>(s, a, part, st);
+        case 8: return conv_launch<Real, 4, 16>(s, a, part, st);
         default: break;
         }
 #endif
-        return conv_launch<Real, 8, 8>(s, a, part);  // 0.65 ms at C5 fp64 against 0.86 for <4,16>, 0.69 <8,16>, 0.88 <16,32>
+        return conv_launch<Real, 8, 8>(s, a, part, st);  // 0.65 ms at C5 fp64 against 0.86 for <4,16>, 0.69 <8,16>, 0.88 <16,32>
     });
 }
 

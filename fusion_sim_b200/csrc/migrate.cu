@@ -63,6 +63,7 @@ struct PackArgs {
     uint32_t *cursor;        // [nranks] running offsets (records) into buf, initialised to the group starts
     const uint32_t *list;    // slots that leave (they become the holes)
     uint32_t nlist;
+    int64_t n;               // live slots (debug-build index checks)
     uint8_t *hole_flag;
     const uint32_t *key;     // non-null: keep the sort histogram consistent
     uint32_t *counts;
@@ -76,8 +77,10 @@ __global__ void __launch_bounds__(256) migrate_pack_kernel(const PackArgs<Real> 
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nlist) return;
     const size_t p = a.list[t];
+    FSIM_ASSERT((int64_t)p < a.n);
     const int d = dest_rank(a.rb, a.src[AZ][p], a.nz);
     const uint32_t slot = atomicAdd(a.cursor + d, 1u);
+    FSIM_ASSERT(slot < a.nlist);  // the groups were sized by migrate_count_kernel
     unsigned char *rec = a.buf + (size_t)slot * (NPART_ARRAYS * sizeof(Real) + 8);
     Real *r = reinterpret_cast<Real *>(rec);
 #pragma unroll
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(256) migrate_unpack_kernel(const UnpackArgs<Re
     size_t slot;
     if (i < (int64_t)a.nholes) {
         slot = a.holes[i];
+        FSIM_ASSERT((int64_t)slot < a.n_old);
         a.hole_flag[slot] = 0;
     } else {
         slot = (size_t)(a.n_old + (i - (int64_t)a.nholes));
@@ -166,7 +170,8 @@ struct MoveArgs {
     uint8_t *alive;
     uint32_t *id;
     const uint32_t *targets, *sources;
-    const uint32_t *ntargets;
+    const uint32_t *ntargets, *nsources;
+    int64_t n_old;  // slots in use before the compaction (upper bound; debug-build index checks)
     uint32_t *key;  // non-null: the per-slot prepass data moves along
     Real *dcol[2];
 };
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(256) compact_move_kernel(const MoveArgs<Real> 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *m.ntargets) return;
     const size_t d = m.targets[i], s = m.sources[i];
+    FSIM_ASSERT(i < *m.nsources && (int64_t)d < m.n_old && (int64_t)s < m.n_old && d < s);  // a tail particle moves DOWN into a hole
 #pragma unroll
     for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k][d] = m.a[k][s];
     m.alive[d] = m.alive[s];
@@ -214,6 +220,7 @@ struct PackFixedArgs {
     unsigned char *send;     // regions of PlanDev::send_off, each: 16-byte header + records
     const uint32_t *list;    // leaver list (perm[]), length ctr[MC_NLEAVERS]
     uint32_t *holes;         // packed leavers' slots
+    uint32_t holes_cap;      // entries `holes` can take (= sum of the send capacities)
     uint8_t *hole_flag;
     uint32_t *ctr;           // mscratch
     const uint32_t *key;     // non-null: keep the sort histogram consistent
@@ -229,6 +236,7 @@ __global__ void __launch_bounds__(256) migrate_pack_fixed_kernel(const PackFixed
     const uint32_t nlist = a.ctr[MC_NLEAVERS];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nlist; t += gridDim.x * blockDim.x) {
         const size_t p = a.list[t];
+        FSIM_ASSERT(p < a.ctr[MC_NLIVE]);
         const int d = dest_rank_plan(pl, a.src[AZ][p], a.nz);
         const uint32_t slot = atomicAdd(a.ctr + MC_CURSOR + d, 1u);
         if (d == pl.self || slot >= pl.send_cap[d]) {  // region full: the particle stays, the run is flagged invalid
@@ -242,7 +250,9 @@ __global__ void __launch_bounds__(256) migrate_pack_fixed_kernel(const PackFixed
         uint32_t *u = reinterpret_cast<uint32_t *>(rec + NPART_ARRAYS * sizeof(Real));
         u[0] = a.id[p];
         u[1] = a.alive[p];
-        a.holes[atomicAdd(a.ctr + MC_NHOLES, 1u)] = (uint32_t)p;
+        const uint32_t hslot = atomicAdd(a.ctr + MC_NHOLES, 1u);
+        FSIM_ASSERT(hslot < a.holes_cap);
+        a.holes[hslot] = (uint32_t)p;
         a.hole_flag[p] = 1;
         if (a.key) atomicSub(a.counts + (a.key[p] & KEY_MASK), 1u);
     }
@@ -334,6 +344,7 @@ __global__ void __launch_bounds__(256) migrate_unpack_fixed_kernel(const UnpackF
     } else {
         slot = (size_t)a.ctr[MC_NOLD] + (i - nholes);
     }
+    FSIM_ASSERT(slot < a.ctr[MC_NNEW] || slot < a.ctr[MC_NOLD]);
     const unsigned char *rec = a.recv + pl.recv_off[k] + MIGRATE_HEADER_BYTES + (size_t)j * REC;
     const Real *r = reinterpret_cast<const Real *>(rec);
     Real v[NPART_ARRAYS];
@@ -368,10 +379,19 @@ compact_lists_fixed_kernel(const uint32_t *__restrict__ holes, const uint8_t *__
     const int64_t n_new = ctr[MC_NNEW], n_old = ctr[MC_NOLD];
     if (t < nholes - nrecv) {
         const uint32_t slot = holes[nrecv + t];
-        if ((int64_t)slot < n_new) targets[atomicAdd(ctr + MC_NTARGETS, 1u)] = slot;
+        FSIM_ASSERT((int64_t)slot < n_old);
+        if ((int64_t)slot < n_new) {
+            const uint32_t at = atomicAdd(ctr + MC_NTARGETS, 1u);
+            FSIM_ASSERT(at < span_max);
+            targets[at] = slot;
+        }
     }
     const int64_t q = n_new + t;
-    if (q < n_old && !hole_flag[q]) sources[atomicAdd(ctr + MC_NSOURCES, 1u)] = (uint32_t)q;
+    if (q < n_old && !hole_flag[q]) {
+        const uint32_t at = atomicAdd(ctr + MC_NSOURCES, 1u);
+        FSIM_ASSERT(at < span_max);
+        sources[at] = (uint32_t)q;
+    }
 }
 
 // clear the flags of the vacated slots, publish the new count, reset the per-frame counters
@@ -456,13 +476,13 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
         if (!s->have_leavers) {  // the push did not emit the list: scan the positions
             FSIM_CUDA(cudaMemsetAsync(nlist_d, 0, sizeof(uint32_t), s->stream));
             find_leavers_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
-                (const Real *)s->part[c][AZ], s->n, nullptr, s->nz, s->own0, s->own_rows, s->perm, nlist_d);
+                (const Real *)s->part[c][AZ], s->n, nullptr, s->nz, s->own0, s->own_rows, s->leavers, nlist_d);
             FSIM_CUDA(cudaGetLastError());
             s->launches++;
         }
         s->have_leavers = false;
         // destination counts of the leavers and the list length: ONE read-back per frame
-        migrate_count_kernel<Real><<<s->nsm * 2, 256, 0, s->stream>>>((const Real *)s->part[c][AZ], s->perm, nlist_d, s->nz, rb,
+        migrate_count_kernel<Real><<<s->nsm * 2, 256, 0, s->stream>>>((const Real *)s->part[c][AZ], s->leavers, nlist_d, s->nz, rb,
                                                                    scr + MC_COUNTS);
         FSIM_CUDA(cudaGetLastError());
         s->launches++;
@@ -490,7 +510,7 @@ int fsim_migrate_pack(fsim_sim *s, const int64_t *row_bounds, int32_t nranks, in
         a.id = s->pid[c];
         a.buf = (unsigned char *)s->migr;
         a.cursor = scr + MC_CURSOR;
-        a.list = s->perm; a.nlist = nlist;
+        a.list = s->leavers; a.nlist = nlist; a.n = s->n;
         a.hole_flag = s->hole_flag;
         a.key = keys ? s->key : nullptr;
         a.counts = s->counts;
@@ -531,7 +551,7 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
             for (int k = 0; k < NPART_ARRAYS; ++k) a.dst[k] = (Real *)s->part[c][k];
             a.alive = s->alive[c]; a.id = s->pid[c];
             a.buf = (const unsigned char *)recv_buf_dev;
-            a.holes = s->perm; a.hole_flag = s->hole_flag;
+            a.holes = s->leavers; a.hole_flag = s->hole_flag;
             a.nholes = (uint32_t)nholes; a.n_old = n_old; a.nrecv = nrecv;
             a.key = s->keys_valid ? s->key : nullptr;
             a.counts = s->counts;
@@ -544,15 +564,16 @@ int fsim_migrate_unpack(fsim_sim *s, const void *recv_buf_dev, int64_t nrecv)
         }
         if (nholes > nrecv) {  // shrink: move tail particles into the remaining holes
             const int64_t span = std::max<int64_t>(nholes - nrecv, n_old - n_new);
-            // target/source lists: the tail of perm[] beyond the hole list (both are tiny)
-            uint32_t *targets = s->perm + s->cap / 2, *sources = s->perm + s->cap / 2 + s->cap / 4;
+            // target/source lists: the upper half of the leaver buffer, beyond the hole list (both are tiny)
+            uint32_t *targets = s->leavers + s->cap / 2, *sources = s->leavers + s->cap / 2 + s->cap / 4;
             compact_lists_kernel<<<grid_for(span, 256), 256, 0, s->stream>>>(
-                s->perm, (uint32_t)nholes, (uint32_t)nrecv, s->hole_flag, n_new, n_old, targets,
+                s->leavers, (uint32_t)nholes, (uint32_t)nrecv, s->hole_flag, n_new, n_old, targets,
                 scr + MC_NTARGETS, sources, scr + MC_NSOURCES);
             MoveArgs<Real> m;
             for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k] = (Real *)s->part[c][k];
             m.alive = s->alive[c]; m.id = s->pid[c];
-            m.targets = targets; m.sources = sources; m.ntargets = scr + MC_NTARGETS;
+            m.targets = targets; m.sources = sources; m.ntargets = scr + MC_NTARGETS; m.nsources = scr + MC_NSOURCES;
+            m.n_old = n_old;
             m.key = s->keys_valid ? s->key : nullptr;
             for (int q = 0; q < 2; ++q) m.dcol[q] = (Real *)s->dcol[q];
             compact_move_kernel<Real><<<grid_for(nholes - nrecv, 256), 256, 0, s->stream>>>(m);
@@ -667,7 +688,7 @@ int fsim_migrate_begin(fsim_sim *s)
             FSIM_CUDA(cudaMemsetAsync(ctr + MC_NLEAVERS, 0, sizeof(uint32_t), s->stream));
             if (s->n) {
                 find_leavers_kernel<Real><<<grid_for(s->n, 256), 256, 0, s->stream>>>(
-                    (const Real *)s->part[c][AZ], s->n, ctr + MC_NLIVE, s->nz, s->own0, s->own_rows, s->perm, ctr + MC_NLEAVERS);
+                    (const Real *)s->part[c][AZ], s->n, ctr + MC_NLIVE, s->nz, s->own0, s->own_rows, s->leavers, ctr + MC_NLEAVERS);
                 FSIM_CUDA(cudaGetLastError());
                 s->launches++;
             }
@@ -677,7 +698,7 @@ int fsim_migrate_begin(fsim_sim *s)
         PackFixedArgs<Real> a;
         for (int k = 0; k < NPART_ARRAYS; ++k) a.src[k] = (const Real *)s->part[c][k];
         a.alive = s->alive[c]; a.id = s->pid[c];
-        a.send = p.send; a.list = s->perm; a.holes = p.holes; a.hole_flag = s->hole_flag;
+        a.send = p.send; a.list = s->leavers; a.holes = p.holes; a.holes_cap = p.send_total; a.hole_flag = s->hole_flag;
         a.ctr = ctr;
         a.key = keys ? s->key : nullptr;
         a.counts = s->counts;
@@ -728,7 +749,8 @@ int fsim_migrate_end(fsim_sim *s)
             MoveArgs<Real> m;
             for (int k = 0; k < NPART_ARRAYS; ++k) m.a[k] = (Real *)s->part[c][k];
             m.alive = s->alive[c]; m.id = s->pid[c];
-            m.targets = p.targets; m.sources = p.sources; m.ntargets = ctr + MC_NTARGETS;
+            m.targets = p.targets; m.sources = p.sources; m.ntargets = ctr + MC_NTARGETS; m.nsources = ctr + MC_NSOURCES;
+            m.n_old = s->cap;
             m.key = s->keys_valid ? s->key : nullptr;
             for (int q = 0; q < 2; ++q) m.dcol[q] = (Real *)s->dcol[q];
             compact_move_kernel<Real><<<grid_for(p.send_total, 256), 256, 0, s->stream>>>(m);

@@ -22,6 +22,11 @@ template <typename Real>
 struct PushArgs {
     Real *a[NPART_ARRAYS];
     uint8_t *alive;
+    // fused re-sort (PERM): slot j of the output takes the particle in slot perm[j] of `in` (the other copy)
+    const Real *in[NPART_ARRAYS];
+    const uint8_t *alive_in;
+    const uint32_t *perm, *id_in;
+    uint32_t *id_out;
     const Real *__restrict__ ent;
     const Real *__restrict__ cellrec;
     const uint32_t *__restrict__ sink;  // 1 bit per GLOBAL cell (2 MB at 8192 x 2048: stays in L2)
@@ -229,7 +234,11 @@ __device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int6
         if (valid) a.key[p0 + k] = newcell[k];
         if (valid && a.leavers) {
             const int gj = tex_idx(t.z[k], a.nz);
-            if (gj < a.own0 || gj >= a.own0 + a.own_rows) a.leavers[atomicAdd(a.nleavers, 1u)] = (uint32_t)(p0 + k);
+            if (gj < a.own0 || gj >= a.own0 + a.own_rows) {
+                const uint32_t at = atomicAdd(a.nleavers, 1u);
+                FSIM_ASSERT((int64_t)at < n);
+                a.leavers[at] = (uint32_t)(p0 + k);
+            }
         }
         int leader;
         uint32_t len, rank;
@@ -260,7 +269,7 @@ __device__ __forceinline__ void store_slots(const PushArgs<Real> &a, const int64
 // held while the streaming loads fly -- was measured 18 % SLOWER on B200: the sweep is not bound by
 // the latency of the streaming loads but by L1TEX wavefronts and dependent fp64 chains, and the
 // detour through shared memory adds to both.  DESIGN.md section 4.)
-template <typename Real, int V, int BLOCK, int MINB, int NH>
+template <typename Real, int V, int BLOCK, int MINB, int NH, bool PERM>
 __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> a)
 {
     // no early exit: the arrays are padded past n (common.cuh), the whole warp stays converged for
@@ -268,29 +277,55 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     const int64_t n = live_count(a.n_dev, a.n);
     Slots<Real, V> t;
-    ld_stream<Real, V>(a.a[AQ2] + p0, t.q2);
-    ld_stream<Real, V>(a.a[AQ3] + p0, t.q3);
-    ld_stream<Real, V>(a.a[AX] + p0, t.x);
-    ld_stream<Real, V>(a.a[AY] + p0, t.y);
-    ld_stream<Real, V>(a.a[AZ] + p0, t.z);
-    ld_stream<Real, V>(a.a[AQ0] + p0, t.q0);
-    ld_stream<Real, V>(a.a[AQ1] + p0, t.q1);
-    ld_stream<Real, V>(a.a[AVX] + p0, t.vx);
-    ld_stream<Real, V>(a.a[AVY] + p0, t.vy);
-    ld_stream<Real, V>(a.a[AVZ] + p0, t.vz);
+    if constexpr (PERM) {
+        // Fused physical re-sort: the sweep READS through the index list of the last binning (gathered, but
+        // the storage is nearly ordered, so neighbouring lanes stay within a few lines) and WRITES the
+        // other copy in cell order, coalesced -- the storage is re-sorted without a pass of its own.
 #pragma unroll
-    for (int k = 0; k < V; ++k) t.al[k] = a.alive[p0 + k];
+        for (int k = 0; k < V; ++k) {
+            const int64_t j = p0 + k;
+            const size_t p = j < n ? (size_t)(a.perm[j] & KEY_MASK) : (size_t)j;
+            FSIM_ASSERT(j >= n || (int64_t)p < n);
+            t.q2[k] = __ldcs(a.in[AQ2] + p); t.q3[k] = __ldcs(a.in[AQ3] + p);
+            t.x[k] = __ldcs(a.in[AX] + p); t.y[k] = __ldcs(a.in[AY] + p); t.z[k] = __ldcs(a.in[AZ] + p);
+            t.q0[k] = __ldcs(a.in[AQ0] + p); t.q1[k] = __ldcs(a.in[AQ1] + p);
+            t.vx[k] = __ldcs(a.in[AVX] + p); t.vy[k] = __ldcs(a.in[AVY] + p); t.vz[k] = __ldcs(a.in[AVZ] + p);
+            t.al[k] = a.alive_in[p];
+            a.id_out[j] = a.id_in[p];
+        }
+    } else {
+        ld_stream<Real, V>(a.a[AQ2] + p0, t.q2);
+        ld_stream<Real, V>(a.a[AQ3] + p0, t.q3);
+        ld_stream<Real, V>(a.a[AX] + p0, t.x);
+        ld_stream<Real, V>(a.a[AY] + p0, t.y);
+        ld_stream<Real, V>(a.a[AZ] + p0, t.z);
+        ld_stream<Real, V>(a.a[AQ0] + p0, t.q0);
+        ld_stream<Real, V>(a.a[AQ1] + p0, t.q1);
+        ld_stream<Real, V>(a.a[AVX] + p0, t.vx);
+        ld_stream<Real, V>(a.a[AVY] + p0, t.vy);
+        ld_stream<Real, V>(a.a[AVZ] + p0, t.vz);
+#pragma unroll
+        for (int k = 0; k < V; ++k) t.al[k] = a.alive[p0 + k];
+    }
     advance<Real, V, NH>(a, p0, n, t);
     store_slots<Real, V>(a, p0, t);
     if (a.key) emit_prepass<Real, V>(a, p0, n, t);
 }
 
 template <typename Real>
-static PushArgs<Real> make_args(fsim_sim *s, bool with_hist)
+static PushArgs<Real> make_args(fsim_sim *s, bool with_hist, bool resort)
 {
     PushArgs<Real> a;
-    for (int k = 0; k < NPART_ARRAYS; ++k) a.a[k] = (Real *)s->part[s->cur][k];
-    a.alive = s->alive[s->cur];
+    const int out = resort ? s->cur ^ 1 : s->cur;  // fused re-sort: read the current copy through perm[], write the other one
+    for (int k = 0; k < NPART_ARRAYS; ++k) {
+        a.a[k] = (Real *)s->part[out][k];
+        a.in[k] = (const Real *)s->part[s->cur][k];
+    }
+    a.alive = s->alive[out];
+    a.alive_in = s->alive[s->cur];
+    a.perm = s->perm;
+    a.id_in = s->pid[s->cur];
+    a.id_out = s->pid[out];
     a.ent = (const Real *)s->entropy;
     a.cellrec = (const Real *)s->cellrec;
     a.sink = s->sink;
@@ -299,7 +334,7 @@ static PushArgs<Real> make_args(fsim_sim *s, bool with_hist)
     for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
     a.counts = s->counts;
     a.oob = s->oob;
-    a.leavers = (with_hist && s->slab) ? s->perm : nullptr;
+    a.leavers = (with_hist && s->slab) ? s->leavers : nullptr;
     a.nleavers = s->mscratch + MC_NLEAVERS;
     a.own0 = s->own0; a.own_rows = s->own_rows;
     a.n = s->n;
@@ -312,13 +347,15 @@ static PushArgs<Real> make_args(fsim_sim *s, bool with_hist)
 }
 
 template <typename Real, int V, int BLOCK, int MINB>
-static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf)
+static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf, bool resort = false)
 {
     const int64_t nvec = (s->n + V - 1) / V;
-    if (nhalf == 2)
-        push_kernel<Real, V, BLOCK, MINB, 2><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+    if (resort)  // only step() re-sorts: two half-steps
+        push_kernel<Real, V, BLOCK, MINB, 2, true><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+    else if (nhalf == 2)
+        push_kernel<Real, V, BLOCK, MINB, 2, false><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     else
-        push_kernel<Real, V, BLOCK, MINB, 1><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+        push_kernel<Real, V, BLOCK, MINB, 1, false><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     FSIM_CUDA(cudaGetLastError());
     return FSIM_OK;
 }
@@ -329,8 +366,11 @@ static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf)
 int g_push_variant = 0;
 #endif
 
-int launch_push(fsim_sim *s, bool with_hist, int nhalf)
+// resort: the sweep also performs the physical re-sort the last binning prepared (perm[] must match the
+// current positions: s->binned); the particle storage flips to the other copy.
+int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
 {
+    if (resort && !(s->binned && nhalf == 2 && with_hist)) resort = false;
     if (with_hist && s->counts_dirty) {  // an unconsumed histogram: start from zero
         FSIM_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(uint32_t) * (s->ncell_local + 1), s->stream));
         s->counts_dirty = false;
@@ -340,8 +380,8 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf)
         using Real = decltype(tag);
         constexpr int V = 16 / sizeof(Real);  // particles per 128 bits
         if (s->n == 0) return (int)FSIM_OK;
-        const PushArgs<Real> a = make_args<Real>(s, with_hist);
-        Bracket b(s, nhalf == 2 ? "push2" : "push");
+        const PushArgs<Real> a = make_args<Real>(s, with_hist, resort);
+        Bracket b(s, resort ? "push2_resort" : (nhalf == 2 ? "push2" : "push"));
 #ifdef FSIM_TUNE
         switch (g_push_variant) {
         case 1: return push_impl<Real, V, 128, 4>(s, a, nhalf);
@@ -356,8 +396,15 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf)
 #endif
         // measured fastest on B200 (profiles/r2_push_variants.md): fp64 one particle per thread (64-bit
         // streams), fp32 two (64-bit streams); 256 threads x 4 blocks per SM = 64 registers per thread
-        return push_impl<Real, V / 2, 256, 4>(s, a, nhalf);
+        return push_impl<Real, V / 2, 256, 4>(s, a, nhalf, resort);
     });
+    if (resort && rc == FSIM_OK && s->n) {
+        s->cur ^= 1;
+        s->ever_sorted = true;
+        s->ids_identity = false;
+        s->steps_since_sort = 0;
+        s->resort_due = false;
+    }
     s->binned = false;
     s->keys_valid = with_hist;
     s->have_leavers = with_hist && s->slab;

@@ -55,12 +55,12 @@ render_kernel(const Real *__restrict__ B, const Real *__restrict__ avg_alpha, in
     reinterpret_cast<uchar4 *>(rgba)[(size_t)i + (size_t)(nz - 1 - j) * nr] = o;
 }
 
-int launch_render(fsim_sim *s, uint8_t *dev_rgba)
+int launch_render(fsim_sim *s, uint8_t *dev_rgba, cudaStream_t st)
 {
     return dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
-        Bracket b(s, "render");
-        render_kernel<Real><<<grid_for((int64_t)s->nr * s->own_rows, 256), 256, 0, s->stream>>>(
+        Bracket b(s, "render", st);
+        render_kernel<Real><<<grid_for((int64_t)s->nr * s->own_rows, 256), 256, 0, st>>>(
             (const Real *)s->B, (const Real *)s->avg + 3 * s->plane, s->pitch, dev_rgba, s->nr, s->nz, s->row0,
             s->own0, s->own_rows);
         FSIM_CUDA(cudaGetLastError());

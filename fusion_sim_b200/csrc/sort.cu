@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) apply_perm_kernel(const PermuteArgs<Real>
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= live_count(a.n_dev, a.n)) return;
     const size_t p = a.perm[j] & KEY_MASK;
+    FSIM_ASSERT((int64_t)p < live_count(a.n_dev, a.n));
     Real v[NPART_ARRAYS];
 #pragma unroll
     for (int k = 0; k < NPART_ARRAYS; ++k) v[k] = a.src[k][p];
@@ -237,6 +238,7 @@ index_scatter_kernel(const uint32_t *__restrict__ key, uint32_t *__restrict__ cu
 #pragma unroll
     for (int k = 0; k < IDX_ITEMS; ++k) {
         const uint32_t b = __shfl_sync(0xffffffffu, base[k], leader[k]);
+        FSIM_ASSERT(c[k] == 0xffffffffu || (int64_t)b + rank[k] < n);  // the cursor stays inside its cell's segment
         if (c[k] != 0xffffffffu) perm[(size_t)b + rank[k]] = (uint32_t)(p0 + 32 * k) | flag[k];
     }
 }

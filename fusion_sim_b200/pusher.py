@@ -126,8 +126,16 @@ class CylindricalParticlePusher:
     def addCurrentLoop(self, r, z, I):
         check(lib().fsim_add_current_loop(self._h, r, z, I))
 
-    def addSpindleCuspPlasmaField(self, r, B_c, beta_c=0.0):
-        check(lib().fsim_add_spindle_cusp_plasma_field(self._h, r, B_c, beta_c))
+    def addSpindleCuspPlasmaField(self, r, B_c, beta_c=1.0):
+        """empic.js:1369.  The reference's version does not run; this one implements its intent (a spindle cusp
+        of two opposing coils of radius r, B_c tesla at a coil's centre, and the surface currents that exclude
+        the field from the plasma, scaled by 1 - sqrt(1 - beta_c)): specification in include/fusionsim.h.
+        Returns what the boundary solve found."""
+        check(lib().fsim_add_spindle_cusp_plasma_field(self._h, float(r), float(B_c), float(beta_c)))
+        x, cur, A, rhs = np.empty(256), np.empty(257), np.empty((256, 256)), np.empty(256)
+        it, diff = C.c_int32(), C.c_double()
+        check(lib().fsim_get_spindle(self._h, ptr(x), ptr(cur), ptr(A), ptr(rhs), C.byref(it), C.byref(diff)))
+        return dict(x=x, currents=cur, A=A, rhs=rhs, iterations=it.value, diff=diff.value)
 
     def addCurrentZ(self, I):
         check(lib().fsim_add_current_z(self._h, I))

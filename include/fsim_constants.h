@@ -31,6 +31,16 @@
 #define FSIM_EPS0             8.8541878128e-12 /* vacuum permittivity (F/m), CODATA 2018  */
 #define FSIM_PI               3.14159265358979323846
 
+/* "next" row N3, second half: spindle-cusp boundary solve written from the intent of spindle.js
+ * (it does not run in the reference); specification in include/fusionsim.h                       */
+#define FSIM_SPINDLE_A        0.4              /* spindle.js:138 shape parameter of the plasma surface    */
+#define FSIM_SPINDLE_NPOWER   3                /* spindle.js:64  makeSORIterative({n_power: 3})           */
+#define FSIM_SPINDLE_L        256              /* 4 (2^n_power)^2 surface elements                        */
+#define FSIM_SPINDLE_QW       0.00628318530718 /* 2 pi / 1000: midpoint-rule weight of the loop quadrature */
+#define FSIM_SPINDLE_TOL      1e-9             /* solver tolerance (the reference's 1e-3 cannot converge)  */
+#define FSIM_SPINDLE_SUBSTEP  64               /* mat-vecs between convergence checks                      */
+#define FSIM_SPINDLE_MAXCHECK 4000             /* at most this many checks                                 */
+
 /* per-cell record produced by precalc(): rows of the Boris matrix and the
  * half-kick constant, 12 reals per cell: R1.xyz R2.xyz R3.xyz A.xyz
  * (empic.js:499-502 keeps them in four RGBA textures).                        */

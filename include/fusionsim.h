@@ -41,7 +41,7 @@ enum {
     FSIM_OK = 0,
     FSIM_ERR_INVALID = 1,     /* bad argument / spec validation (utilities.js:118-127)      */
     FSIM_ERR_CUDA = 2,        /* CUDA runtime failure; sticky on the handle                 */
-    FSIM_ERR_UNSUPPORTED = 3, /* addSpindleCuspPlasmaField: does not run in the reference   */
+    FSIM_ERR_UNSUPPORTED = 3, /* not available in this mode (e.g. solveFields on a slab handle)  */
     FSIM_ERR_STATE = 4,       /* call order violated (e.g. step before precalc)             */
     FSIM_ERR_RANGE = 5        /* "function out of range" (empic.js:1294-1296), capacity     */
 };
@@ -52,6 +52,8 @@ enum { FSIM_F64 = 0, FSIM_F32 = 1 };
 #define FSIM_FLAG_CORRECTED_PREA  1u /* textbook h(E.B)B instead of the scalar add of empic.js:645 */
 #define FSIM_FLAG_KEEP_MOMENTS    2u /* density() also stores moments01 and moments01_norm          */
 #define FSIM_FLAG_ATOMIC_DEPOSIT  4u /* measured alternative: global-atomic per-cell sums           */
+#define FSIM_FLAG_SERIAL_POST     8u /* measurement: stencil and canvas draws on the main stream instead
+                                      * of the second stream that overlaps them with the next sweep   */
 
 typedef struct fsim_sim fsim_sim;
 
@@ -107,7 +109,40 @@ int fsim_add_current_loop(fsim_sim *sim, double r, double z, double I); /* addCu
 int fsim_add_current_z(fsim_sim *sim, double I);                        /* addCurrentZ    :1380 */
 int fsim_add_bz(fsim_sim *sim, double Bz);                              /* addBZ          :1391 */
 int fsim_add_btheta(fsim_sim *sim, double Btheta);                      /* addBTheta      :1402 */
-int fsim_add_spindle_cusp_plasma_field(fsim_sim *sim, double r, double B_c, double beta_c); /* :1369 */
+/* out.addSpindleCuspPlasmaField(r, B_c, beta_c), empic.js:1369.  spindle.makeSpindleCuspPlasmaField does not run
+ * in the reference, so this entry point implements the INTENT of spindle.js:27-30 and
+ * :632-654 -- "solves the boundary conditions for a perfect conductor in center of a spindle cusp magnetic field",
+ * then superposes the solution on B -- with this specification (parity unpinned; oracle:
+ * oracle/fsim_oracle_spindle_impl.h, bit-identical):
+ *   field added = two opposing coils of radius r [m], +I_c at z = 0 and -I_c at z = height (the demo's cusp,
+ *     fusionsim.js:137-138), I_c = 2 r B_c / mu0 (B_c [T] = field of one coil at its own centre), PLUS the surface
+ *     currents that make B.n = 0 on the plasma surface, scaled by 1 - sqrt(1 - beta_c) (1: full exclusion, 0: vacuum);
+ *   surface (lower half, spindle.js:138-147; the upper half is its mirror image about z = height/2 carrying the
+ *     opposite current, :357-366): x = R cos(-phi) + radius, z = s R sin(-phi), R = radius sqrt(1 + a^2), a = 0.4,
+ *     phi in [theta, theta + arc], theta = atan(a) + pi, arc = pi/2 - 2 atan(a), s = height / (2 radius)
+ *     (s = 1 in the demo: from the axis point (0, a radius) to the ring cusp (radius (1-a), height/2));
+ *   L = 256 elements (makeSORIterative n_power 3, :64): nodes at phi_l = theta + l arc / L, l = 0..L (the
+ *     reference divides by 1000, a slip that covers a quarter of the arc); node 0 is put on the axis (x = 0);
+ *     collocation point p at l = p + 1/2 with unit normal (-s cos(-phi), -sin(-phi)) / |.|;
+ *   unknown x_e = strength of element e: a loop of current +x_e through node e and one of -x_e through node e+1
+ *     (:161-176, signs :351-391), each with its mirror image of opposite sign;  A[p][e] = n_p . (field of element e
+ *     at point p), rhs[p] = -n_p . (field of the coils at p);  the constant vector is a null vector of A (node l
+ *     carries x_l - x_{l-1}): gauge x_{L-1} = 0, the last collocation point (the ring-cusp tip) is dropped, row and
+ *     column L-1 of the solved system are those of the identity;
+ *   loop field [T/A] at (x, z) of a loop of radius Rl at height Zl -- the quadrature of programCurrentLoopShape
+ *     (empic.js:308-326) at the exact relative position, in metres, midpoint-rule weight W = 2 pi / 1000:
+ *       K = Rl W mu0 / (4 pi);  for k < 1000: c = cos(pi (k + .5) / 1000), rho = sqrt(Rl^2 + x^2 + dz^2 - 2 x Rl c),
+ *       f = rho > 0 ? K / (rho rho rho) : 0,  B_r += dz f c,  B_z += f (Rl - x c),  dz = z - Zl   (left to right, no FMA);
+ *   solver: fsim_jacobi_* (matrix_webgl.makeSORIterative), fp64, relaxation 1, tolerance 1e-9, substep 64, at
+ *     most 4000 checks (the Jacobi spectral radius of this system is 0.999: the reference's tolerance 1e-3 and
+ *     10 iterations cannot converge);  FSIM_ERR_RANGE if it does not converge;
+ *   B(cell) += sum over loops, in the order coil z=0, coil z=height, then node 0, mirror 0, node 1, mirror 1, ...,
+ *     of I_l x (loop field at the cell centre ((i+.5) radius/nr, (j+.5) height/nz)), in the engine's precision.   */
+int fsim_add_spindle_cusp_plasma_field(fsim_sim *sim, double r, double B_c, double beta_c);
+/* what the last call found (any pointer may be NULL): element strengths x [256], node currents [257] in amperes,
+ * the solved system A [256][256] row-major and rhs [256], solver checks and final diff (matrix_webgl.js:687)   */
+int fsim_get_spindle(fsim_sim *sim, double *x, double *currents, double *A, double *rhs, int32_t *iterations,
+                     double *diff);
 
 /* ---- precalc / step / density / canvas ----------------------------------------------------- */
 int fsim_precalc(fsim_sim *sim);   /* out.precalc :1413-1434: (E,B) -> R1,R2,R3,A per cell      */

@@ -59,6 +59,22 @@ static inline float orc_floor_f32(float x) { return floorf(x); }
 #undef REAL
 #undef SFX
 
+/* "next" row N3, second half: spindle-cusp boundary solve (specification written from the intent of spindle.js) */
+#define REAL double
+#define SFX f64
+#define ORC_SQRT sqrt
+#include "fsim_oracle_spindle_impl.h"
+#undef ORC_SQRT
+#undef REAL
+#undef SFX
+#define REAL float
+#define SFX f32
+#define ORC_SQRT sqrtf
+#include "fsim_oracle_spindle_impl.h"
+#undef ORC_SQRT
+#undef REAL
+#undef SFX
+
 /* per-column Jacobi coefficients [nr][4] = cE cW cZ cB (header of fsim_oracle_fields_impl.h) */
 void orc_relax_coeffs(int64_t nr, double dr, double dz, double *out)
 {

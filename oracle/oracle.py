@@ -33,7 +33,7 @@ def build(force: bool = False) -> str:
     import fcntl
     so = os.path.join(_HERE, "libfsim_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("fsim_oracle.c", "fsim_oracle_impl.h", "fsim_oracle_jacobi_impl.h",
-                                             "fsim_oracle_fields_impl.h", "Makefile")]
+                                             "fsim_oracle_fields_impl.h", "fsim_oracle_spindle_impl.h", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "fsim_constants.h"))
 
     def stale():
@@ -201,8 +201,34 @@ class OraclePusher:
     def addBTheta(self, Bt):
         self._uniform(2, Bt)
 
-    def addSpindleCuspPlasmaField(self, r, B_c, beta_c=None):
-        raise RuntimeError("spindle.makeSpindleCuspPlasmaField does not run in the reference")
+    def addSpindleCuspPlasmaField(self, r, B_c, beta_c=1.0):
+        """Spindle cusp with a field-excluding plasma (specification: include/fusionsim.h,
+        oracle/fsim_oracle_spindle_impl.h; written from the intent of spindle.js, which does not run)."""
+        from .jacobi import OracleSOR
+        L = 256
+        sp = self.spec
+        radius, height = float(sp["radius"]), float(sp["height"])
+        nodes, points, normals = np.empty((L + 1, 2)), np.empty((L, 2)), np.empty((L, 2))
+        lib().orcs_geometry(C.c_double(radius), C.c_double(height), _p(nodes), _p(points), _p(normals))
+        cos64 = cos_table(False)
+        coil_I = 2.0 * float(r) * float(B_c) / 1.25663706e-6
+        A, rhs = np.empty((L, L)), np.empty(L)
+        lib().orcs_assemble(C.c_double(radius), C.c_double(height), C.c_double(float(r)), C.c_double(coil_I), _p(cos64),
+                            _p(nodes), _p(points), _p(normals), _p(A), _p(rhs), C.c_int(self.nthreads))
+        sor = OracleSOR({"n_power": 3, "relaxation": 1.0}, nthreads=self.nthreads)
+        res = sor.set_matrix(A).set_b(rhs).solve({"tolerance": 1e-9, "substep": 64, "max_iterations": 4000})
+        cur = np.empty(L + 1)
+        lib().orcs_node_currents(_p(np.ascontiguousarray(res["result"])), C.c_double(float(beta_c)), _p(cur))
+        loops = [(float(r), 0.0, coil_I), (float(r), height, -coil_I)]
+        for l in range(L + 1):
+            loops.append((nodes[l, 0], nodes[l, 1], cur[l]))
+            loops.append((nodes[l, 0], height - nodes[l, 1], -cur[l]))
+        loops = np.ascontiguousarray(np.asarray(loops, np.float64))
+        self._f("orcs_add_loops")(C.c_int64(self.nr), C.c_int64(self.nz), C.c_double(radius), C.c_double(height),
+                                  C.c_int64(len(loops)), _p(loops), _p(self.costab), _p(self.B), C.c_int(self.nthreads))
+        self.spindle = dict(nodes=nodes, points=points, normals=normals, A=A, rhs=rhs, x=res["result"], currents=cur,
+                            iterations=res["iterations"], diff=res["diff"], coil_current=coil_I, loops=loops)
+        return self.spindle
 
     # -- precalc(), empic.js:1413-1434 -------------------------------------------------
     def precalc(self):

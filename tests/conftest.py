@@ -50,3 +50,36 @@ def assert_same(a, b, what=""):
         bad = np.argwhere(~ok)
         k = tuple(bad[0])
         raise AssertionError(f"{what}: {len(bad)} of {a.size} differ; first at {k}: {a[k]!r} vs {b[k]!r}")
+
+
+def deposit_reorder_bound(pos, vel, nr, nz, shape, dtype):
+    """Per cell and channel, how far two floating-point sums of the SAME deposit terms in DIFFERENT orders can
+    lie apart: the literal sprite raster adds a pixel's terms in particle order (GL blend order, empic.js:1473-1478),
+    the canonical form adds per-cell sums times weights.  With n terms t_k each sum is within gamma_n * sum|t_k| of
+    the exact value (gamma_n ~ n*eps), the per-cell partial sums of the canonical form add one more rounding per
+    term: |literal - canonical| <= 2 (n + 2) eps sum|t_k|.  Returns that bound, shape [nr*nz][4], in fp64."""
+    pos = np.asarray(pos, np.float64)
+    vel = np.asarray(vel, np.float64)
+    with np.errstate(all="ignore"):
+        r = np.sqrt(pos[:, 0] ** 2 + pos[:, 1] ** 2)
+        dx, dy = pos[:, 0] / r, pos[:, 1] / r
+        col = 0.001 * np.abs(np.stack([vel[:, 0] * dx + vel[:, 1] * dy, vel[:, 1] * dx - vel[:, 0] * dy,
+                                       vel[:, 2], np.ones(len(pos))], 1))
+        xw, yw = r * nr, pos[:, 2] * nz
+        ok = (xw >= 0) & (xw < nr) & (yw >= 0) & (yw < nz) & ~np.isnan(col).any(1)
+    cell = xw[ok].astype(np.int64) + nr * yw[ok].astype(np.int64)
+    A = np.zeros((nz + 10, nr + 10, 4))
+    N = np.zeros((nz + 10, nr + 10))
+    np.add.at(A.reshape(-1, 4), (cell // nr + 5) * (nr + 10) + cell % nr + 5, col[ok])
+    np.add.at(N.reshape(-1), (cell // nr + 5) * (nr + 10) + cell % nr + 5, 1.0)
+    w = np.asarray(shape, np.float64).reshape(11, 11)
+    T = np.zeros((nz, nr, 4))
+    K = np.zeros((nz, nr))
+    for tj in range(11):
+        for ti in range(11):
+            if w[tj, ti] == 0:
+                continue
+            T += A[10 - tj:10 - tj + nz, 10 - ti:10 - ti + nr] * w[tj, ti]
+            K += N[10 - tj:10 - tj + nz, 10 - ti:10 - ti + nr]
+    eps = np.finfo(dtype).eps
+    return (2.0 * (K[..., None] + 2.0) * eps * T).reshape(nr * nz, 4) + float(np.finfo(dtype).tiny)  # + one denormal step

@@ -227,8 +227,8 @@ def test_errors_are_thrown():
     with pytest.raises(Error, match=r"\.nr <- Non-optional property is undefined!"):
         makeCylindricalParticlePusher({k: v for k, v in sc["spec"].items() if k != "nr"})
     g = makeCylindricalParticlePusher(sc["spec"])
-    with pytest.raises(Error, match="spindle"):
-        g.addSpindleCuspPlasmaField(1.0, 0.5)
+    with pytest.raises(Error, match="beta_c"):
+        g.addSpindleCuspPlasmaField(1.0, 0.5, 2.0)
     with pytest.raises(Error):
         g.set({"position": np.zeros((3, 3))})
 
