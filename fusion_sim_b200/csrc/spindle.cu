@@ -6,8 +6,8 @@
 // center of a spindle cusp magnetic field", :138-176 the surface arc and its loop pairs, :418-630 the normal field
 // of fixed and variable loops at the surface points, :632-654 solve A x = b with makeSORIterative and superpose
 // the loops -- on the reference's own solver, fsim_jacobi_* (jacobi.cu).  The specification is written out in
-// include/fusionsim.h; oracle/fsim_oracle_spindle_impl.h states it a second time on the CPU and the two must
-// agree bit for bit.  PARITY UNPINNED (there is nothing in the reference to be equal to).
+// include/fusionsim.h; the test suite holds a second, CPU statement of it and the two must agree bit for
+// bit.  PARITY UNPINNED (there is nothing in the reference to be equal to).
 //
 //   1. surface geometry on the host (libm, fp64);
 //   2. node_field_kernel: the field of every surface loop (and its mirror image) at every collocation point --
