@@ -352,3 +352,37 @@ def test_checkpoint_restore_resumes_bit_for_bit(precision):
     for nm in ("moments01_avg", "phi", "E", "A", "cell_count"):
         assert_same(a.getField(nm), b.getField(nm), "resumed " + nm)
     assert_same(a.canvas, b.canvas, "resumed canvas")
+
+
+def test_check_digest_and_fused_resort_and_serial_post_flag():
+    """fsim_check_digest against NumPy on the accessor values; the re-sort fused into step()'s sweep (every
+    sort_interval-th frame) and the stencil / canvas draws on the second stream change no bit: a run with
+    sort_interval 2 and one with FSIM_FLAG_SERIAL_POST equal the default run."""
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene
+    sc = small_scene(n=20000, speed=0.05, blob=(0.7, 0.9))
+    runs = []
+    for extra in ({}, {"sort_interval": 2}, {"flags": 8}):
+        g = makeCylindricalParticlePusher(dict(sc["spec"], **extra))
+        apply_scene(g, sc)
+        imgs = []
+        for k in range(9):
+            g.step(); g.density(); g.draw_canvas()
+            if k % 4 == 0:
+                imgs.append(g.canvas.copy())
+        runs.append((g, imgs))
+    g0 = runs[0][0]
+    for g, imgs in runs[1:]:
+        assert_same(g.getPosition(), g0.getPosition(), "position")
+        assert_same(g.getRand(), g0.getRand(), "rand")
+        assert_same(g.getField("moments01_avg"), g0.getField("moments01_avg"), "running average")
+        assert_same(g.getField("cell_count"), g0.getField("cell_count"), "counts")
+        for a, b in zip(imgs, runs[0][1]):
+            assert_same(a, b, "canvas")
+    assert not np.array_equal(runs[1][0].getIds(), g0.getIds())  # the storage orders DO differ
+    d = g0.check_digest()
+    ids = g0.getIds().astype(np.uint64)
+    assert d["particles"] == 20000 and d["id_xor"] == int(np.bitwise_xor.reduce(ids)) and d["id_sum"] == int(ids.sum())
+    cnt = g0.getField("cell_count")
+    assert d["deposited"] == int(cnt.sum())
+    np.testing.assert_allclose(d["sum_alpha"], g0.getField("cell_sums")[:, 3].sum(), rtol=1e-12)
