@@ -455,7 +455,7 @@ def run_ours(args):
     for _ in range(args.steps):
         frame()
     kern = {}
-    for nm in ("push", "push2", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_warp", "cellsum_heavy", "conv",
+    for nm in ("push", "push2", "push2_resort", "prepass", "scan", "index_scatter", "permute", "cellsum", "cellsum_warp", "cellsum_heavy", "conv",
                "render", "migrate_pack", "migrate_unpack", "charge_source", "relax4", "relax2", "relax1", "efield", "precalc"):
         ms, cnt = sim.timing_get(nm)
         if cnt:

@@ -1121,7 +1121,10 @@ int fsim_density_begin(fsim_sim *s)
     // the deposit is done with the index list; now, every sort_interval frames, put the storage
     // itself into cell order for the pushes that follow
     // -- fused into the next step()'s sweep, which reads through this frame's index list (no pass of its own)
-    if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) s->resort_due = true;
+    if (!s->ever_sorted || s->steps_since_sort >= sort_interval(s)) {
+        if (s->spec.flags & FSIM_FLAG_UNFUSED_SORT) FSIM_TRY(finish(s, launch_apply_perm(s)));  // measurement only
+        else s->resort_due = true;
+    }
     s->conv_interior_done = false;
     return FSIM_OK;
 }

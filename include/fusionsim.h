@@ -52,6 +52,8 @@ enum { FSIM_F64 = 0, FSIM_F32 = 1 };
 #define FSIM_FLAG_CORRECTED_PREA  1u /* textbook h(E.B)B instead of the scalar add of empic.js:645 */
 #define FSIM_FLAG_KEEP_MOMENTS    2u /* density() also stores moments01 and moments01_norm          */
 #define FSIM_FLAG_ATOMIC_DEPOSIT  4u /* measured alternative: global-atomic per-cell sums           */
+#define FSIM_FLAG_UNFUSED_SORT   16u /* measurement: physical re-sort as a pass of its own in density()
+                                      * (round-1 behaviour) instead of fused into the next step()'s sweep  */
 #define FSIM_FLAG_SERIAL_POST     8u /* measurement: stencil and canvas draws on the main stream instead
                                       * of the second stream that overlaps them with the next sweep   */
 

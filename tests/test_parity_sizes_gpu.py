@@ -113,7 +113,12 @@ def test_c1_thousand_frames():
     never = np.ones(o.n, bool)
     respawns = 0
     for f in range(1000):
-        g.step(); o.step()
+        g.step()
+        for _ in range(2):  # out.step = two half-steps (empic.js:1436-1469); a respawn shows in the alive flag for ONE of them
+            o.half_step()
+            alive = o.position[:, 3] == 1
+            respawns += int((~alive).sum())
+            never &= alive
         g.density(); o.density()
         if f % 50 == 49:
             last = f == 999
@@ -125,9 +130,6 @@ def test_c1_thousand_frames():
             assert_same(g.getField("moments01_avg"), o.getField("moments01_avg"), f"C1 frame {f} running average")
             if last:
                 assert_same(g.canvas, o.canvas, "C1 canvas after 1000 frames")
-        alive = o.position[:, 3] == 1
-        respawns += int((~alive).sum())
-        never &= alive
     g.sync()
     assert respawns > 1000  # the blob reached the wall (after ~1500 half-steps)
     # Boris rotation with E = 0 conserves |v|: 2000 rotations x ~1e-16 each

@@ -21,7 +21,7 @@ sim = makeCylindricalParticlePusher(spec)
 import ctypes as _C  # noqa: E402
 _L = _C.CDLL(os.environ["FSIM_LIB_PATH"])  # the tuning build exports fsim_tune_set
 apply_scene(sim, sc)
-names = ("push", "push2", "scan", "permute", "index_scatter", "cellsum", "cellsum_warp", "cellsum_heavy", "conv", "prepass")
+names = ("push", "push2", "push2_resort", "scan", "permute", "index_scatter", "cellsum", "cellsum_warp", "cellsum_heavy", "conv", "prepass")
 out = {}
 for v in variants:
     _L.fsim_tune_set(int(v), 0)
