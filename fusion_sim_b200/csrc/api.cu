@@ -355,6 +355,7 @@ cudaStream_t post_begin(fsim_sim *s)
     if (!s->post_stream) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (s->spec.flags & FSIM_FLAG_POST_NO_PRIORITY) hi = 0;
         if (cudaStreamCreateWithPriority(&s->post_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return s->stream;
         cudaEventCreateWithFlags(&s->post_fork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s->post_done, cudaEventDisableTiming);

@@ -14,6 +14,8 @@
 // than 128-bit loads, which need 128 registers and halve the occupancy: profiles/r2_push_variants.md);
 // tables come through the read-only path.  Arithmetic is IEEE, left to right as the GLSL is
 // written, compiled with -fmad=false so it rounds exactly like the CPU oracle.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace fsim {
@@ -312,6 +314,82 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
     if (a.key) emit_prepass<Real, V>(a, p0, n, t);
 }
 
+
+// ---- the same sweep with the particle state staged by the TMA unit ------------------------------------------
+// Persistent blocks, one tile of 256 consecutive particles at a time.  The ten state arrays (and the alive
+// bytes) of a tile are brought into shared memory by eleven 1-D bulk copies (cp.async.bulk, SASS UBLKCP,
+// completion counted in bytes on an mbarrier), STAGES tiles ahead of the arithmetic: the copies of the next
+// tiles fly while the warps gather and rotate the current one, with no register held for them and no
+// per-thread load instruction.  Measured on B200 (tools/stream_layout_bench.cu): this access pattern by
+// itself streams at 6.86 TB/s, the per-thread-load sweep moved its bytes at 5.1 TB/s -- it waited on the
+// first use of the streamed state with too few bytes in flight per SM (32 warps x 10 x 256 B, most of the
+// time in the gather / fp64 phases).  Same arithmetic in the same order, hence the same bits.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        if (spin > (1u << 26)) __trap();  // a copy that never lands must not hang the GPU
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+template <typename Real, int NH, int STAGES, int MINB>
+__global__ void __launch_bounds__(256, MINB) push_tma_kernel(const PushArgs<Real> a, const int64_t ntiles)
+{
+    constexpr int T = 256;
+    constexpr uint32_t ARR_BYTES = T * sizeof(Real);
+    constexpr uint32_t STAGE_BYTES = NPART_ARRAYS * ARR_BYTES + T;  // + the alive bytes
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) unsigned long long full[STAGES];
+    const int tid = threadIdx.x;
+    const int64_t n = live_count(a.n_dev, a.n);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < STAGES; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[k])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned long long policy = 0;  // streamed once: first out of L2, the tables stay
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    auto issue = [&](int stage, int64_t tile) {  // one thread: arm the barrier, launch the eleven copies of `tile`
+        const uint32_t bar = smem_addr(&full[stage]);
+        unsigned char *dst = tile_smem + (size_t)stage * STAGE_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(STAGE_BYTES) : "memory");
+#pragma unroll
+        for (int k = 0; k < NPART_ARRAYS; ++k)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(smem_addr(dst + k * ARR_BYTES)), "l"(a.a[k] + tile * T), "r"(ARR_BYTES), "r"(bar), "l"(policy) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(smem_addr(dst + NPART_ARRAYS * ARR_BYTES)), "l"(a.alive + tile * T), "r"((uint32_t)T), "r"(bar), "l"(policy) : "memory");
+    };
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < STAGES; ++k)
+            if (first + k * stride < ntiles) issue(k, first + k * stride);
+    }
+    int it = 0;
+    for (int64_t tile = first; tile < ntiles; tile += stride, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(smem_addr(&full[stage]), (uint32_t)(it / STAGES) & 1u);
+        const Real *sm = reinterpret_cast<const Real *>(tile_smem + (size_t)stage * STAGE_BYTES);
+        Slots<Real, 1> t;
+        t.x[0] = sm[AX * T + tid]; t.y[0] = sm[AY * T + tid]; t.z[0] = sm[AZ * T + tid];
+        t.vx[0] = sm[AVX * T + tid]; t.vy[0] = sm[AVY * T + tid]; t.vz[0] = sm[AVZ * T + tid];
+        t.q0[0] = sm[AQ0 * T + tid]; t.q1[0] = sm[AQ1 * T + tid]; t.q2[0] = sm[AQ2 * T + tid]; t.q3[0] = sm[AQ3 * T + tid];
+        t.al[0] = tile_smem[(size_t)stage * STAGE_BYTES + NPART_ARRAYS * ARR_BYTES + tid];
+        __syncthreads();  // every thread holds its particle in registers: the stage is free for the tile STAGES ahead
+        if (tid == 0 && tile + STAGES * stride < ntiles) issue(stage, tile + STAGES * stride);
+        const int64_t p0 = tile * T + tid;
+        advance<Real, 1, NH>(a, p0, n, t);
+        store_slots<Real, 1>(a, p0, t);
+        if (a.key) emit_prepass<Real, 1>(a, p0, n, t);
+    }
+}
+
 template <typename Real>
 static PushArgs<Real> make_args(fsim_sim *s, bool with_hist, bool resort)
 {
@@ -360,6 +438,23 @@ static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf, bool resor
     return FSIM_OK;
 }
 
+// The TMA-staged sweep: persistent grid, STAGES tiles in flight per block, MINB blocks per SM.
+template <typename Real, int STAGES, int MINB>
+static int push_tma_impl(fsim_sim *s, const PushArgs<Real> &a)
+{
+    constexpr size_t smem = (size_t)STAGES * (NPART_ARRAYS * 256 * sizeof(Real) + 256);
+    constexpr uint32_t bit = 1u << ((sizeof(Real) == 8 ? 0 : 1) + 2 * (STAGES - 2) + 2);  // bits 2..7 of smem_opt_in
+    if (!(s->smem_opt_in & bit)) {
+        FSIM_CUDA(cudaFuncSetAttribute(push_tma_kernel<Real, 2, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s->smem_opt_in |= bit;
+    }
+    const int64_t ntiles = (s->n + 255) / 256;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)s->nsm * MINB);
+    push_tma_kernel<Real, 2, STAGES, MINB><<<grid, 256, smem, s->stream>>>(a, ntiles);
+    FSIM_CUDA(cudaGetLastError());
+    return FSIM_OK;
+}
+
 #ifdef FSIM_TUNE
 // Tuning build only (make EXTRA=-DFSIM_TUNE, tools/tune.py): vector width / block size / register cap
 // variants selectable at run time through fsim_tune_set().  The product compiles ONE variant per precision.
@@ -391,9 +486,17 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
         case 5: return push_impl<Real, V / 2, 128, 6>(s, a, nhalf);
         case 6: return push_impl<Real, V / 2, 512, 2>(s, a, nhalf);
         case 7: return push_impl<Real, V, 256, 2>(s, a, nhalf);
+        case 10: if (nhalf == 2 && !resort) return push_tma_impl<Real, 2, 3>(s, a); break;
+        case 11: if (nhalf == 2 && !resort) return push_tma_impl<Real, 2, 4>(s, a); break;
+        case 12: if (nhalf == 2 && !resort) return push_tma_impl<Real, 3, 3>(s, a); break;
+        case 13: if (nhalf == 2 && !resort) return push_tma_impl<Real, 4, 2>(s, a); break;
+        case 14: if (nhalf == 2 && !resort) return push_tma_impl<Real, 3, 2>(s, a); break;
+        case 15: if (nhalf == 2 && !resort) return push_tma_impl<Real, 2, 5>(s, a); break;
         default: break;
         }
 #endif
+        // step()'s plain sweep: particle state staged by the TMA unit, 3 tiles in flight per block, 3 blocks per SM
+        if (nhalf == 2 && !resort && !(s->spec.flags & FSIM_FLAG_DIRECT_LOADS)) return push_tma_impl<Real, 3, 3>(s, a);
         // measured fastest on B200 (profiles/r2_push_variants.md): fp64 one particle per thread (64-bit
         // streams), fp32 two (64-bit streams); 256 threads x 4 blocks per SM = 64 registers per thread
         return push_impl<Real, V / 2, 256, 4>(s, a, nhalf, resort);
