@@ -351,7 +351,7 @@ int check_handle(fsim_sim *s)
 // above the main stream: its blocks are scheduled as soon as the sweep's retire.
 cudaStream_t post_begin(fsim_sim *s)
 {
-    if (s->spec.flags & FSIM_FLAG_SERIAL_POST) return s->stream;
+    if (!(s->spec.flags & FSIM_FLAG_POST_STREAM)) return s->stream;  // default: one stream (measured faster)
     if (!s->post_stream) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -366,7 +366,7 @@ cudaStream_t post_begin(fsim_sim *s)
 }
 int post_end(fsim_sim *s)
 {
-    if (!s->post_stream || (s->spec.flags & FSIM_FLAG_SERIAL_POST)) return FSIM_OK;
+    if (!s->post_stream || !(s->spec.flags & FSIM_FLAG_POST_STREAM)) return FSIM_OK;
     FSIM_CUDA(cudaEventRecord(s->post_done, s->post_stream));
     s->post_pending = true;
     return FSIM_OK;
@@ -558,7 +558,7 @@ static void free_all(fsim_sim *s)
                     s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf, s->leavers};
     for (void *p : ptrs) cudaFree(p);
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef);
-    cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);
+    cudaFree(s->bmag); cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);
     if (s->n_pinned) cudaFreeHost(s->n_pinned);
     for (auto &e : s->n_event)
         if (e) cudaEventDestroy(e);
@@ -748,6 +748,7 @@ int fsim_set_E(fsim_sim *s, const double *E)
 int fsim_set_B(fsim_sim *s, const double *B)
 {
     FSIM_TRY(check(s));
+    s->bmag_valid = false;
     return finish(s, field_in(s, B, s->B));
 }
 int fsim_set_position(fsim_sim *s, const double *pos)
@@ -905,27 +906,32 @@ int fsim_set_ids(fsim_sim *s, const uint64_t *ids)
 int fsim_add_current_loop(fsim_sim *s, double r, double z, double I)
 {
     FSIM_TRY(check(s));
+    s->bmag_valid = false;  // the |B| layer of the canvas is stale
     // u_R = r*factor_r, u_Z = z*factor_z, empic.js:1355-1357
     return finish(s, launch_add_loop(s, r * s->factor_r, z * s->factor_z, I));
 }
 int fsim_add_current_z(fsim_sim *s, double I)
 {
     FSIM_TRY(check(s));
+    s->bmag_valid = false;  // the |B| layer of the canvas is stale
     return finish(s, launch_add_uniform(s, 0, I));
 }
 int fsim_add_bz(fsim_sim *s, double Bz)
 {
     FSIM_TRY(check(s));
+    s->bmag_valid = false;  // the |B| layer of the canvas is stale
     return finish(s, launch_add_uniform(s, 1, Bz));
 }
 int fsim_add_btheta(fsim_sim *s, double Bt)
 {
     FSIM_TRY(check(s));
+    s->bmag_valid = false;  // the |B| layer of the canvas is stale
     return finish(s, launch_add_uniform(s, 2, Bt));
 }
 int fsim_add_spindle_cusp_plasma_field(fsim_sim *s, double r, double B_c, double beta_c)
 {
     FSIM_TRY(check(s));
+    s->bmag_valid = false;  // the |B| layer of the canvas is stale
     // spindle.makeSpindleCuspPlasmaField does not run in the reference (spindle.js:57,328,333,624,643,651); this is
     // the boundary solve it was written towards, specified in include/fusionsim.h (spindle.cu)
     auto bad = [](double v) { return !(v == v) || isinf(v); };

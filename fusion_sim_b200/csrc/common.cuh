@@ -111,10 +111,11 @@ struct fsim_sim {
     int nsm = 148;            // multiprocessors of the device (grid sizes of the grid-stride kernels)
     uint32_t smem_opt_in = 0; // kernels whose dynamic shared-memory limit was raised ON THIS DEVICE (one bit each)
     cudaStream_t stream = nullptr;
-    // stencil + canvas draws ("post" work: reads the per-cell sums, writes the running average and the canvas)
-    // run on a second, higher-priority stream so that they overlap the NEXT frame's sweep: the sweep is
-    // bound by DRAM, the stencil by the fp64 pipe.  post_begin forks it off the main stream, post_join makes the
-    // main stream wait for it (before anything that reads the average / writes the sums or B).
+    // MEASURED ALTERNATIVE (FSIM_FLAG_POST_STREAM): stencil + canvas draws ("post" work: reads the per-cell sums,
+    // writes the running average and the canvas) on a second, higher-priority stream so that they overlap the NEXT
+    // frame's sweep.  post_begin forks it off the main stream, post_join makes the main stream wait for it (before
+    // anything that reads the average / writes the sums or B).  Off by default: on B200 the overlap doubles the
+    // sweep's time (the stencil's shared memory shrinks the L1 the sweep's gathers live on).
     cudaStream_t post_stream = nullptr;
     cudaEvent_t post_fork = nullptr, post_done = nullptr;
     bool post_pending = false;
@@ -219,6 +220,9 @@ struct fsim_sim {
     std::map<std::string, fsim::KernelTimer> timers;
     int64_t launches = 0;
     cudaEvent_t marks[16] = {};
+
+    void *bmag = nullptr;          // [nr * own_rows] uchar4: the |B| layer of the canvas (first draw), kept until B changes
+    bool bmag_valid = false;
 
     // asynchronous canvas read-back (fsim_render_rgba8_async): two device images, copy stream
     cudaStream_t copy_stream = nullptr;

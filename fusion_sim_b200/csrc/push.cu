@@ -81,6 +81,16 @@ __device__ __forceinline__ void ld_ro4(const double *p, double (&o)[4])
 {
     ld_ro256(p, o[0], o[1], o[2], o[3]);
 }
+// entropy texel: a random 32-byte gather from a 33.5 MB table never hits L1 again -- do not let it evict the
+// cell records and sink words that do (L1::no_allocate)
+__device__ __forceinline__ void ld_ent_na(const double *p, double (&o)[4])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_ent_na(const float *p, float (&o)[4])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p));
+}
 __device__ __forceinline__ void ld_ro4(const float *p, float (&o)[4])
 {
     float4 a = __ldg(reinterpret_cast<const float4 *>(p));
@@ -123,7 +133,9 @@ struct Slots {
 // out.step() is two half-steps with nothing in between that couples particles (static fields), so
 // NH = 2 performs the B-pass and the A-pass of empic.js:1438-1467 in one sweep over HBM: state
 // read once, written once.  Same operations in the same order, hence the same bits.
-template <typename Real, int V, int NH>
+// OPT bit 0: entropy gathers bypass L1 allocation; bit 1: the entropy texel of the NEXT half-step is fetched as soon
+// as the new RNG state exists (it depends on nothing else), under the Boris arithmetic of this one.
+template <typename Real, int V, int NH, int OPT = 0>
 __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p0, const int64_t n, Slots<Real, V> &t)
 {
     Real (&x)[V] = t.x, (&y)[V] = t.y, (&z)[V] = t.z, (&vx)[V] = t.vx, (&vy)[V] = t.vy, (&vz)[V] = t.vz;
@@ -132,15 +144,22 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
 #pragma unroll
     for (int k = 0; k < V; ++k) rcur[k] = fsqrt(x[k] * x[k] + y[k] * y[k]);
 
-#pragma unroll 1
-    for (int hs = 0; hs < NH; ++hs) {
-        // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
-        Real e[V][4], rec[V][RECSTRIDE], dx[V], dy[V];
+    auto gather_entropy = [&](Real (&e)[V][4]) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int ie = tex_idx(q2[k], FSIM_N_ENTROPY) + FSIM_N_ENTROPY * tex_idx(q3[k], FSIM_N_ENTROPY);
-            ld_ro4(a.ent + 4 * (size_t)ie, e[k]);
+            if constexpr (OPT & 1) ld_ent_na(a.ent + 4 * (size_t)ie, e[k]);
+            else ld_ro4(a.ent + 4 * (size_t)ie, e[k]);
         }
+    };
+    Real e[V][4];
+    if constexpr (OPT & 2) gather_entropy(e);
+
+#pragma unroll 1
+    for (int hs = 0; hs < NH; ++hs) {
+        // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
+        Real rec[V][RECSTRIDE], dx[V], dy[V];
+        if constexpr (!(OPT & 2)) gather_entropy(e);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const Real r = rcur[k];
@@ -169,6 +188,13 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
             q1[k] = (m1 > (Real)1.0) ? m1 - (Real)1.0 : m1;
             q2[k] = (Real)4.0 * x0 * ((Real)1.0 - x0);
             q3[k] = (Real)4.0 * x1 * ((Real)1.0 - x1);
+            if constexpr ((OPT & 2) != 0) {  // next half-step's texel, as early as its address exists
+                if (hs + 1 < NH) {
+                    const int ie = tex_idx(q2[k], FSIM_N_ENTROPY) + FSIM_N_ENTROPY * tex_idx(q3[k], FSIM_N_ENTROPY);
+                    if constexpr (OPT & 1) ld_ent_na(a.ent + 4 * (size_t)ie, e[k]);
+                    else ld_ro4(a.ent + 4 * (size_t)ie, e[k]);
+                }
+            }
 
             // ---- step_velocity_frag, empic.js:758-772 ----
             const Real vr = vx[k] * dx[k] + vy[k] * dy[k];
@@ -271,7 +297,7 @@ __device__ __forceinline__ void store_slots(const PushArgs<Real> &a, const int64
 // held while the streaming loads fly -- was measured 18 % SLOWER on B200: the sweep is not bound by
 // the latency of the streaming loads but by L1TEX wavefronts and dependent fp64 chains, and the
 // detour through shared memory adds to both.  DESIGN.md section 4.)
-template <typename Real, int V, int BLOCK, int MINB, int NH, bool PERM>
+template <typename Real, int V, int BLOCK, int MINB, int NH, bool PERM, int OPT = 0>
 __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> a)
 {
     // no early exit: the arrays are padded past n (common.cuh), the whole warp stays converged for
@@ -309,21 +335,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
 #pragma unroll
         for (int k = 0; k < V; ++k) t.al[k] = a.alive[p0 + k];
     }
-    advance<Real, V, NH>(a, p0, n, t);
+    advance<Real, V, NH, OPT>(a, p0, n, t);
     store_slots<Real, V>(a, p0, t);
     if (a.key) emit_prepass<Real, V>(a, p0, n, t);
 }
 
 
-// ---- the same sweep with the particle state staged by the TMA unit ------------------------------------------
+#ifdef FSIM_TUNE
+// ---- MEASURED ALTERNATIVE (tuning build only): the same sweep with the particle state staged by the TMA unit ----
 // Persistent blocks, one tile of 256 consecutive particles at a time.  The ten state arrays (and the alive
 // bytes) of a tile are brought into shared memory by eleven 1-D bulk copies (cp.async.bulk, SASS UBLKCP,
-// completion counted in bytes on an mbarrier), STAGES tiles ahead of the arithmetic: the copies of the next
-// tiles fly while the warps gather and rotate the current one, with no register held for them and no
-// per-thread load instruction.  Measured on B200 (tools/stream_layout_bench.cu): this access pattern by
-// itself streams at 6.86 TB/s, the per-thread-load sweep moved its bytes at 5.1 TB/s -- it waited on the
-// first use of the streamed state with too few bytes in flight per SM (32 warps x 10 x 256 B, most of the
-// time in the gather / fp64 phases).  Same arithmetic in the same order, hence the same bits.
+// completion counted in bytes on an mbarrier), STAGES tiles ahead of the arithmetic.  The idea: this access
+// pattern by itself streams at 6.86 TB/s (tools/stream_layout_bench.cu) while the per-thread-load sweep moves
+// its bytes at 5.1 TB/s, so keep more bytes in flight.  The measurement (profiles/r2_push_variants.md): SLOWER,
+// 3.31 ms (2 stages x 3 blocks per SM) to 4.05 ms (4 stages) against 2.94 ms -- the more shared memory the
+// stages take, the slower: shared memory and L1 are one array on the SM, and the sweep lives on the L1 hits of
+// its cell-record and sink gathers.  Not in the product (and its multi-tile path has an unresolved
+// data hazard at > 3 tiles per block; it is kept for the measurement only).
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
@@ -390,6 +418,8 @@ __global__ void __launch_bounds__(256, MINB) push_tma_kernel(const PushArgs<Real
     }
 }
 
+#endif  // FSIM_TUNE
+
 template <typename Real>
 static PushArgs<Real> make_args(fsim_sim *s, bool with_hist, bool resort)
 {
@@ -424,26 +454,30 @@ static PushArgs<Real> make_args(fsim_sim *s, bool with_hist, bool resort)
     return a;
 }
 
-template <typename Real, int V, int BLOCK, int MINB>
+template <typename Real, int V, int BLOCK, int MINB, int OPT = 0>
 static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf, bool resort = false)
 {
     const int64_t nvec = (s->n + V - 1) / V;
     if (resort)  // only step() re-sorts: two half-steps
-        push_kernel<Real, V, BLOCK, MINB, 2, true><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+        push_kernel<Real, V, BLOCK, MINB, 2, true, OPT><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     else if (nhalf == 2)
-        push_kernel<Real, V, BLOCK, MINB, 2, false><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+        push_kernel<Real, V, BLOCK, MINB, 2, false, OPT><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     else
         push_kernel<Real, V, BLOCK, MINB, 1, false><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     FSIM_CUDA(cudaGetLastError());
     return FSIM_OK;
 }
 
+#ifdef FSIM_TUNE
 // The TMA-staged sweep: persistent grid, STAGES tiles in flight per block, MINB blocks per SM.
 template <typename Real, int STAGES, int MINB>
 static int push_tma_impl(fsim_sim *s, const PushArgs<Real> &a)
 {
     constexpr size_t smem = (size_t)STAGES * (NPART_ARRAYS * 256 * sizeof(Real) + 256);
-    constexpr uint32_t bit = 1u << ((sizeof(Real) == 8 ? 0 : 1) + 2 * (STAGES - 2) + 2);  // bits 2..7 of smem_opt_in
+    constexpr uint32_t bit = 1u << (sizeof(Real) == 8 ? 30 : 31);  // bits 30, 31 of smem_opt_in
+#ifdef FSIM_TUNE
+    s->smem_opt_in &= ~bit;  // several instantiations share the bit in the tuning build
+#endif
     if (!(s->smem_opt_in & bit)) {
         FSIM_CUDA(cudaFuncSetAttribute(push_tma_kernel<Real, 2, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         s->smem_opt_in |= bit;
@@ -455,7 +489,6 @@ static int push_tma_impl(fsim_sim *s, const PushArgs<Real> &a)
     return FSIM_OK;
 }
 
-#ifdef FSIM_TUNE
 // Tuning build only (make EXTRA=-DFSIM_TUNE, tools/tune.py): vector width / block size / register cap
 // variants selectable at run time through fsim_tune_set().  The product compiles ONE variant per precision.
 int g_push_variant = 0;
@@ -492,11 +525,14 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
         case 13: if (nhalf == 2 && !resort) return push_tma_impl<Real, 4, 2>(s, a); break;
         case 14: if (nhalf == 2 && !resort) return push_tma_impl<Real, 3, 2>(s, a); break;
         case 15: if (nhalf == 2 && !resort) return push_tma_impl<Real, 2, 5>(s, a); break;
+        case 20: return push_impl<Real, V / 2, 256, 4, 1>(s, a, nhalf, resort);
+        case 21: return push_impl<Real, V / 2, 256, 4, 2>(s, a, nhalf, resort);
+        case 22: return push_impl<Real, V / 2, 256, 4, 3>(s, a, nhalf, resort);
+        case 23: return push_impl<Real, V / 2, 256, 3, 3>(s, a, nhalf, resort);
+        case 24: return push_impl<Real, V, 256, 2, 3>(s, a, nhalf, resort);
         default: break;
         }
 #endif
-        // step()'s plain sweep: particle state staged by the TMA unit, 3 tiles in flight per block, 3 blocks per SM
-        if (nhalf == 2 && !resort && !(s->spec.flags & FSIM_FLAG_DIRECT_LOADS)) return push_tma_impl<Real, 3, 3>(s, a);
         // measured fastest on B200 (profiles/r2_push_variants.md): fp64 one particle per thread (64-bit
         // streams), fp32 two (64-bit streams); 256 threads x 4 blocks per SM = 64 registers per thread
         return push_impl<Real, V / 2, 256, 4>(s, a, nhalf, resort);

@@ -54,11 +54,10 @@ enum { FSIM_F64 = 0, FSIM_F32 = 1 };
 #define FSIM_FLAG_ATOMIC_DEPOSIT  4u /* measured alternative: global-atomic per-cell sums           */
 #define FSIM_FLAG_UNFUSED_SORT   16u /* measurement: physical re-sort as a pass of its own in density()
                                       * (round-1 behaviour) instead of fused into the next step()'s sweep  */
-#define FSIM_FLAG_DIRECT_LOADS   32u /* measurement: the sweep loads its state with per-thread streaming loads
-                                      * instead of the TMA bulk-copy pipeline                              */
-#define FSIM_FLAG_POST_NO_PRIORITY 64u /* measurement: the second stream at the main stream's priority    */
-#define FSIM_FLAG_SERIAL_POST     8u /* measurement: stencil and canvas draws on the main stream instead
-                                      * of the second stream that overlaps them with the next sweep   */
+#define FSIM_FLAG_POST_STREAM     8u /* measured alternative: stencil and canvas draws on a second stream, under the
+                                      * next frame's sweep (slower on B200: the stencil's shared memory is L1 the
+                                      * sweep's gathers lose while the two share an SM)      */
+#define FSIM_FLAG_POST_NO_PRIORITY 64u /* ... that stream at the main stream's priority instead of above it       */
 
 typedef struct fsim_sim fsim_sim;
 

@@ -354,15 +354,15 @@ def test_checkpoint_restore_resumes_bit_for_bit(precision):
     assert_same(a.canvas, b.canvas, "resumed canvas")
 
 
-def test_check_digest_and_fused_resort_and_serial_post_flag():
+def test_check_digest_and_fused_resort_and_post_stream_flags():
     """fsim_check_digest against NumPy on the accessor values; the re-sort fused into step()'s sweep (every
-    sort_interval-th frame) and the stencil / canvas draws on the second stream change no bit: a run with
-    sort_interval 2 and one with FSIM_FLAG_SERIAL_POST equal the default run."""
+    sort_interval-th frame), the un-fused re-sort pass and the stencil / canvas draws on a second stream change
+    no bit: runs with sort_interval 2, FSIM_FLAG_POST_STREAM and FSIM_FLAG_UNFUSED_SORT equal the default run."""
     from fusion_sim_b200 import makeCylindricalParticlePusher
     from fusion_sim_b200.scenes import apply_scene
     sc = small_scene(n=20000, speed=0.05, blob=(0.7, 0.9))
     runs = []
-    for extra in ({}, {"sort_interval": 2}, {"flags": 8}):
+    for extra in ({}, {"sort_interval": 2}, {"flags": 8}, {"flags": 16, "sort_interval": 3}):
         g = makeCylindricalParticlePusher(dict(sc["spec"], **extra))
         apply_scene(g, sc)
         imgs = []

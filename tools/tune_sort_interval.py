@@ -1,4 +1,5 @@
-"""Frame time vs physical re-sort interval on the bench scene (one B200), and the second-stream A/B.
+"""Frame time vs physical re-sort interval on the bench scene (one B200), and A/B over the engine flags
+(8 = stencil and canvas draws on a second stream, 16 = re-sort as a pass of its own, 64 = second stream without priority).
     python tools/tune_sort_interval.py [workload] [precision] [intervals, comma separated] [flags]
 The re-sort is fused into the sweep (push2_resort), so a sort costs the difference between push2_resort and
 push2; what an interval buys is a more coherent cell-table gather (push2), longer runs of equal keys
