@@ -512,13 +512,13 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
         Bracket b(s, resort ? "push2_resort" : (nhalf == 2 ? "push2" : "push"));
 #ifdef FSIM_TUNE
         switch (g_push_variant) {
-        case 1: return push_impl<Real, V, 128, 4>(s, a, nhalf);
-        case 2: return push_impl<Real, V, 256, 3>(s, a, nhalf);
-        case 3: return push_impl<Real, V / 2, 256, 3>(s, a, nhalf);
-        case 4: return push_impl<Real, V / 2, 256, 4>(s, a, nhalf);
-        case 5: return push_impl<Real, V / 2, 128, 6>(s, a, nhalf);
-        case 6: return push_impl<Real, V / 2, 512, 2>(s, a, nhalf);
-        case 7: return push_impl<Real, V, 256, 2>(s, a, nhalf);
+        case 1: return push_impl<Real, V, 128, 4>(s, a, nhalf, resort);
+        case 2: return push_impl<Real, V, 256, 3>(s, a, nhalf, resort);
+        case 3: return push_impl<Real, V / 2, 256, 3>(s, a, nhalf, resort);
+        case 4: return push_impl<Real, V / 2, 256, 4>(s, a, nhalf, resort);
+        case 5: return push_impl<Real, V / 2, 128, 6>(s, a, nhalf, resort);
+        case 6: return push_impl<Real, V / 2, 512, 2>(s, a, nhalf, resort);
+        case 7: return push_impl<Real, V, 256, 2>(s, a, nhalf, resort);
         case 10: if (nhalf == 2 && !resort) return push_tma_impl<Real, 2, 3>(s, a); break;
         case 11: if (nhalf == 2 && !resort) return push_tma_impl<Real, 2, 4>(s, a); break;
         case 12: if (nhalf == 2 && !resort) return push_tma_impl<Real, 3, 3>(s, a); break;
