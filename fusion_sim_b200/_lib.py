@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("FSIM_LIB_PATH") or os.path.join(_HERE, "csrc", "libfu
 
 FSIM_F64, FSIM_F32 = 0, 1
 FLAG_CORRECTED_PREA, FLAG_KEEP_MOMENTS, FLAG_ATOMIC_DEPOSIT = 1, 2, 4
+FLAG_POST_STREAM, FLAG_UNFUSED_SORT, FLAG_POST_NO_PRIORITY, FLAG_PERIODIC_Z = 8, 16, 64, 128
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_RANGE = 1, 2, 3, 4, 5
 
 

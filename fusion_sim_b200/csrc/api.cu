@@ -89,7 +89,10 @@ __global__ void field_in_kernel(const double *__restrict__ in, Real *__restrict_
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= (int64_t)nr * rows) return;
-    const int i = (int)(c % nr), j = (int)(c / nr) + row0;
+    const int i = (int)(c % nr);
+    int j = (int)(c / nr) + row0;
+    if (j < 0) j += nz;  // periodic z: ghost rows take the wrapped rows
+    if (j >= nz) j -= nz;
     const double *p = in + 3 * ((size_t)i * nz + j);
     out[3 * c] = (Real)p[0]; out[3 * c + 1] = (Real)p[1]; out[3 * c + 2] = (Real)p[2];
 }
@@ -458,6 +461,10 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
         const int hi = std::min<int64_t>(s->nz, sp->slab_row0 + sp->slab_rows + sp->halo_rows);
         s->row0 = lo;
         s->rows = hi - lo;
+    } else if (sp->flags & FSIM_FLAG_PERIODIC_Z) {  // EXTENSION: nz owned rows + ghost rows that hold the wrapped rows
+        const int h = (int)std::max<int64_t>(sp->halo_rows, 8);
+        s->ring = true;
+        s->own0 = 0; s->own_rows = s->nz; s->row0 = -h; s->rows = s->nz + 2 * h;
     } else {
         s->own0 = 0; s->own_rows = s->nz; s->row0 = 0; s->rows = s->nz;
     }
@@ -557,7 +564,7 @@ static void free_all(fsim_sim *s)
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
                     s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf, s->leavers};
     for (void *p : ptrs) cudaFree(p);
-    cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef);
+    cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef); cudaFree(s->background);
     cudaFree(s->bmag); cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);
     if (s->n_pinned) cudaFreeHost(s->n_pinned);
     for (auto &e : s->n_event)
@@ -717,6 +724,8 @@ int fsim_create(const fsim_spec *sp, fsim_sim **out)
         return fail(FSIM_ERR_INVALID, ".id_base <- id_base + particle slots must stay below 2^32 (ids are 32-bit)");
     if (sp->slab_rows < 0 || sp->slab_row0 < 0 || sp->slab_row0 + sp->slab_rows > sp->nz)
         return fail(FSIM_ERR_INVALID, ".slab_rows <- slab outside the grid");
+    if ((sp->flags & FSIM_FLAG_PERIODIC_Z) && (sp->slab_rows > 0 || sp->nz < 8))
+        return fail(FSIM_ERR_UNSUPPORTED, ".flags <- periodic z runs on one GPU (no slab) and needs at least 8 rows");
     if (sp->slab_rows > 0 && sp->halo_rows < FSIM_SHAPE_MID)
         return fail(FSIM_ERR_INVALID, ".halo_rows <- slab mode needs at least 5 halo rows (deposit footprint)");
     fsim_sim *s = new fsim_sim();
@@ -851,9 +860,9 @@ int fsim_set_field(fsim_sim *s, const char *name, const double *data)
     int nch = 0;
     void *dst = nullptr;
     if (n == "moments01_avg") { nch = 4; dst = s->avg; }
-    else if (n == "phi") {
+    else if (n == "phi" || n == "background") {
         FSIM_TRY(finish(s, ensure_fieldsolve(s)));
-        nch = 1; dst = s->phi[s->phi_cur];
+        nch = 1; dst = n == "phi" ? s->phi[s->phi_cur] : s->background;
     } else return fail(FSIM_ERR_INVALID, "set field: unknown name " + n);
     FSIM_TRY(finish(s, stage_in(s, data, sizeof(double) * nch * nc)));
     return finish(s, dispatch(s, [&](auto tag) {
@@ -992,10 +1001,15 @@ int fsim_solve_fields(fsim_sim *s, double macro_weight, int32_t sweeps, double o
     FSIM_TRY(solve_args_ok(s, sweeps, omega, source));
     FSIM_TRY(finish(s, ensure_fieldsolve(s)));
     FSIM_TRY(finish(s, solve_charge_source(s, macro_weight, source)));
+    // periodic z: what a slab rank exchanges with its neighbours between the stages (dist.py, solve_fields_slab) this
+    // handle exchanges with itself -- 4 rows of the source once, 4 rows of the potential before every launch of <= 4 sweeps
+    auto wrap = [&](void *plane) { return s->ring ? finish(s, ring_wrap_rows(s, plane, 4)) : (int)FSIM_OK; };
+    FSIM_TRY(wrap(s->rho_src));
     int left = sweeps;
-    for (; left >= 4; left -= 4) FSIM_TRY(finish(s, launch_relax(s, 4, omega)));
-    if (left >= 2) { FSIM_TRY(finish(s, launch_relax(s, 2, omega))); left -= 2; }
-    if (left >= 1) FSIM_TRY(finish(s, launch_relax(s, 1, omega)));
+    for (; left >= 4; left -= 4) { FSIM_TRY(wrap(s->phi[s->phi_cur])); FSIM_TRY(finish(s, launch_relax(s, 4, omega))); }
+    if (left >= 2) { FSIM_TRY(wrap(s->phi[s->phi_cur])); FSIM_TRY(finish(s, launch_relax(s, 2, omega))); left -= 2; }
+    if (left >= 1) { FSIM_TRY(wrap(s->phi[s->phi_cur])); FSIM_TRY(finish(s, launch_relax(s, 1, omega))); }
+    FSIM_TRY(wrap(s->phi[s->phi_cur]));
     FSIM_TRY(finish(s, launch_efield(s)));
     FSIM_TRY(finish(s, launch_precalc(s)));
     s->have_precalc = true;
@@ -1124,7 +1138,7 @@ int fsim_density_begin(fsim_sim *s)
         FSIM_TRY(finish(s, launch_cellsum_atomic(s)));  // measured alternative, not bit-reproducible
     else
         FSIM_TRY(finish(s, launch_cellsum(s)));
-    if (s->slab) FSIM_TRY(finish(s, launch_halo_pack(s)));  // own boundary rows -> send buffers (the caller's exchange starts here)
+    if (s->slab || s->ring) FSIM_TRY(finish(s, launch_halo_pack(s)));  // own boundary rows -> send buffers (the caller's exchange starts here)
     // the deposit is done with the index list; now, every sort_interval frames, put the storage
     // itself into cell order for the pushes that follow
     // -- fused into the next step()'s sweep, which reads through this frame's index list (no pass of its own)
@@ -1147,7 +1161,14 @@ int fsim_density_interior(fsim_sim *s)
 int fsim_density_end(fsim_sim *s)
 {
     FSIM_TRY(check_handle(s));
-    if (s->slab) FSIM_TRY(finish(s, launch_halo_unpack(s)));  // neighbours' boundary rows -> halo rows of the sums
+    if (s->ring) {  // periodic z: the exchange is with itself -- bottom rows above the top, top rows below the bottom
+        void *p[4];
+        int64_t each = 0;
+        FSIM_TRY(fsim_halo_ptrs(s, &p[0], &p[1], &p[2], &p[3], &each));
+        FSIM_CUDA(cudaMemcpyAsync(p[3], p[0], (size_t)each, cudaMemcpyDeviceToDevice, s->stream));
+        FSIM_CUDA(cudaMemcpyAsync(p[2], p[1], (size_t)each, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    if (s->slab || s->ring) FSIM_TRY(finish(s, launch_halo_unpack(s)));  // neighbours' boundary rows -> halo rows of the sums
     const int part = s->conv_interior_done ? 2 : 0;
     s->conv_interior_done = false;
     return finish(s, launch_conv_rows(s, part));

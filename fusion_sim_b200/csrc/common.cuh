@@ -134,6 +134,7 @@ struct fsim_sim {
     alignas(64) unsigned char tm_sums[128] = {};  // CUtensorMap of the per-cell sums (deposit.cu)
     int tm_sums_rows = 0;                         // box height the map was encoded with
     bool slab = false;
+    bool ring = false;        // FSIM_FLAG_PERIODIC_Z: nz owned rows + ghost rows either side that hold the wrapped rows
 
     // physical constants (host doubles, empic.js:44-46, :852)
     double h = 0, factor_r = 0, factor_z = 0, step_factor = 0;
@@ -186,6 +187,7 @@ struct fsim_sim {
     void *phi[2] = {};           // potential, planar [rows][pitch], ping-pong
     int phi_cur = 0;
     void *rho_src = nullptr;     // rho/eps0, planar
+    void *background = nullptr;  // neutralising background in density units, planar (zero until fsim_set_field)
     void *relax_coef = nullptr;  // [nr][4] Jacobi coefficients cE cW cZ cB
     alignas(64) unsigned char tm_phi[2][128] = {};  // CUtensorMaps of phi[0], phi[1], rho_src
     alignas(64) unsigned char tm_src[128] = {};
@@ -401,6 +403,7 @@ int spindle_solve(fsim_sim *s, double coil_r, double B_c, double beta_c);  // sp
 int launch_render(fsim_sim *s, uint8_t *dev_rgba, cudaStream_t st);
 int ensure_fieldsolve(fsim_sim *s);
 int launch_charge_source(fsim_sim *s, const void *dens_a, double rho_scale);
+int ring_wrap_rows(fsim_sim *s, void *plane_base, int nrows);  // periodic z: owned boundary rows -> ghost rows (planar field)
 int launch_relax(fsim_sim *s, int sweeps, double omega);  // 1..4 sweeps, one launch
 int launch_efield(fsim_sim *s);
 int launch_plane_out(fsim_sim *s, const void *plane, double *dev_out);

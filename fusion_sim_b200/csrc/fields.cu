@@ -116,7 +116,10 @@ add_loop_kernel(Real *__restrict__ B, int nr, int nz, int row0, int rows, Real R
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= (int64_t)nr * rows) return;
-    const int i = (int)(c % nr), j = (int)(c / nr) + row0;
+    const int i = (int)(c % nr);
+    int j = (int)(c / nr) + row0;
+    if (j < 0) j += nz;  // periodic z: a ghost row holds the field of the row it mirrors
+    if (j >= nz) j -= nz;
     const Real u = ((Real)i + (Real)0.5) / (Real)nr;
     const Real v = ((Real)j + (Real)0.5) / (Real)nz;
     // programCurrentLoop, empic.js:367-377

@@ -142,12 +142,13 @@ relax_kernel(const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ 
 
 template <typename Real>
 __global__ void __launch_bounds__(256)
-charge_source_kernel(const Real *__restrict__ dens_a, Real *__restrict__ src, int nr, int rows, int pitch, Real scale)
+charge_source_kernel(const Real *__restrict__ dens_a, const Real *__restrict__ background, Real *__restrict__ src, int nr,
+                     int rows, int pitch, Real scale)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= (int64_t)nr * rows) return;
     const size_t o = (size_t)(c / nr) * pitch + (size_t)(c % nr);
-    src[o] = scale * dens_a[o];
+    src[o] = scale * (dens_a[o] - background[o]);  // background is zero until set: x - 0 = x, bit for bit
 }
 
 template <typename Real>
@@ -229,6 +230,8 @@ int ensure_fieldsolve(fsim_sim *s)
     }
     FSIM_CUDA(cudaMalloc(&s->rho_src, bytes));
     FSIM_CUDA(cudaMemsetAsync(s->rho_src, 0, bytes, s->stream));
+    FSIM_CUDA(cudaMalloc(&s->background, bytes));
+    FSIM_CUDA(cudaMemsetAsync(s->background, 0, bytes, s->stream));
     FSIM_TRY(encode_plane_map(s, s->rho_src, s->tm_src));
     FSIM_CUDA(cudaMalloc(&s->relax_coef, s->rs * 4 * (size_t)s->nr));
     // per-column coefficients in host fp64 (specification: include/fusionsim.h)
@@ -283,7 +286,7 @@ int launch_charge_source(fsim_sim *s, const void *dens_a, double rho_scale)
         using Real = decltype(tag);
         Bracket b(s, "charge_source");
         charge_source_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>(
-            (const Real *)dens_a, (Real *)s->rho_src, s->nr, s->rows, s->pitch, (Real)rho_scale);
+            (const Real *)dens_a, (const Real *)s->background, (Real *)s->rho_src, s->nr, s->rows, s->pitch, (Real)rho_scale);
         FSIM_CUDA(cudaGetLastError());
         return (int)FSIM_OK;
     });
@@ -302,6 +305,25 @@ int launch_relax(fsim_sim *s, int sweeps, double omega)
         default: set_error("relax: 1..4 sweeps per launch"); return (int)FSIM_ERR_INVALID;
         }
     });
+}
+
+// Periodic z (FSIM_FLAG_PERIODIC_Z): the `nrows` owned rows at either end of a planar field go into the ghost rows
+// beyond the other end -- the exchange a slab rank does with its neighbours, here with itself.  Rows are contiguous.
+int ring_wrap_rows(fsim_sim *s, void *plane_base, int nrows)
+{
+    const int h = s->own0 - s->row0;  // ghost rows below the owned block
+    if (nrows > h || nrows > s->own_rows) {
+        set_error("periodic z: more rows to wrap than ghost rows");
+        return FSIM_ERR_RANGE;
+    }
+    const size_t row = s->rs * (size_t)s->pitch;
+    char *b = (char *)plane_base;
+    // bottom owned rows -> ghost rows above the top; top owned rows -> ghost rows below the bottom
+    FSIM_CUDA(cudaMemcpyAsync(b + row * (size_t)(h + s->own_rows), b + row * (size_t)h, row * (size_t)nrows, cudaMemcpyDeviceToDevice,
+                              s->stream));
+    FSIM_CUDA(cudaMemcpyAsync(b + row * (size_t)(h - nrows), b + row * (size_t)(h + s->own_rows - nrows), row * (size_t)nrows,
+                              cudaMemcpyDeviceToDevice, s->stream));
+    return FSIM_OK;
 }
 
 int launch_efield(fsim_sim *s)

@@ -42,6 +42,7 @@ struct PushArgs {
     int64_t n;              // live slots (an upper bound when n_dev is set)
     const uint32_t *n_dev;  // asynchronous slab exchange: the exact count lives on the device
     int nr, nz, row0, rows, own_lo, own_hi;
+    int periodic;           // EXTENSION: z wraps (FSIM_FLAG_PERIODIC_Z)
     Real sf, h, k13, k31;
 };
 
@@ -219,7 +220,11 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
             // ---- step_position_frag, empic.js:714-719 ----
             const Real nx = x[k] + a.sf * nvx;
             const Real ny = y[k] + a.sf * nvy;
-            const Real nzp = z[k] + a.sf * nvz;
+            Real nzp = z[k] + a.sf * nvz;
+            if (a.periodic) {  // EXTENSION (no reference counterpart): periodic in z
+                nzp = nzp - ffloor(nzp);
+                if (nzp >= (Real)1.0) nzp = (Real)0.0;
+            }
             const Real rn = fsqrt(nx * nx + ny * ny);
             bool keep = false;
             if (rn == rn && nzp == nzp) {  // NaN position => absorbed (documented rule)
@@ -449,6 +454,7 @@ static PushArgs<Real> make_args(fsim_sim *s, bool with_hist, bool resort)
     a.n_dev = s->n_async ? s->mscratch + MC_NLIVE : nullptr;
     a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
     a.own_lo = s->own0 - s->row0; a.own_hi = a.own_lo + s->own_rows;
+    a.periodic = s->ring ? 1 : 0;
     a.sf = (Real)s->step_factor;
     a.h = (Real)s->h; a.k13 = (Real)s->k13; a.k31 = (Real)s->k31;
     return a;

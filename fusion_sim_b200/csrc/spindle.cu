@@ -93,7 +93,10 @@ add_loops_kernel(Real *__restrict__ B, int nr, int nz, int row0, int rows, Real 
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= (int64_t)nr * rows) return;
-    const int i = (int)(c % nr), j = (int)(c / nr) + row0;
+    const int i = (int)(c % nr);
+    int j = (int)(c / nr) + row0;
+    if (j < 0) j += nz;  // periodic z: ghost rows mirror the wrapped rows
+    if (j >= nz) j -= nz;
     const Real x = ((Real)i + (Real)0.5) * dr;
     const Real z = ((Real)j + (Real)0.5) * dzc;
     Real sr = (Real)0, sz = (Real)0;

@@ -22,7 +22,7 @@ from ._lib import Error, FsimSpec, check, lib, ptr
 
 _REQUIRED = ("radius", "height", "nr", "nz", "dt", "nparticles", "particle_mass", "particle_charge")
 _EXT = ("precision", "device", "flags", "sort_interval", "nparticles_total", "capacity", "slab_row0",
-        "slab_rows", "halo_rows", "id_base", "seed", "corrected_preA", "keep_moments")
+        "slab_rows", "halo_rows", "id_base", "seed", "corrected_preA", "keep_moments", "periodic_z")
 
 
 def validate_object(test: dict, control: dict):
@@ -61,7 +61,13 @@ class CylindricalParticlePusher:
             flags |= _lib.FLAG_CORRECTED_PREA
         if spec.get("keep_moments"):
             flags |= _lib.FLAG_KEEP_MOMENTS
+        if spec.get("periodic_z"):  # EXTENSION: z periodic; the reference has no such boundary
+            flags |= _lib.FLAG_PERIODIC_Z
         cs.flags = flags
+        # periodic z: the engine's cell tables carry ghost rows either side of the nz owned rows; the accessors of
+        # this mirror return / take the owned rows only
+        self.periodic = bool(flags & _lib.FLAG_PERIODIC_Z)
+        self.ghost_rows = max(int(spec.get("halo_rows", 0)), 8) if self.periodic else 0
         for k in ("device", "sort_interval", "nparticles_total", "capacity", "slab_row0", "slab_rows",
                   "halo_rows", "id_base"):
             setattr(cs, k, int(spec.get(k, 0)))
@@ -224,7 +230,34 @@ class CylindricalParticlePusher:
     def getCells(self):
         return self._get(lib().fsim_get_cells, (self.n,), np.int64)
 
+    def _owned(self, a):
+        """Periodic z: strip the ghost rows of a cell-indexed array [local cells][...]."""
+        if not self.periodic:
+            return a
+        g = self.ghost_rows * self.nr
+        return np.ascontiguousarray(a[g:g + self.nr * self.nz])
+
+    def _with_ghosts(self, a):
+        """Periodic z: owned rows [nz*nr][...] -> the engine's local table with the wrapped rows as ghosts."""
+        if not self.periodic:
+            return a
+        g = self.ghost_rows * self.nr
+        return np.ascontiguousarray(np.concatenate([a[-g:], a, a[:g]]))
+
+    def setBackground(self, background):
+        """EXTENSION: the neutralising background solveFields() subtracts from the density, [nz*nr] in the units
+        of the density texture (e.g. getField("moments01_norm")[:, 3] at t = 0: immobile ions)."""
+        b = self._with_ghosts(_f64(background, (self.nr * self.nz,)))
+        check(lib().fsim_set_field(self._h, b"background", ptr(b)))
+
     def getField(self, name: str):
+        if self.periodic and name not in ("sink_mask", "inv_cdf", "entropy"):
+            self.periodic = False
+            try:
+                a = self.getField(name)
+            finally:
+                self.periodic = True
+            return self._owned(a)
         nc = self.ncell_local
         if name == "cell_count":
             return self._get(lib().fsim_get_cell_count, (nc,), np.uint32)
@@ -263,9 +296,10 @@ class CylindricalParticlePusher:
         check(L.fsim_precalc(h))
         check(L.fsim_set_state(h, ptr(_f64(ck["position"], (self.n, 4))), ptr(_f64(ck["velocity"], (self.n, 3))),
                                ptr(_f64(ck["rand"], (self.n, 4)))))
-        check(L.fsim_set_field(h, b"moments01_avg", ptr(_f64(ck["moments01_avg"], (nc, 4)))))
+        nown = self.nr * self.nz if self.periodic else nc
+        check(L.fsim_set_field(h, b"moments01_avg", ptr(self._with_ghosts(_f64(ck["moments01_avg"], (nown, 4))))))
         if ck.get("phi") is not None:
-            check(L.fsim_set_field(h, b"phi", ptr(_f64(ck["phi"], (nc,)))))
+            check(L.fsim_set_field(h, b"phi", ptr(self._with_ghosts(_f64(ck["phi"], (nown,))))))
 
     def setState(self, position4=None, velocity3=None, rand4=None):
         """Raw particle state in normalised units (see fsim_set_state)."""

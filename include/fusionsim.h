@@ -54,6 +54,13 @@ enum { FSIM_F64 = 0, FSIM_F32 = 1 };
 #define FSIM_FLAG_ATOMIC_DEPOSIT  4u /* measured alternative: global-atomic per-cell sums           */
 #define FSIM_FLAG_UNFUSED_SORT   16u /* measurement: physical re-sort as a pass of its own in density()
                                       * (round-1 behaviour) instead of fused into the next step()'s sweep  */
+#define FSIM_FLAG_PERIODIC_Z    128u /* EXTENSION (the reference has no periodic
+                                      * boundary: CLAMP_TO_EDGE textures and absorbing sink rows): z is periodic --
+                                      * a pushed position wraps (z <- z - floor(z), exactly 1 -> 0) before the sink
+                                      * lookup, the 11x11 deposit footprint wraps in z, and the field solve's Poisson
+                                      * stencil and gradient wrap in z instead of the grounded end walls.  Single GPU.
+                                      * The local tables carry 8 ghost rows either side of the nz owned rows
+                                      * (fsim_local_cells = nr (nz + 16)): cell-indexed accessors return them too  */
 #define FSIM_FLAG_POST_STREAM     8u /* measured alternative: stencil and canvas draws on a second stream, under the
                                       * next frame's sweep (slower on B200: the stencil's shared memory is L1 the
                                       * sweep's gathers lose while the two share an SM)      */
@@ -173,7 +180,7 @@ int fsim_sync(fsim_sim *sim);      /* wait for the handle's stream              
  * matrix_webgl.js:224-300) on the 5-point cylindrical Poisson operator with grounded walls, warm
  * started from the previous potential, E = -grad(phi) (overwrites E), then precalc().
  *   cells (i,j) centred at r = (i+.5) dr, z = (j+.5) dz, dr = radius/nr, dz = height/nz;
- *   src = (q macro_weight / (pi radius dr dz eps0)) * density.a;
+ *   src = (q macro_weight / (pi radius dr dz eps0)) * (density.a - background)   (background: fsim_set_field, default 0);
  *   per-column coefficients in host fp64, rounded to the engine's real type:
  *     aE = (i+1)/((i+.5) dr^2), aW = i/((i+.5) dr^2), aZ = 1/dz^2, aC = aE + aW + 2 aZ,
  *     cE = aE/aC, cW = aW/aC, cZ = aZ/aC, cB = 1/aC     (finite volumes on rings; no axis ghost);
@@ -197,7 +204,9 @@ int fsim_field_rows(fsim_sim *sim, const char *name, int64_t first_row, int64_t 
 /* ---- checkpoint restore (extension; the reference can neither read nor restore its state) ---------
  * fsim_set_state is the exact inverse of fsim_get_position / _velocity / _rand: normalised units,
  * particle-id order, alive flag in position[..][3]; any pointer may be NULL.  fsim_set_field restores
- * "moments01_avg" [cells][4] (the running average of density()) or "phi" [cells].                  */
+ * "moments01_avg" [cells][4] (the running average of density()), "phi" [cells], or "background" [cells]:
+ * the neutralising background the field solve subtracts from the density, in the units of the density
+ * texture (e.g. the species' own density at t = 0 = immobile ions; zero until set).               */
 int fsim_set_state(fsim_sim *sim, const double *position4, const double *velocity3, const double *rand4);
 int fsim_set_field(fsim_sim *sim, const char *name, const double *data);
 

@@ -18,6 +18,13 @@
 
 #include "../include/fsim_constants.h"
 
+/* EXTENSION: periodic boundary in z.  The reference has none (CLAMP_TO_EDGE textures,
+ * absorbing sink mask rows, utilities.js:530-531, fusionsim.js:109-112).  When set, (1) a pushed position wraps,
+ * z <- z - floor(z) (and exactly 1 -> 0), before the sink lookup; (2) the 11x11 footprint wraps in z; (3) the
+ * Poisson stencil and the gradient wrap in z.  Set by OraclePusher before each call (spec.periodic_z). */
+static int g_periodic_z = 0;
+void orc_set_periodic_z(int on) { g_periodic_z = on; }
+
 static inline double orc_sqrt_f64(double x) { return sqrt(x); }
 static inline float orc_sqrt_f32(float x) { return sqrtf(x); }
 static inline double orc_floor_f64(double x) { return floor(x); }

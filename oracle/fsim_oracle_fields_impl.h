@@ -35,6 +35,13 @@ void ORC(orc_charge_source)(int64_t ncell, const REAL *dens, double rho_scale_d,
     const REAL k = (REAL)rho_scale_d;
     for (int64_t c = 0; c < ncell; ++c) src[c] = k * dens[4 * c + 3];
 }
+/* ... with a neutralising background given per cell in the units of the density texture (e.g. the density
+ * of the same species at t = 0 = immobile ions): src = k (dens.a - background) */
+void ORC(orc_charge_source_bg)(int64_t ncell, const REAL *dens, double rho_scale_d, const REAL *background, REAL *src)
+{
+    const REAL k = (REAL)rho_scale_d;
+    for (int64_t c = 0; c < ncell; ++c) src[c] = k * (dens[4 * c + 3] - background[c]);
+}
 
 /* `sweeps` weighted-Jacobi sweeps; phi is updated in place (tmp is scratch of the same size) */
 void ORC(orc_relax)(int64_t nr, int64_t nz, REAL *phi, REAL *tmp, const REAL *src, const double *coef_d,
@@ -52,8 +59,12 @@ void ORC(orc_relax)(int64_t nr, int64_t nz, REAL *phi, REAL *tmp, const REAL *sr
                 const int64_t c = i + j * nr;
                 const REAL pE = (i + 1 < nr) ? in[c + 1] : RC(0.0);
                 const REAL pW = (i > 0) ? in[c - 1] : RC(0.0);
-                const REAL pN = (j + 1 < nz) ? in[c + nr] : RC(0.0);
-                const REAL pS = (j > 0) ? in[c - nr] : RC(0.0);
+                REAL pN = (j + 1 < nz) ? in[c + nr] : RC(0.0);
+                REAL pS = (j > 0) ? in[c - nr] : RC(0.0);
+                if (g_periodic_z) { /* EXTENSION: periodic in z instead of the grounded end walls */
+                    if (j + 1 >= nz) pN = in[i];
+                    if (j == 0) pS = in[i + (nz - 1) * nr];
+                }
                 const REAL *k = coef + 4 * i;
                 const REAL t = ((k[0] * pE + k[1] * pW) + k[2] * (pN + pS)) + k[3] * src[c];
                 out[c] = om * t + one_m * in[c];
@@ -73,8 +84,12 @@ void ORC(orc_efield)(int64_t nr, int64_t nz, const REAL *phi, double inv2dr_d, d
             const int64_t c = i + j * nr;
             const REAL pE = (i + 1 < nr) ? phi[c + 1] : RC(0.0);
             const REAL pW = (i > 0) ? phi[c - 1] : phi[c];
-            const REAL pN = (j + 1 < nz) ? phi[c + nr] : RC(0.0);
-            const REAL pS = (j > 0) ? phi[c - nr] : RC(0.0);
+            REAL pN = (j + 1 < nz) ? phi[c + nr] : RC(0.0);
+            REAL pS = (j > 0) ? phi[c - nr] : RC(0.0);
+            if (g_periodic_z) {
+                if (j + 1 >= nz) pN = phi[i];
+                if (j == 0) pS = phi[i + (nz - 1) * nr];
+            }
             E[4 * c] = -((pE - pW) * inv2dr);
             E[4 * c + 1] = RC(0.0);
             E[4 * c + 2] = -((pN - pS) * inv2dz);

@@ -117,6 +117,10 @@ void ORC(orc_half_step)(int64_t n, REAL *pos, REAL *vel, REAL *rnd,
             REAL nx = P[0] + sf * nvx;
             REAL ny = P[1] + sf * nvy;
             REAL nzp = P[2] + sf * nvz;
+            if (g_periodic_z) { /* EXTENSION: periodic in z */
+                nzp = nzp - ORC(orc_floor)(nzp);
+                if (nzp >= RC(1.0)) nzp = RC(0.0);
+            }
             REAL r = ORC(orc_sqrt)(nx * nx + ny * ny);
             int keep = 0;
             if (r == r && nzp == nzp) { /* NaN => absorbed (documented rule) */
@@ -395,6 +399,7 @@ static inline void ORC(conv_row_pair)(const REAL *S, int64_t nr, int64_t nz, int
                                       REAL h[4])
 {
     h[0] = h[1] = h[2] = h[3] = RC(0.0);
+    if (g_periodic_z) jj = (jj % nz + nz) % nz; /* EXTENSION: the footprint wraps in z */
     if (jj < 0 || jj >= nz) return;
     if (i - di >= 0) {
         const REAL *s = S + 4 * ((i - di) + jj * nr);

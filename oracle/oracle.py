@@ -109,6 +109,7 @@ class OraclePusher:
         self.factor_z = 1 / spec["height"]
         self.step_factor = spec["dt"] * C_LIGHT  # empic.js:852
         self.corrected = bool(spec.get("corrected_preA", False))
+        self.periodic = 1 if spec.get("periodic_z") else 0  # EXTENSION, no reference counterpart
         z4 = lambda n: np.zeros((n, 4), self.dt)
         self.position, self.velocity, self.rand = z4(self.n), z4(self.n), z4(self.n)
         self.entropy = z4(N_ENTROPY * N_ENTROPY)
@@ -242,6 +243,7 @@ class OraclePusher:
 
     # -- step(), empic.js:1436-1469 ------------------------------------------------------
     def half_step(self):
+        lib().orc_set_periodic_z(C.c_int(self.periodic))
         self._f("orc_half_step")(
             C.c_int64(self.n), _p(self.position), _p(self.velocity), _p(self.rand),
             _p(self.entropy), _p(self.R1), _p(self.R2), _p(self.R3), _p(self.A),
@@ -254,6 +256,7 @@ class OraclePusher:
 
     # -- density(), empic.js:1471-1505 ---------------------------------------------------
     def density(self, literal_sprites: bool = False, timing_mt: bool = False):
+        lib().orc_set_periodic_z(C.c_int(self.periodic))
         if literal_sprites:
             self._f("orc_deposit_sprites")(
                 C.c_int64(self.n), _p(self.position), _p(self.velocity), _p(self.shape),
@@ -288,7 +291,11 @@ class OraclePusher:
         if not hasattr(self, "phi"):
             self.phi = np.zeros(self.ncell, self.dt)
             self.rho_src = np.zeros(self.ncell, self.dt)
-        self._f("orc_charge_source")(C.c_int64(self.ncell), _p(dens), C.c_double(rho_scale), _p(self.rho_src))
+        lib().orc_set_periodic_z(C.c_int(self.periodic))
+        if not hasattr(self, "background"):
+            self.background = np.zeros(self.ncell, self.dt)
+        self._f("orc_charge_source_bg")(C.c_int64(self.ncell), _p(dens), C.c_double(rho_scale), _p(self.background),
+                                        _p(self.rho_src))
         coef = np.empty((self.nr, 4), np.float64)
         lib().orc_relax_coeffs(C.c_int64(self.nr), C.c_double(dr), C.c_double(dz), _p(coef))
         tmp = np.empty_like(self.phi)
