@@ -15,6 +15,14 @@ from conftest import assert_same
 import dist_helpers as dh
 
 FRAMES = 6
+ONLY_WORLD = int(os.environ.get("FSIM_TEST_WORLD", "0"))  # a multi-GPU box is paid per GPU: run one world size per call
+
+
+def need_gpus(world):
+    if ONLY_WORLD and world != ONLY_WORLD:
+        pytest.skip(f"FSIM_TEST_WORLD={ONLY_WORLD}")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
 
 
 def free_port():
@@ -63,8 +71,7 @@ def test_gpus_nccl_match_single_oracle(tmp_path, world, exchange):
     """world ranks on world GPUs against the single-process oracle, bit for bit.  With 4 and 8 slabs the
     middle ranks have two neighbours (both halos), the source region (rows 28..36 of 64) lies outside
     the cell table of the outer ranks, and particles absorbed there respawn into a NON-neighbouring slab."""
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    need_gpus(world)
     path = str(tmp_path / "res.npz")
     mp.spawn(dh.gpu_worker, args=(world, free_port(), FRAMES, path, False, exchange), nprocs=world, join=True)
     check_against_single(path)
@@ -81,8 +88,7 @@ def test_two_ranks_gloo_self_consistent_fields(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4])
 def test_gpus_nccl_self_consistent_fields(tmp_path, world):
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    need_gpus(world)
     path = str(tmp_path / "res.npz")
     mp.spawn(dh.gpu_worker, args=(world, free_port(), FRAMES, path, True), nprocs=world, join=True)
     check_against_single(path, solve=True)
@@ -92,8 +98,7 @@ def test_gpus_nccl_self_consistent_fields(tmp_path, world):
 def test_two_gpus_replicated_alternative(tmp_path):
     """The measured alternative: particles bit-identical (the push does not communicate), counts exact,
     running average equal to 1e-12 (cross-rank sums are not in id order) and identical on both ranks."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    need_gpus(2)
     path = str(tmp_path / "res.npz")
     mp.spawn(dh.gpu_worker_replicated, args=(2, free_port(), FRAMES, path), nprocs=2, join=True)
     got = np.load(path)
