@@ -27,7 +27,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -69,48 +68,91 @@ def env_int(name, default):
         return default
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+_SAMPLER_SRC = r"""
+import sys, time
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+    print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+    while True:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        print("s", repr(time.time()), sm, int(r), flush=True)
+        time.sleep(0.003)
+except Exception as e:
+    print("err", type(e).__name__, flush=True)
+"""
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (NVML) -- from a process of its own, so that
+    neither the GIL nor the launch loop of the bench can starve it; samples are time-stamped and the ones
+    inside [begin(), end()] are kept."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag, self.recording = index, False, False
-        self.sm, self.reasons, self.sm_max = [], set(), None
-        self.ready = threading.Event()  # NVML is initialised: the timed region may start
-
-    def run(self):
+        import subprocess
+        import tempfile
+        self.t0 = self.t1 = None
+        self.sm_max = None
+        self.first = []
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
-            }
-            self.ready.set()
-            while not self.stop_flag:
-                if self.recording:  # only samples taken DURING the timed region count
-                    self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                    try:
-                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                    except Exception:
-                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for bit, nm in names.items():
-                        if r & bit:
-                            self.reasons.add(nm)
-                time.sleep(0.002)
-        except Exception as e:  # NVML missing: record that, never fail the bench
-            self.reasons.add("nvml_unavailable:" + type(e).__name__)
-            self.ready.set()
+            self.log = tempfile.NamedTemporaryFile("w+", suffix=".clocks", delete=False)  # a file, not a pipe: never blocks the sampler
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=self.log,
+                                         stderr=subprocess.DEVNULL)
+            for _ in range(2000):  # "max <MHz>" once NVML is up: the timed region may start
+                with open(self.log.name) as f:
+                    line = f.readline()
+                if line.endswith("\n"):
+                    self.first = line.split()
+                    break
+                if self.proc.poll() is not None:
+                    break
+                time.sleep(0.01)
+        except Exception:
+            self.proc = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def result(self):
-        sm = sorted(self.sm)
+        sm, reasons = [], set()
+        if self.proc is None or not self.first or self.first[0] != "max":
+            try:
+                if self.proc is not None:
+                    self.proc.kill()
+                os.unlink(self.log.name)
+            except Exception:
+                pass
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"], "samples": 0}
+        self.sm_max = int(self.first[1])
+        time.sleep(0.01)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        with open(self.log.name) as f:
+            out = f.read()
+        os.unlink(self.log.name)
+        for line in out.splitlines():
+            f = line.split()
+            if len(f) == 4 and f[0] == "s" and self.t0 <= float(f[1]) <= self.t1:
+                sm.append(int(f[2]))
+                for bit, nm in self.REASONS.items():
+                    if int(f[3]) & bit:
+                        reasons.add(nm)
+        sm.sort()
         return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def measured_peak():
@@ -401,13 +443,11 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing: W warm-up frames, then exactly K frames ----
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local)  # returns once its process has NVML up
     for _ in range(args.warmup):
         frame()
-    sampler.ready.wait(timeout=20)  # NVML start-up must not eat the timed region
     barrier()
-    sampler.recording = True
+    sampler.begin()
     l0 = sim.launch_count
     t_host0 = time.perf_counter()
     sim.mark(0)
@@ -416,12 +456,11 @@ def run_ours(args):
     sim.mark(1)
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     ms_total = sim.elapsed_ms(0, 1)
-    sampler.recording = False
+    sampler.end()
     barrier()
-    sampler.stop_flag = True
     launches = sim.launch_count - l0
     ms_total = reduce_max(ms_total)
-    sampler.join(timeout=2)
+    clocks = sampler.result()
     n_total = n_local * world
     value = 2.0 * n_total * args.steps / (ms_total * 1e-3)
 
@@ -573,7 +612,7 @@ def run_ours(args):
             "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
             "config": make_config(args.workload, world, args.precision, n_total, nr, nz, args.field_sweeps, args.decomposition),
-            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb, "check": check_line, "comm_ms_per_step": comm,
             "push_only_pushes_per_s": halves * n_local * world / (push_ms * 1e-3),
             "extension_field_solve": ext,
