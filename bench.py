@@ -506,8 +506,11 @@ def run_ours(args):
         c = sim.comm_ms()
         sim.comm_timing = False
         comm = {k: reduce_max(v / args.steps) for k, v in c.items()}
+        comm["migrate_exchange_min_over_ranks"] = -reduce_max(-c["migrate_exchange"] / args.steps)  # the slowest rank waits least
+        comm["migrate_exchange_alone"] = reduce_max(sim.exchange_alone_ms())  # the collective by itself, all ranks entering together
         comm["what"] = ("max over ranks, ms per frame, CUDA events on the frame's stream: migrate_exchange = the all-to-all of "
-                        "the fixed-size record regions (includes waiting for the slowest peer); halo_exchange_exposed = what "
+                        "the fixed-size record regions (includes waiting for the slowest peer: compare migrate_exchange_alone, "
+                        "the same collective timed with all ranks entering together, and the minimum over ranks); halo_exchange_exposed = what "
                         "is left of the 5-row halo exchange after the interior stencil ran under it; host_wait = host time "
                         "blocked in synchronisations inside the frame (none with the fixed-region exchange)")
         comm["exchange"] = args.exchange

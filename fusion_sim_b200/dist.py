@@ -257,6 +257,24 @@ class SlabPusher:
                 self._ev["halo_exchange_exposed"].append((e0, self._mark()))
         self._lib.check(L.fsim_density_end(h))       # halo rows in, stencil on the boundary tiles
 
+    def exchange_alone_ms(self, reps: int = 50) -> float:
+        """Device time of ONE all-to-all of the (fixed-size) migration regions with nothing else going on: every
+        rank enters together, so this is the collective's own cost -- what migrate_exchange exceeds it by inside a
+        frame is time spent waiting for the slowest rank."""
+        if self.exchange != "fixed":
+            return float("nan")
+        with torch.cuda.stream(self.stream):
+            for _ in range(5):
+                exchange_regions(self._send, self._send_bytes, self._recv, self._recv_bytes)
+            self.stream.synchronize()
+            dist.barrier()
+            e0 = self._mark()
+            for _ in range(reps):
+                exchange_regions(self._send, self._send_bytes, self._recv, self._recv_bytes)
+            e1 = self._mark()
+            e1.synchronize()
+        return float(e0.elapsed_time(e1)) / reps
+
     def comm_ms(self, reset: bool = True) -> dict:
         """Device time (ms, CUDA events on the frame's stream) spent in the exchanges since the last
         call: the migration all-to-all (it waits for the slowest peer) and the part of the halo
