@@ -190,8 +190,14 @@ def build_scene(workload, rank, world, seed=2026):
         return c1_scene(seed)
     nz = nz_local * world
     spec = scaled_spec(nr, nz, n * world)
-    lo = max(0.02, rank / world)
-    hi = min(0.98, (rank + 1) / world)
+    # The plasma keeps the SAME margin in grid rows from the two end walls whatever the number of slabs (2 % of one
+    # slab = 41 rows at C5, as on one GPU), so every rank sees the particle density of the single-GPU case to within
+    # 2 %.  (Round 1 kept 2 % of the WHOLE height free: at 8 slabs the two end ranks then held their 64 Mi particles
+    # in 84 % of their rows, 19 % denser than the middle ranks -- their per-cell pass ran 0.08 ms slower and every
+    # frame waited for them.)
+    margin = 0.02 / world
+    lo = max(margin, rank / world)
+    hi = min(1.0 - margin, (rank + 1) / world)
     pos, vel = plasma_particles(spec, n, seed + rank, z_lo=lo, z_hi=hi)
     sink, source = c1_sink_source(nr, nz)
     return dict(spec=spec, position=pos, velocity=vel, sink_mask=sink, source_pdf=source,
@@ -466,6 +472,7 @@ def run_ours(args):
 
     # ---- run invariants, reduced over the ranks: nothing lost, nothing duplicated, everything deposited ----
     dg = sim.check_digest()
+    n_local_now = dg["particles"]
     tot = all_ranks([dg["particles"], dg["id_sum"], dg["deposited"]])
     (xr,) = all_ranks([dg["id_xor"]], op="xor")
     want_sum = (n_total * (n_total - 1) // 2) & 0xffffffffffffffff
@@ -515,6 +522,19 @@ def run_ours(args):
                         "blocked in synchronisations inside the frame (none with the fixed-region exchange)")
         comm["exchange"] = args.exchange
         comm["host_enqueue_ms_per_step"] = reduce_max(host_enqueue_ms / args.steps)
+    per_rank = None
+    if world > 1:  # who sets the pace: every rank's own kernel time per frame, its sweep, its SM clock under load
+        import torch.distributed as dist
+        mine = [sum(v["ms_per_step"] for v in kern.values()), kern.get("push2", {}).get("ms_per_launch", 0.0),
+                kern.get("cellsum", {}).get("ms_per_launch", 0.0), float(clocks["sm_mhz"] or 0),
+                1.0 if "sw_power_cap" in clocks["reasons"] else 0.0, float(n_local_now)]
+        t = torch.tensor(mine, dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        cols = list(zip(*[a.tolist() for a in allr]))
+        per_rank = {"kernels_ms_per_step": [round(v, 4) for v in cols[0]], "push2_ms_per_launch": [round(v, 4) for v in cols[1]],
+                    "cellsum_ms_per_launch": [round(v, 4) for v in cols[2]], "sm_mhz_median": cols[3],
+                    "sw_power_cap_seen": [bool(v) for v in cols[4]], "particles": [int(v) for v in cols[5]]}
     peak, peak_kind = measured_peak()
     # dominant kernel: the fused step sweep (both half-steps of step() in one pass over HBM,
     # push.cu NH=2).  Its algorithmic bytes are those of ONE sweep: particle state read + written
@@ -616,7 +636,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": make_config(args.workload, world, args.precision, n_total, nr, nz, args.field_sweeps, args.decomposition),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cb, "check": check_line, "comm_ms_per_step": comm,
+            "roofline": roofline, "cpu_baseline": cb, "check": check_line, "comm_ms_per_step": comm, "per_rank": per_rank,
             "push_only_pushes_per_s": halves * n_local * world / (push_ms * 1e-3),
             "extension_field_solve": ext,
         }
