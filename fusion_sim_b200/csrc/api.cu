@@ -471,6 +471,9 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     s->ncell_local = (int64_t)s->nr * s->rows;
     s->pitch = (s->nr + 3) / 4 * 4;
     s->plane = (int64_t)s->pitch * s->rows;
+#ifdef FSIM_TUNE
+    if (const char *e = getenv("FSIM_PLANE_PAD")) s->plane += atoll(e) / 4 * 4;  // tuning build only: channel-plane stride padding (reals)
+#endif
 
     // physical quantities, empic.js:44-46, :852 and the toFixed(20) literals of :527,:606,:647
     s->h = sp->particle_charge * sp->dt / (2 * sp->particle_mass);
