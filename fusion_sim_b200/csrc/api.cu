@@ -497,7 +497,6 @@ static int create_impl(const fsim_spec *sp, fsim_sim *s)
     }
     FSIM_TRY(dalloc(&s->key, s->cap));
     FSIM_TRY(dalloc(&s->perm, s->cap));
-    if (!s->slab) FSIM_TRY(dalloc(&s->rank8, s->cap));
     for (int q = 0; q < 2; ++q) FSIM_TRY(dalloc_bytes(&s->dcol[q], s->rs * s->cap));
     FSIM_TRY(dalloc(&s->counts, s->ncell_local + 1));
     FSIM_TRY(dalloc(&s->starts, s->ncell_local + 2));
@@ -566,7 +565,7 @@ static void free_all(fsim_sim *s)
     }
     void *ptrs[] = {s->key, s->perm, s->dcol[0], s->dcol[1], s->counts, s->starts, s->cursor, s->blocksums, s->cellrec, s->E, s->B, s->sink,
                     s->entropy, s->invcdf, s->cellsum, s->cellcount, s->mom, s->norm, s->avg,
-                    s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf, s->leavers, s->rank8};
+                    s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf, s->leavers};
     for (void *p : ptrs) cudaFree(p);
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef); cudaFree(s->background);
     cudaFree(s->bmag); cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);

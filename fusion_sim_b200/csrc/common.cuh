@@ -158,9 +158,6 @@ struct fsim_sim {
     uint32_t *perm = nullptr;     // [cap] particle slots ordered by cell (index sort)
     void *dcol[2] = {};           // [cap] sprite colour 0.001*(v_r, v_a) of each slot (deposit prepass); 0.001*v_z is
                                   // formed by the per-cell pass from the stored v_z (8 bytes less written per particle)
-    uint8_t *rank8 = nullptr;     // [cap] place of each particle inside its cell's segment, as the histogram atomic returned it
-                                  // (255 = 255 or more); saves the cursor atomics of the index scatter.  Not in slab mode.
-    bool ranks_valid = false;     // rank8[] matches key[] and counts[]
     bool keys_valid = false;      // key[] and the histogram in counts[] match the current positions
     bool counts_dirty = false;    // counts[] holds a histogram that no scan has consumed yet
     bool binned = false;          // starts[] and perm[] match the current positions

@@ -36,7 +36,6 @@ struct PushArgs {
     uint32_t *key;      // optional deposit prepass: sort key, sprite colour, histogram
     Real *dcol[2];
     uint32_t *counts;
-    uint8_t *rank8;     // optional: place of each particle in its cell (returned by the histogram atomics)
     uint32_t *oob;
     uint32_t *leavers, *nleavers;  // slab mode: slots whose new row is not owned (migration list)
     int own0, own_rows;
@@ -249,17 +248,8 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
 
 // Deposit prepass on the NEW state (what density() will see): sort key, sprite colour and the
 // warp-aggregated histogram of the counting sort.  Whole warps must call this converged.
-// What the histogram atomics hand back: the place of each particle inside its cell's segment (arrival order).
-// With it the index scatter of the counting sort needs no cursor atomics (sort.cu).
-template <int V>
-struct CellRank {
-    uint32_t base[V], rank[V];
-    int leader[V];
-};
-
 template <typename Real, int V>
-__device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int64_t p0, const int64_t n, const Slots<Real, V> &t,
-                                             CellRank<V> &cr)
+__device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int64_t p0, const int64_t n, const Slots<Real, V> &t)
 {
     const int lane = threadIdx.x & 31;
     uint32_t newcell[V];
@@ -268,25 +258,12 @@ __device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int6
     for (int k = 0; k < V; ++k)
         newcell[k] = sprite_key_colour<Real>(t.x[k], t.y[k], t.z[k], t.rcur[k], t.vx[k], t.vy[k], t.vz[k], a.nr, a.nz,
                                              a.row0, a.rows, a.own_lo, a.own_hi, col[0][k], col[1][k], col[2][k]);
-    // histogram first: when the ranks are wanted the atomics RETURN a value, and their round trip to L2 then runs
-    // under the stores that follow
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const bool valid = p0 + k < n;
-        const uint32_t c = valid ? (newcell[k] & KEY_MASK) : 0xffffffffu;
-        uint32_t len;
-        warp_runs(c, lane, cr.leader[k], len, cr.rank[k]);
-        cr.base[k] = 0;
-        if (valid && cr.rank[k] == 0) {
-            if (a.rank8) cr.base[k] = atomicAdd(a.counts + c, len);
-            else atomicAdd(a.counts + c, len);
-        }
-    }
 #pragma unroll
     for (int q = 0; q < 2; ++q) st_stream<Real, V>(a.dcol[q] + p0, col[q]);  // 0.001 v_z is formed by the per-cell pass from v_z itself
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const bool valid = p0 + k < n;
+        const uint32_t c = valid ? (newcell[k] & KEY_MASK) : 0xffffffffu;
         if (valid) a.key[p0 + k] = newcell[k];
         if (valid && a.leavers) {
             const int gj = tex_idx(t.z[k], a.nz);
@@ -296,18 +273,10 @@ __device__ __forceinline__ void emit_prepass(const PushArgs<Real> &a, const int6
                 a.leavers[at] = (uint32_t)(p0 + k);
             }
         }
-    }
-}
-
-// ... and, after the particle state has been stored, the place in the cell as one byte per slot (255 = "255 or more":
-// those few take a cursor atomic in the scatter)
-template <int V>
-__device__ __forceinline__ void store_cell_ranks(uint8_t *rank8, const int64_t p0, const int64_t n, const CellRank<V> &cr)
-{
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const uint32_t b = __shfl_sync(0xffffffffu, cr.base[k], cr.leader[k]);
-        if (p0 + k < n) rank8[p0 + k] = (uint8_t)min(b + cr.rank[k], 255u);
+        int leader;
+        uint32_t len, rank;
+        warp_runs(c, lane, leader, len, rank);
+        if (valid && rank == 0) atomicAdd(a.counts + c, len);
     }
 }
 
@@ -372,10 +341,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) push_kernel(const PushArgs<Real> 
         for (int k = 0; k < V; ++k) t.al[k] = a.alive[p0 + k];
     }
     advance<Real, V, NH, OPT>(a, p0, n, t);
-    CellRank<V> cr;
-    if (a.key) emit_prepass<Real, V>(a, p0, n, t, cr);
     store_slots<Real, V>(a, p0, t);
-    if (a.key && a.rank8) store_cell_ranks<V>(a.rank8, p0, n, cr);
+    if (a.key) emit_prepass<Real, V>(a, p0, n, t);
 }
 
 
@@ -451,10 +418,8 @@ __global__ void __launch_bounds__(256, MINB) push_tma_kernel(const PushArgs<Real
         if (tid == 0 && tile + STAGES * stride < ntiles) issue(stage, tile + STAGES * stride);
         const int64_t p0 = tile * T + tid;
         advance<Real, 1, NH>(a, p0, n, t);
-        CellRank<1> cr;
-        if (a.key) emit_prepass<Real, 1>(a, p0, n, t, cr);
         store_slots<Real, 1>(a, p0, t);
-        if (a.key && a.rank8) store_cell_ranks<1>(a.rank8, p0, n, cr);
+        if (a.key) emit_prepass<Real, 1>(a, p0, n, t);
     }
 }
 
@@ -481,7 +446,6 @@ static PushArgs<Real> make_args(fsim_sim *s, bool with_hist, bool resort)
     a.key = with_hist ? s->key : nullptr;
     for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
     a.counts = s->counts;
-    a.rank8 = (with_hist && !s->slab && !(s->spec.flags & FSIM_FLAG_CURSOR_SCATTER)) ? s->rank8 : nullptr;  // a slab's migration changes the segments
     a.oob = s->oob;
     a.leavers = (with_hist && s->slab) ? s->leavers : nullptr;
     a.nleavers = s->mscratch + MC_NLEAVERS;
@@ -588,7 +552,6 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
     }
     s->binned = false;
     s->keys_valid = with_hist;
-    s->ranks_valid = with_hist && !s->slab && !(s->spec.flags & FSIM_FLAG_CURSOR_SCATTER);
     s->have_leavers = with_hist && s->slab;
     if (with_hist) s->counts_dirty = true;
     return rc;

@@ -23,7 +23,6 @@ template <typename Real>
 struct PrepassArgs {
     const Real *x, *y, *z, *vx, *vy, *vz;
     uint32_t *key, *counts;
-    uint8_t *rank8;  // optional: place of each particle inside its cell (see push.cu)
     Real *dcol[2];
     int64_t n;
     const uint32_t *n_dev;
@@ -51,15 +50,7 @@ __global__ void __launch_bounds__(256) prepass_kernel(const PrepassArgs<Real> a)
     int leader;
     uint32_t len, rank;
     warp_runs(c, (int)(threadIdx.x & 31), leader, len, rank);
-    uint32_t base = 0;
-    if (valid && rank == 0) {
-        if (a.rank8) base = atomicAdd(a.counts + c, len);
-        else atomicAdd(a.counts + c, len);
-    }
-    if (a.rank8) {
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid) a.rank8[p] = (uint8_t)min(base + rank, 255u);
-    }
+    if (valid && rank == 0) atomicAdd(a.counts + c, len);
 }
 
 // ---- exclusive scan over ncell counts: per-block sums, scan of block sums, final pass ----
@@ -146,7 +137,7 @@ scan_tile_offsets_kernel(uint32_t *tile_sums, int ntiles)
 // counts[] for the next histogram.
 __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_final_kernel(uint32_t *__restrict__ counts, int64_t m, const uint32_t *__restrict__ tile_offsets,
-                  uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor, uint32_t cursor_bias)
+                  uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor)
 {
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
@@ -164,11 +155,10 @@ scan_final_kernel(uint32_t *__restrict__ counts, int64_t m, const uint32_t *__re
     if (base + SCAN_ITEMS <= m) {
         const uint4 a = make_uint4(o[0], o[1], o[2], o[3]), b = make_uint4(o[4], o[5], o[6], o[7]);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t cb = cursor_bias;  // ranked scatter: only places 255.. of a cell come from the cursor
         *reinterpret_cast<uint4 *>(starts + base) = a;
         *reinterpret_cast<uint4 *>(starts + base + 4) = b;
-        *reinterpret_cast<uint4 *>(cursor + base) = make_uint4(o[0] + cb, o[1] + cb, o[2] + cb, o[3] + cb);
-        *reinterpret_cast<uint4 *>(cursor + base + 4) = make_uint4(o[4] + cb, o[5] + cb, o[6] + cb, o[7] + cb);
+        *reinterpret_cast<uint4 *>(cursor + base) = a;
+        *reinterpret_cast<uint4 *>(cursor + base + 4) = b;
         *reinterpret_cast<uint4 *>(counts + base) = z;
         *reinterpret_cast<uint4 *>(counts + base + 4) = z;
     } else {
@@ -176,7 +166,7 @@ scan_final_kernel(uint32_t *__restrict__ counts, int64_t m, const uint32_t *__re
         for (int k = 0; k < SCAN_ITEMS; ++k)
             if (base + k < m) {
                 starts[base + k] = o[k];
-                cursor[base + k] = o[k] + cursor_bias;
+                cursor[base + k] = o[k];
                 counts[base + k] = 0;
             }
     }
@@ -253,21 +243,6 @@ index_scatter_kernel(const uint32_t *__restrict__ key, uint32_t *__restrict__ cu
     }
 }
 
-// The same index list without cursor atomics: the place of a particle inside its cell's segment came back from
-// the histogram atomic that counted it (rank8, written by the sweep / the prepass); only particles that are the
-// 256th or later of their cell still take a cursor atomic.  Pure data movement: 9 bytes read, 4 written per particle.
-__global__ void __launch_bounds__(256)
-index_scatter_ranked_kernel(const uint32_t *__restrict__ key, const uint8_t *__restrict__ rank8,
-                            const uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm, int64_t n)
-{
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const uint32_t kk = key[p], c = kk & KEY_MASK, r = rank8[p];
-    const uint32_t at = (r < 255u) ? starts[c] + r : atomicAdd(cursor + c, 1u);
-    FSIM_ASSERT((int64_t)at < n && at < starts[c + 1]);
-    perm[at] = (uint32_t)p | (kk & KEY_CLIPPED);
-}
-
 // key[] + colour + histogram from the stored state
 int launch_keys(fsim_sim *s)
 {
@@ -284,7 +259,6 @@ int launch_keys(fsim_sim *s)
             a.z = (const Real *)s->part[c][AZ]; a.vx = (const Real *)s->part[c][AVX];
             a.vy = (const Real *)s->part[c][AVY]; a.vz = (const Real *)s->part[c][AVZ];
             a.key = s->key; a.counts = s->counts;
-            a.rank8 = (!s->slab && !(s->spec.flags & FSIM_FLAG_CURSOR_SCATTER)) ? s->rank8 : nullptr;
             for (int q = 0; q < 2; ++q) a.dcol[q] = (Real *)s->dcol[q];
             a.n = s->n; a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0; a.rows = s->rows;
             a.n_dev = s->n_async ? s->mscratch + MC_NLIVE : nullptr;
@@ -297,7 +271,6 @@ int launch_keys(fsim_sim *s)
         FSIM_TRY(rc);
     }
     s->keys_valid = true;
-    s->ranks_valid = !s->slab && !(s->spec.flags & FSIM_FLAG_CURSOR_SCATTER);
     s->counts_dirty = true;
     return FSIM_OK;
 }
@@ -311,17 +284,12 @@ int launch_bin(fsim_sim *s)
         Bracket b(s, "scan");
         scan_tile_sums_kernel<<<ntiles, SCAN_BLOCK, 0, s->stream>>>(s->counts, m, s->blocksums);
         scan_tile_offsets_kernel<<<1, SCAN_BLOCK, 0, s->stream>>>(s->blocksums, ntiles);
-        scan_final_kernel<<<ntiles, SCAN_BLOCK, 0, s->stream>>>(s->counts, m, s->blocksums, s->starts, s->cursor,
-                                                                 s->ranks_valid ? 255u : 0u);
+        scan_final_kernel<<<ntiles, SCAN_BLOCK, 0, s->stream>>>(s->counts, m, s->blocksums, s->starts, s->cursor);
         s->launches += 2;
         FSIM_CUDA(cudaGetLastError());
     }
     s->counts_dirty = false;  // scan_final zeroed counts[]
-    if (s->n && s->ranks_valid) {
-        Bracket b(s, "index_scatter");
-        index_scatter_ranked_kernel<<<grid_for(s->n, 256), 256, 0, s->stream>>>(s->key, s->rank8, s->starts, s->cursor, s->perm, s->n);
-        FSIM_CUDA(cudaGetLastError());
-    } else if (s->n) {
+    if (s->n) {
         Bracket b(s, "index_scatter");
         index_scatter_kernel<<<grid_for((s->n + IDX_ITEMS - 1) / IDX_ITEMS, 256), 256, 0, s->stream>>>(
             s->key, s->cursor, s->perm, s->n, s->n_async ? s->mscratch + MC_NLIVE : nullptr);

@@ -61,9 +61,6 @@ enum { FSIM_F64 = 0, FSIM_F32 = 1 };
                                       * stencil and gradient wrap in z instead of the grounded end walls.  Single GPU.
                                       * The local tables carry 8 ghost rows either side of the nz owned rows
                                       * (fsim_local_cells = nr (nz + 16)): cell-indexed accessors return them too  */
-#define FSIM_FLAG_CURSOR_SCATTER 256u /* measurement: the counting sort's index scatter takes its places from cursor
-                                      * atomics (round 1; always so on a slab) instead of the ranks the histogram
-                                      * atomics of the sweep returned                                             */
 #define FSIM_FLAG_POST_STREAM     8u /* measured alternative: stencil and canvas draws on a second stream, under the
                                       * next frame's sweep (slower on B200: the stencil's shared memory is L1 the
                                       * sweep's gathers lose while the two share an SM)      */
