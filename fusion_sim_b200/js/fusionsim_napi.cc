@@ -94,7 +94,13 @@ class Sim : public Napi::ObjectWrap<Sim> {
     Napi::Value AddCurrentZ(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_current_z(sim_, i[0].As<Napi::Number>())); return i.Env().Undefined(); }
     Napi::Value AddBZ(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_bz(sim_, i[0].As<Napi::Number>())); return i.Env().Undefined(); }
     Napi::Value AddBTheta(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_btheta(sim_, i[0].As<Napi::Number>())); return i.Env().Undefined(); }
-    Napi::Value AddSpindle(const Napi::CallbackInfo &i) { check(i.Env(), fsim_add_spindle_cusp_plasma_field(sim_, 0, 0, 0)); return i.Env().Undefined(); }
+    // addSpindleCuspPlasmaField(r, B_c, beta_c = 1): empic.js:1369; the boundary solve specified in include/fusionsim.h
+    Napi::Value AddSpindle(const Napi::CallbackInfo &i)
+    {
+        const double beta = i.Length() > 2 && i[2].IsNumber() ? i[2].As<Napi::Number>().DoubleValue() : 1.0;
+        check(i.Env(), fsim_add_spindle_cusp_plasma_field(sim_, i[0].As<Napi::Number>(), i[1].As<Napi::Number>(), beta));
+        return i.Env().Undefined();
+    }
     Napi::Value Precalc(const Napi::CallbackInfo &i) { check(i.Env(), fsim_precalc(sim_)); return i.Env().Undefined(); }
     Napi::Value Step(const Napi::CallbackInfo &i) { check(i.Env(), fsim_step(sim_)); return i.Env().Undefined(); }
     Napi::Value Density(const Napi::CallbackInfo &i) { check(i.Env(), fsim_density(sim_)); return i.Env().Undefined(); }
