@@ -325,3 +325,30 @@ def gpu_worker_replicated(rank, world, port, frames, result_path):
             np.savez(result_path, **res)
     finally:
         dist.destroy_process_group()
+
+
+def gpu_worker_overflow(rank, world, port, result_path):
+    """Exchange regions far too small for the scene: sync() must say so (never a silent loss of particles)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from fusion_sim_b200 import Error
+        from fusion_sim_b200.dist import SlabPusher
+        sc = scene_for_dist()
+        loc, ids = split_scene(sc, rank, world)
+        s = SlabPusher(dict(sc["spec"], device=rank), loc, rank, world, halo_rows=8, cap_neighbour=2, cap_far=1)
+        msg = ""
+        try:
+            for _ in range(3):
+                s.step()
+                s.density()
+            s.sync()
+        except Error as e:
+            msg = str(e)
+        out = _gather(rank, world, msg)
+        if rank == 0:
+            with open(result_path, "w") as f:
+                f.write("\n".join(out))
+    finally:
+        dist.destroy_process_group()

@@ -49,6 +49,30 @@ def check_against_single(path, solve=False):
     assert int(got["moved"]) > 0  # particles really crossed the slab boundary / respawned across it
 
 
+def test_exchange_region_layout():
+    """Host side of the fixed-region exchange: both ends of a pair compute the same sizes without talking."""
+    from fusion_sim_b200.dist import HEADER_BYTES, region_bytes, region_capacities
+    for world in (2, 4, 8):
+        caps = [region_capacities(r, world, 1000, 10) for r in range(world)]
+        for a in range(world):
+            assert caps[a][a] == 0
+            for b in range(world):
+                assert caps[a][b] == caps[b][a]  # what a sends to b is what b expects from a
+                if a != b:
+                    assert caps[a][b] == (1000 if abs(a - b) == 1 else 10)
+    assert region_bytes(0, 88) == HEADER_BYTES and region_bytes(3, 88) % 16 == 0 and region_bytes(3, 88) >= HEADER_BYTES + 3 * 88
+
+
+@pytest.mark.gpu
+def test_gpus_exchange_overflow_is_reported(tmp_path):
+    """A send region too small for a frame's leavers: sync() raises FSIM_ERR_RANGE on the rank it happened on."""
+    need_gpus(2)
+    path = str(tmp_path / "msg.txt")
+    mp.spawn(dh.gpu_worker_overflow, args=(2, free_port(), path), nprocs=2, join=True)
+    msgs = open(path).read().split("\n")
+    assert any("send region" in m for m in msgs), msgs
+
+
 def test_slab_bounds():
     from fusion_sim_b200.dist import slab_bounds
     assert slab_bounds(800, 8) == [0, 100, 200, 300, 400, 500, 600, 700, 800]
