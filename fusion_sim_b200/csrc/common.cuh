@@ -147,6 +147,8 @@ struct fsim_sim {
     uint32_t *pid[2] = {};
     int cur = 0;
     bool ids_identity = true;   // storage order == id order
+    bool fresh = true;          // nothing per particle has been set or computed since create / fsim_set_particle_count
+    bool rand_default = true;   // the RNG state is the engine's default draw (a function of the particle id)
     uint32_t id_base = 0;
 
     // sort scratch
