@@ -1388,10 +1388,11 @@ int fsim_sync(fsim_sim *s)
     if (merr) {
         FSIM_CUDA(cudaMemsetAsync(s->mscratch + MC_ERR, 0, sizeof merr, s->stream));
         return fail(FSIM_ERR_RANGE, std::string("slab exchange: ") +
-                    ((merr & MERR_SEND_OVERFLOW) ? "more particles left for one rank in a frame than its send region holds "
-                                                   "(raise the exchange capacity, or use the exact exchange); " : "") +
-                    ((merr & MERR_CAPACITY) ? "arrivals exceed the particle capacity of this rank; " : "") +
-                    "the particle state is no longer valid");
+                    ((merr & MERR_SEND_OVERFLOW) ? "more particles left for one rank in a frame than its send region holds: the "
+                                                   "stragglers stayed behind (they migrate in a later frame), so that frame's "
+                                                   "density misses them -- raise the exchange capacity, or use the exact exchange; " : "") +
+                    ((merr & MERR_CAPACITY) ? "arrivals exceeded the particle capacity of this rank and were DROPPED: the "
+                                              "particle state is no longer valid; " : ""));
     }
     if (oob) {
         FSIM_CUDA(cudaMemsetAsync(s->oob, 0, sizeof oob, s->stream));  // ordered before the next push by the stream
