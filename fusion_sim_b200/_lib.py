@@ -107,6 +107,10 @@ _SIGS = {
     "fsim_set_field": (C.c_int, [_P, C.c_char_p, _P]),
     "fsim_solve_fields": (C.c_int, [_P, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_solve_fields_stage": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_int32]),
+    "fsim_em_init": (C.c_int, [_P]),
+    "fsim_em_set": (C.c_int, [_P, C.c_char_p, _P]),
+    "fsim_em_get": (C.c_int, [_P, C.c_char_p, _P]),
+    "fsim_em_step": (C.c_int, [_P, C.c_double, C.c_int32]),
     "fsim_field_rows": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fsim_cellsum_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fsim_migrate_setup": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(_P), C.POINTER(_P), _P, _P]),

@@ -614,6 +614,7 @@ static void free_all(fsim_sim *s)
                     s->heavy_list, s->medium_list, s->heavy_n, s->oob, s->stage, s->migr, s->mscratch, s->hole_flag, s->halo_buf, s->leavers};
     for (void *p : ptrs) cudaFree(p);
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef); cudaFree(s->background);
+    em_free(s);
     cudaFree(s->bmag); cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);
     if (s->n_pinned) cudaFreeHost(s->n_pinned);
     for (auto &e : s->n_event)
@@ -1122,6 +1123,55 @@ int fsim_solve_fields(fsim_sim *s, double macro_weight, int32_t sweeps, double o
     if (left >= 1) { FSIM_TRY(wrap(s->phi[s->phi_cur])); FSIM_TRY(finish(s, launch_relax(s, 1, omega))); }
     FSIM_TRY(wrap(s->phi[s->phi_cur]));
     FSIM_TRY(finish(s, launch_efield(s)));
+    FSIM_TRY(finish(s, launch_precalc(s)));
+    s->have_precalc = true;
+    return FSIM_OK;
+}
+
+// EXTENSION (BASELINE configs[2]): electromagnetic field update on an axisymmetric Yee mesh (em.cu).
+// Specification: include/fusionsim.h (fsim_em_step).
+static int em_ready(fsim_sim *s)
+{
+    if (!s->em_on) return fail(FSIM_ERR_STATE, "no electromagnetic fields on this handle: call fsim_em_init first");
+    return FSIM_OK;
+}
+int fsim_em_init(fsim_sim *s)
+{
+    FSIM_TRY(check(s));
+    if (s->slab || s->ring)
+        return fail(FSIM_ERR_UNSUPPORTED, "emInit: the electromagnetic update runs on one GPU holding the whole, non-periodic grid");
+    FSIM_TRY(finish(s, em_init(s)));
+    s->em_on = true;
+    return FSIM_OK;
+}
+int fsim_em_set(fsim_sim *s, const char *name, const double *data)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(em_ready(s));
+    if (!name || !data) return fail(FSIM_ERR_INVALID, "null argument");
+    const int f = em_field_index(name);
+    if (f < 0) return fail(FSIM_ERR_INVALID, std::string("emSet: unknown field ") + name + " (Er Ez Bt Et Br Bz)");
+    const int64_t cnt = em_field_count(s, f);
+    return finish(s, table_in(s, data, s->em[f], cnt));
+}
+int fsim_em_get(fsim_sim *s, const char *name, double *out)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(em_ready(s));
+    if (!name || !out) return fail(FSIM_ERR_INVALID, "null argument");
+    const int f = em_field_index(name);
+    if (f < 0) return fail(FSIM_ERR_INVALID, std::string("emGet: unknown field ") + name + " (Er Ez Bt Et Br Bz)");
+    return finish(s, table_out(s, s->em[f], out, em_field_count(s, f)));
+}
+int fsim_em_step(fsim_sim *s, double macro_weight, int32_t with_current)
+{
+    FSIM_TRY(check(s));
+    FSIM_TRY(em_ready(s));
+    if (!(macro_weight == macro_weight) || isinf(macro_weight)) return fail(FSIM_ERR_INVALID, ".macro_weight <- must be a finite number");
+    if (with_current && !s->mom)
+        return fail(FSIM_ERR_STATE, "emStep: the current comes from moments01, kept only with FSIM_FLAG_KEEP_MOMENTS");
+    FSIM_TRY(finish(s, em_step(s, macro_weight, with_current != 0)));
+    s->bmag_valid = false;  // the |B| layer of the canvas is stale
     FSIM_TRY(finish(s, launch_precalc(s)));
     s->have_precalc = true;
     return FSIM_OK;

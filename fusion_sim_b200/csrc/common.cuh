@@ -194,6 +194,13 @@ struct fsim_sim {
     alignas(64) unsigned char tm_phi[2][128] = {};  // CUtensorMaps of phi[0], phi[1], rho_src
     alignas(64) unsigned char tm_src[128] = {};
 
+    // EXTENSION: electromagnetic (Yee) field update (em.cu), allocated by fsim_em_init()
+    void *em[6] = {};            // E_r E_z B_t E_t B_r B_z on their own lattices, row-major [j][i]
+    void *em_B0 = nullptr;       // [ncell_local][3] the static B underneath
+    void *em_coef = nullptr;     // [nr+1][6] per-column coefficients
+    double em_weight = 0.0;      // macro weight the coefficients were formed with (NaN: not uploaded)
+    bool em_on = false;
+
     // staging
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -404,6 +411,12 @@ int launch_add_uniform(fsim_sim *s, int kind, double val);
 int spindle_solve(fsim_sim *s, double coil_r, double B_c, double beta_c);  // spindle.cu
 int launch_render(fsim_sim *s, uint8_t *dev_rgba, cudaStream_t st);
 int ensure_fieldsolve(fsim_sim *s);
+// em.cu
+int em_init(fsim_sim *s);
+int em_step(fsim_sim *s, double macro_weight, bool with_current);
+void em_free(fsim_sim *s);
+int em_field_index(const std::string &name);
+int64_t em_field_count(const fsim_sim *s, int field);
 int launch_charge_source(fsim_sim *s, const void *dens_a, double rho_scale);
 int ring_wrap_rows(fsim_sim *s, void *plane_base, int nrows);  // periodic z: owned boundary rows -> ghost rows (planar field)
 int launch_relax(fsim_sim *s, int sweeps, double omega);  // 1..4 sweeps, one launch

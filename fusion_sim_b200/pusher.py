@@ -177,6 +177,37 @@ class CylindricalParticlePusher:
         check(lib().fsim_solve_fields(self._h, float(value["macro_weight"]), int(value["sweeps"]),
                                       float(value.get("omega", 1.0)), 0 if source == "avg" else 1))
 
+    # -- EXTENSION (no reference counterpart, SURVEY.md section 8f N4 / BASELINE configs[2]): Yee field update --------
+    EM_SHAPES = {"Er": (1, 0), "Ez": (0, 1), "Bt": (0, 0), "Et": (1, 1), "Br": (0, 1), "Bz": (1, 0)}  # (extra rows, extra columns)
+
+    def _em_shape(self, name):
+        if name not in self.EM_SHAPES:
+            raise Error(f".name <- unknown field {name!r} (Er Ez Bt Et Br Bz)", _lib.ERR_INVALID)
+        dj, di = self.EM_SHAPES[name]
+        return (self.nz + dj, self.nr + di)
+
+    def emInit(self):
+        """Zero electromagnetic fields on an axisymmetric Yee mesh; the B present now stays underneath as the static
+        field.  Specification: include/fusionsim.h (fsim_em_step)."""
+        check(lib().fsim_em_init(self._h))
+
+    def emSet(self, name: str, data):
+        shape = self._em_shape(name)
+        a = np.ascontiguousarray(data, np.float64)
+        if a.size != shape[0] * shape[1]:
+            raise Error(f".{name} <- expected {shape[0]} x {shape[1]} values", _lib.ERR_INVALID)
+        check(lib().fsim_em_set(self._h, name.encode(), ptr(a)))
+
+    def emGet(self, name: str) -> np.ndarray:
+        out = np.empty(self._em_shape(name), np.float64)
+        check(lib().fsim_em_get(self._h, name.encode(), ptr(out)))
+        return out.reshape(-1)
+
+    def emStep(self, macro_weight: float = 0.0, with_current: bool = True):
+        """One leap-frog step of dt: B from curl E, E from curl B and the deposited current (moments01 of the last
+        density(); needs keep_moments), cell-centred E and B for the push, precalc().  Pair with half_step()."""
+        check(lib().fsim_em_step(self._h, float(macro_weight), 1 if with_current else 0))
+
     def render(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
             out = np.empty((self.nz, self.nr, 4), np.uint8)

@@ -201,6 +201,48 @@ int fsim_solve_fields_stage(fsim_sim *sim, int32_t stage, double macro_weight, i
                             int32_t source);
 int fsim_field_rows(fsim_sim *sim, const char *name, int64_t first_row, int64_t nrows, void **ptr, int64_t *nbytes);
 
+/* ---- EXTENSION, NO REFERENCE COUNTERPART (BASELINE.json configs[2] "Boris + Yee
+ * FDTD"): electromagnetic field update.  The reference's E and B never change (value.E / value.B, empic.js:1159-1197);
+ * this advances them with Maxwell's equations on an axisymmetric Yee mesh laid over the cells of the field
+ * textures, with the current the deposit measures as the source.  PARITY UNPINNED by construction.
+ *   cell (i,j) = [i dr, (i+1) dr] x [j dz, (j+1) dz];  all arrays row-major [j][i]:
+ *     "Er" (i+1/2, j) [nz+1][nr]     "Ez" (i, j+1/2) [nz][nr+1]     "Bt" (i+1/2, j+1/2) [nz][nr]      TM set
+ *     "Et" (i, j)     [nz+1][nr+1]   "Br" (i, j+1/2) [nz][nr+1]     "Bz" (i+1/2, j)     [nz+1][nr]    TE set
+ *   perfectly conducting wall at r = radius and end plates at z = 0, height: the tangential E there (Ez at i = nr,
+ *   Et at i = nr and j = 0, nz, Er at j = 0, nz) is never updated; Et on the axis likewise.
+ * fsim_em_init: zero Yee fields; the B present at the call stays underneath as the static field B0 (changes made to
+ *   E or B through the other entry points afterwards are overwritten by the next fsim_em_step; call fsim_em_init
+ *   again after changing the static field).  Fails unless c dt sqrt(1/dr^2 + 1/dz^2) < 1.  One GPU, not periodic.
+ * fsim_em_set / fsim_em_get: one of the six arrays above, host doubles.
+ * fsim_em_step: ONE leap-frog step of spec.dt -- pair it with fsim_half_step() + fsim_density(), which advance the
+ *   particles by the same dt and leave the moments.  Every product formed as written, left to right, no fused
+ *   multiply-add; scalar and per-column coefficients in host fp64, rounded to the engine's real type:
+ *     kz = dt/dz, kr = dt/dr, cz = c^2 dt/dz, cr = c^2 dt/dr, cj = dt/eps0, ax = 4 c^2 dt/dr,
+ *     a1_i = dt (i+1) dr/((i+1/2) dr dr), a0_i = dt i dr/((i+1/2) dr dr),
+ *     b1_i = c^2 dt (i+1/2) dr/(i dr dr), b0_i = c^2 dt (i-1/2) dr/(i dr dr)   (i >= 1)
+ *   B from E:
+ *     Br += kz (Et[j+1][i] - Et[j][i])
+ *     Bt -= (kz (Er[j+1][i] - Er[j][i])) - (kr (Ez[j][i+1] - Ez[j][i]))
+ *     Bz -= (a1_i Et[j][i+1]) - (a0_i Et[j][i])
+ *   E from the new B and the current density J at the cell centres:
+ *     Er += (-(cz (Bt[j][i] - Bt[j-1][i]))) - cj (0.5 (Jr[j-1][i] + Jr[j][i]))                       1 <= j <= nz-1
+ *     Et += ((cz (Br[j][i] - Br[j-1][i])) - (cr (Bz[j][i] - Bz[j][i-1])))
+ *           - cj (0.25 (((Jt[j-1][i-1] + Jt[j-1][i]) + Jt[j][i-1]) + Jt[j][i]))                      1 <= i <= nr-1, 1 <= j <= nz-1
+ *     Ez += ((b1_i Bt[j][i]) - (b0_i Bt[j][i-1])) - cj (0.5 (Jz[j][i-1] + Jz[j][i]))                 1 <= i <= nr-1
+ *     Ez[j][0] += (ax Bt[j][0]) - cj Jz[j][0]                                                        (axis: 4 B/dr)
+ *   J_q[j][i] = g_q,i * moments01.q of cell (i,j) (the raw deposit of the last fsim_density(), needs
+ *   FSIM_FLAG_KEEP_MOMENTS; J = 0 when with_current == 0):  g_r,i = g_t,i = G_i radius, g_z,i = G_i height,
+ *     G_i = particle_charge macro_weight 1000 c / (2 pi u_i radius dr dz),  u_i = (i + 1/2)/nr
+ *   (the sprites deposit 0.001 v in the normalised units v/c (1/radius, 1/radius, 1/height); 2 pi r dr dz is the
+ *   volume of the cell's ring);
+ *   then the fields the push gathers, at the cell centres, and precalc():
+ *     E = (0.5 (Er[j][i] + Er[j+1][i]), 0.25 (((Et[j][i] + Et[j][i+1]) + Et[j+1][i]) + Et[j+1][i+1]), 0.5 (Ez[j][i] + Ez[j][i+1]))
+ *     B = B0 + (0.5 (Br[j][i] + Br[j][i+1]), Bt[j][i], 0.5 (Bz[j][i] + Bz[j+1][i]))                              */
+int fsim_em_init(fsim_sim *sim);
+int fsim_em_set(fsim_sim *sim, const char *name, const double *data);
+int fsim_em_get(fsim_sim *sim, const char *name, double *out);
+int fsim_em_step(fsim_sim *sim, double macro_weight, int32_t with_current);
+
 /* ---- checkpoint restore (extension; the reference can neither read nor restore its state) ---------
  * fsim_set_state is the exact inverse of fsim_get_position / _velocity / _rand: normalised units,
  * particle-id order, alive flag in position[..][3]; any pointer may be NULL.  fsim_set_field restores

@@ -82,6 +82,39 @@ static inline float orc_floor_f32(float x) { return floorf(x); }
 #undef REAL
 #undef SFX
 
+/* EXTENSION: axisymmetric Yee update driven by the deposited current (BASELINE configs[2]) */
+#define REAL double
+#define SFX f64
+#include "fsim_oracle_em_impl.h"
+#undef REAL
+#undef SFX
+#define REAL float
+#define SFX f32
+#include "fsim_oracle_em_impl.h"
+#undef REAL
+#undef SFX
+
+/* coefficients of the Yee update (header of fsim_oracle_em_impl.h): coef [nr+1][6] = a1 a0 b1 b0 gR gZ, scal [6] =
+ * kz kr cz cr cj ax; host doubles */
+void orce_coeffs(int64_t nr, int64_t nz, double radius, double height, double dt, double charge, double macro_weight,
+                 double *coef, double *scal)
+{
+    const double dr = radius / (double)nr, dz = height / (double)nz, c2 = FSIM_C_LIGHT * FSIM_C_LIGHT;
+    scal[0] = dt / dz; scal[1] = dt / dr; scal[2] = c2 * dt / dz; scal[3] = c2 * dt / dr; scal[4] = dt / FSIM_EPS0;
+    scal[5] = 4.0 * c2 * dt / dr;
+    for (int64_t i = 0; i <= nr; ++i) {
+        const double rh = ((double)i + 0.5) * dr;
+        coef[6 * i] = dt * ((double)i + 1.0) * dr / (rh * dr);
+        coef[6 * i + 1] = dt * (double)i * dr / (rh * dr);
+        coef[6 * i + 2] = i ? c2 * dt * rh / ((double)i * dr * dr) : 0.0;
+        coef[6 * i + 3] = i ? c2 * dt * (((double)i - 0.5) * dr) / ((double)i * dr * dr) : 0.0;
+        const double u = ((double)i + 0.5) / (double)nr;
+        const double G = charge * macro_weight * 1000.0 * FSIM_C_LIGHT / (2.0 * FSIM_PI * u * radius * dr * dz);
+        coef[6 * i + 4] = G * radius;
+        coef[6 * i + 5] = G * height;
+    }
+}
+
 /* per-column Jacobi coefficients [nr][4] = cE cW cZ cB (header of fsim_oracle_fields_impl.h) */
 void orc_relax_coeffs(int64_t nr, double dr, double dz, double *out)
 {

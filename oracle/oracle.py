@@ -33,7 +33,7 @@ def build(force: bool = False) -> str:
     import fcntl
     so = os.path.join(_HERE, "libfsim_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("fsim_oracle.c", "fsim_oracle_impl.h", "fsim_oracle_jacobi_impl.h",
-                                             "fsim_oracle_fields_impl.h", "fsim_oracle_spindle_impl.h", "Makefile")]
+                                             "fsim_oracle_fields_impl.h", "fsim_oracle_spindle_impl.h", "fsim_oracle_em_impl.h", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "fsim_constants.h"))
 
     def stale():
@@ -304,6 +304,36 @@ class OraclePusher:
                              C.c_int(self.nthreads))
         self._f("orc_efield")(C.c_int64(self.nr), C.c_int64(self.nz), _p(self.phi), C.c_double(1 / (2 * dr)),
                               C.c_double(1 / (2 * dz)), _p(self.E))
+        self.precalc()
+
+    # -- EXTENSION (BASELINE configs[2]): axisymmetric Yee update driven by the deposited current ----
+    EM_SHAPES = {"Er": (1, 0), "Ez": (0, 1), "Bt": (0, 0), "Et": (1, 1), "Br": (0, 1), "Bz": (1, 0)}  # (extra rows, extra columns)
+
+    def emInit(self):
+        """Zero Yee fields; the static field present now stays underneath (specification: fsim_oracle_em_impl.h)."""
+        self.em = {k: np.zeros((self.nz + dj) * (self.nr + di), self.dt) for k, (dj, di) in self.EM_SHAPES.items()}
+        self.B0 = self.B.copy()
+        sp = self.spec
+        dr, dz = sp["radius"] / self.nr, sp["height"] / self.nz
+        if C_LIGHT * sp["dt"] * np.sqrt(1 / dr ** 2 + 1 / dz ** 2) >= 1.0:
+            raise RuntimeError(".dt <- the Yee update needs c dt sqrt(1/dr^2 + 1/dz^2) < 1")
+
+    def emSet(self, name, data):
+        self.em[name][:] = np.asarray(data, np.float64).reshape(-1)
+
+    def emGet(self, name):
+        return self.em[name].astype(np.float64)
+
+    def emStep(self, macro_weight=0.0, with_current=True):
+        sp = self.spec
+        coef, scal = np.empty((self.nr + 1, 6)), np.empty(6)
+        lib().orce_coeffs(C.c_int64(self.nr), C.c_int64(self.nz), C.c_double(sp["radius"]), C.c_double(sp["height"]),
+                          C.c_double(sp["dt"]), C.c_double(sp["particle_charge"]), C.c_double(float(macro_weight)), _p(coef), _p(scal))
+        e = self.em
+        self._f("orce_step")(C.c_int64(self.nr), C.c_int64(self.nz), _p(e["Er"]), _p(e["Ez"]), _p(e["Bt"]), _p(e["Et"]), _p(e["Br"]),
+                             _p(e["Bz"]), _p(coef), _p(scal), _p(self.moments01) if with_current else None, C.c_int(self.nthreads))
+        self._f("orce_cells")(C.c_int64(self.nr), C.c_int64(self.nz), _p(e["Er"]), _p(e["Ez"]), _p(e["Bt"]), _p(e["Et"]), _p(e["Br"]),
+                              _p(e["Bz"]), _p(self.B0), _p(self.E), _p(self.B))
         self.precalc()
 
     @property
