@@ -61,6 +61,19 @@ exports.makeCylindricalParticlePusher = function (spec) {
     sim.solveFields(value.macro_weight, value.sweeps, typeof value.omega === 'number' ? value.omega : 1.0,
                     value.source === 'instant' ? 1 : 0);
   };
+  // EXTENSION (no reference counterpart): electromagnetic update on an axisymmetric Yee mesh, include/fusionsim.h.
+  // A frame of the loop is halfStep() + density() + emStep(macro_weight): particles and fields advance by the same dt.
+  out.halfStep = () => sim.halfStep();
+  out.emInit = () => sim.emInit();
+  out.emSet = (name, data) => sim.emSet(name, Float64Array.from(data));
+  out.emGet = function (name) {
+    const extra = { Er: [1, 0], Ez: [0, 1], Bt: [0, 0], Et: [1, 1], Br: [0, 1], Bz: [1, 0] }[name];
+    if (!extra) throw new Error('.name <- unknown field ' + name + ' (Er Ez Bt Et Br Bz)');
+    const a = new Float64Array((spec.nz + extra[0]) * (spec.nr + extra[1]));
+    sim.emGet(name, a);
+    return a;
+  };
+  out.emStep = (macro_weight, with_current) => sim.emStep(macro_weight || 0.0, with_current !== false);
   // checkpoint / restore (extension): everything a run needs to continue bit for bit
   out.checkpoint = function () {
     const n = spec.nparticles * spec.nparticles, nc = spec.nr * spec.nz;

@@ -34,6 +34,11 @@ class Sim : public Napi::ObjectWrap<Sim> {
             InstanceMethod("step", &Sim::Step),
             InstanceMethod("density", &Sim::Density),
             InstanceMethod("solveFields", &Sim::SolveFields),
+            InstanceMethod("halfStep", &Sim::HalfStep),
+            InstanceMethod("emInit", &Sim::EmInit),
+            InstanceMethod("emSet", &Sim::EmSet),
+            InstanceMethod("emGet", &Sim::EmGet),
+            InstanceMethod("emStep", &Sim::EmStep),
             InstanceMethod("setState", &Sim::SetState),
             InstanceMethod("setField", &Sim::SetField),
             InstanceMethod("render", &Sim::Render),
@@ -124,6 +129,33 @@ class Sim : public Napi::ObjectWrap<Sim> {
     {
         check(i.Env(), fsim_solve_fields(sim_, i[0].As<Napi::Number>().DoubleValue(), i[1].As<Napi::Number>().Int32Value(),
                                          i[2].As<Napi::Number>().DoubleValue(), i[3].As<Napi::Number>().Int32Value()));
+        return i.Env().Undefined();
+    }
+    // EXTENSION (no reference counterpart): electromagnetic update on a Yee mesh -- emInit(), emSet(name, Float64Array),
+    // emGet(name, Float64Array out), emStep(macro_weight, with_current); a frame is halfStep() + density() + emStep()
+    Napi::Value HalfStep(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_half_step(sim_));
+        return i.Env().Undefined();
+    }
+    Napi::Value EmInit(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_em_init(sim_));
+        return i.Env().Undefined();
+    }
+    Napi::Value EmSet(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_em_set(sim_, i[0].As<Napi::String>().Utf8Value().c_str(), i[1].As<Napi::Float64Array>().Data()));
+        return i.Env().Undefined();
+    }
+    Napi::Value EmGet(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_em_get(sim_, i[0].As<Napi::String>().Utf8Value().c_str(), i[1].As<Napi::Float64Array>().Data()));
+        return i.Env().Undefined();
+    }
+    Napi::Value EmStep(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_em_step(sim_, i[0].As<Napi::Number>().DoubleValue(), i[1].ToBoolean().Value() ? 1 : 0));
         return i.Env().Undefined();
     }
     Napi::Value Render(const Napi::CallbackInfo &i)
