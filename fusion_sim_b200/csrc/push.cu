@@ -468,8 +468,8 @@ static int push_impl(fsim_sim *s, const PushArgs<Real> &a, int nhalf, bool resor
         push_kernel<Real, V, BLOCK, MINB, 2, true, OPT><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     else if (nhalf == 2)
         push_kernel<Real, V, BLOCK, MINB, 2, false, OPT><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
-    else
-        push_kernel<Real, V, BLOCK, MINB, 1, false><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
+    else  // the single half-step keeps more values live per particle: it spills under a cap below 64 registers
+        push_kernel<Real, V, BLOCK, (MINB * BLOCK > 1024 ? 1024 / BLOCK : MINB), 1, false><<<grid_for(nvec, BLOCK), BLOCK, 0, s->stream>>>(a);
     FSIM_CUDA(cudaGetLastError());
     return FSIM_OK;
 }
@@ -512,11 +512,11 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
     if (with_hist && s->slab) FSIM_CUDA(cudaMemsetAsync(s->mscratch + MC_NLEAVERS, 0, sizeof(uint32_t), s->stream));
     int rc = dispatch(s, [&](auto tag) {
         using Real = decltype(tag);
-        constexpr int V = 16 / sizeof(Real);  // particles per 128 bits
         if (s->n == 0) return (int)FSIM_OK;
         const PushArgs<Real> a = make_args<Real>(s, with_hist, resort);
         Bracket b(s, resort ? "push2_resort" : (nhalf == 2 ? "push2" : "push"));
 #ifdef FSIM_TUNE
+        constexpr int V = 16 / sizeof(Real);  // particles per 128 bits
         switch (g_push_variant) {
         case 1: return push_impl<Real, V, 128, 4>(s, a, nhalf, resort);
         case 2: return push_impl<Real, V, 256, 3>(s, a, nhalf, resort);
@@ -536,12 +536,24 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
         case 22: return push_impl<Real, V / 2, 256, 4, 3>(s, a, nhalf, resort);
         case 23: return push_impl<Real, V / 2, 256, 3, 3>(s, a, nhalf, resort);
         case 24: return push_impl<Real, V, 256, 2, 3>(s, a, nhalf, resort);
+        // more resident warps at a tighter register cap (one particle per thread; fp32: also two)
+        case 30: return push_impl<Real, 1, 256, 5>(s, a, nhalf, resort);
+        case 31: return push_impl<Real, 1, 256, 6>(s, a, nhalf, resort);
+        case 32: return push_impl<Real, 1, 256, 8>(s, a, nhalf, resort);
+        case 33: return push_impl<Real, 1, 256, 4>(s, a, nhalf, resort);
+        case 34: return push_impl<Real, V / 2, 256, 5>(s, a, nhalf, resort);
+        case 35: return push_impl<Real, V / 2, 256, 6>(s, a, nhalf, resort);
+        case 36: return push_impl<Real, 1, 256, 6, 2>(s, a, nhalf, resort);
+        case 37: return push_impl<Real, 1, 512, 3>(s, a, nhalf, resort);
+        case 38: return push_impl<Real, 1, 128, 12>(s, a, nhalf, resort);
+        case 39: return push_impl<Real, 1, 256, 7>(s, a, nhalf, resort);
         default: break;
         }
 #endif
-        // measured fastest on B200 (profiles/r2_push_variants.md): fp64 one particle per thread (64-bit
-        // streams), fp32 two (64-bit streams); 256 threads x 4 blocks per SM = 64 registers per thread
-        return push_impl<Real, V / 2, 256, 4>(s, a, nhalf, resort);
+        // measured fastest on B200 (profiles/r2_push_variants.md): one particle per thread; fp64 256 threads x 4 blocks
+        // per SM (64 registers, 32 warps), fp32 x 6 blocks (40 registers, 48 warps, no spills): more particles in
+        // flight under the latency of the dependent gathers (fp64 spills below 62 registers and loses 30 %)
+        return push_impl<Real, 1, 256, (sizeof(Real) == 4 ? 6 : 4)>(s, a, nhalf, resort);
     });
     if (resort && rc == FSIM_OK && s->n) {
         s->cur ^= 1;
