@@ -26,6 +26,20 @@ int upload_costab(const double *c64, const float *c32)
     return FSIM_OK;
 }
 
+// the 8-real record leaves as whole 32-byte sectors: two 256-bit stores in fp64 (st.global.v4.f64, sm_100), two 128-bit
+// stores in fp32 -- eight scalar stores at a 64-byte stride wrote every sector of the warp's 2 KB four (fp32: eight)
+// times over and kept the kernel at 0.5 of the copy bandwidth on L1TEX wavefronts
+__device__ __forceinline__ void st_rec(double *p, const double (&o)[RECSTRIDE])
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(o[0]), "d"(o[1]), "d"(o[2]), "d"(o[3]) : "memory");
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(o[4]), "d"(o[5]), "d"(o[6]), "d"(o[7]) : "memory");
+}
+__device__ __forceinline__ void st_rec(float *p, const float (&o)[RECSTRIDE])
+{
+    reinterpret_cast<float4 *>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(256)
 precalc_kernel(const Real *__restrict__ E, const Real *__restrict__ B, Real *__restrict__ rec,
@@ -39,7 +53,7 @@ precalc_kernel(const Real *__restrict__ E, const Real *__restrict__ B, Real *__r
     const Real hB2 = h * h * Bmag * Bmag;
     const Real f = (Real)2.0 / ((Real)1.0 + hB2);
     const Real one_m = (Real)1.0 - hB2 * f;
-    Real *o = rec + RECSTRIDE * c;
+    Real o[RECSTRIDE];
     // what programPre1/2/3 need of B (empic.js:520-522); the nine entries are rebuilt by boris_rows()
     o[REC_BX] = Bx; o[REC_BY] = By; o[REC_BZ] = Bz;
     o[REC_F] = f;
@@ -65,6 +79,7 @@ precalc_kernel(const Real *__restrict__ E, const Real *__restrict__ B, Real *__r
     o[REC_AX] = ax * kr;
     o[REC_AY] = ay * kr;
     o[REC_AZ] = az * kz;
+    st_rec(rec + RECSTRIDE * c, o);
 }
 
 // accessor support: expand the records to the reference's four textures R1 R2 R3 A (12 reals)
