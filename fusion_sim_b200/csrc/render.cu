@@ -56,28 +56,31 @@ __global__ void __launch_bounds__(256)
 render_kernel(const uchar4 *__restrict__ base, const Real *__restrict__ avg_alpha, int pitch,
               uint8_t *__restrict__ rgba, int nr, int nz, int row0, int own0, int own_rows)
 {
-    // v / 255 for the 256 values a stored canvas byte can take: one IEEE division per thread instead of four
+    // v / 255 for the 256 values a stored canvas byte can take: one IEEE division per 256-cell group of a block's
+    // grid-stride walk instead of four per cell (the table is built once per block)
     __shared__ Real inv255[256];
     inv255[threadIdx.x] = (Real)threadIdx.x / (Real)255.0;  // blockDim.x == 256
     __syncthreads();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)nr * own_rows) return;
-    const int i = (int)(t % nr), j = own0 + (int)(t / nr);
-    const uchar4 b8 = base[t];
-    const uint8_t *pb = reinterpret_cast<const uint8_t *>(&b8);
-    const Real a = avg_alpha[(size_t)(j - row0) * pitch + i];  // alpha plane of the running average
-    const Real sc = (Real)FSIM_RENDER_DENSITY * a;
-    const Real src[4] = {sc, sc, sc, (Real)FSIM_RENDER_DENSITY * (Real)1.0};
-    const Real sa = clamp01(src[3]);
-    uchar4 o;
-    uint8_t *po = reinterpret_cast<uint8_t *>(&o);
+    // the alpha channel of both draws is constant: src = (d, d, d, 1) * RENDER_DENSITY
+    const Real sa = clamp01((Real)FSIM_RENDER_DENSITY * (Real)1.0);
+    const uint32_t total = (uint32_t)nr * (uint32_t)own_rows;  // cells fit 31 bits (the sort key does)
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int i = (int)(t % (uint32_t)nr), j = own0 + (int)(t / (uint32_t)nr);
+        const uchar4 b8 = base[t];
+        const uint8_t *pb = reinterpret_cast<const uint8_t *>(&b8);
+        const Real a = avg_alpha[(size_t)(j - row0) * pitch + i];  // alpha plane of the running average
+        const Real sc = (Real)FSIM_RENDER_DENSITY * a;
+        const Real src[4] = {sc, sc, sc, (Real)FSIM_RENDER_DENSITY * (Real)1.0};
+        uchar4 o;
+        uint8_t *po = reinterpret_cast<uint8_t *>(&o);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const Real dst = inv255[pb[q]];
-        const Real out = clamp01(src[q]) * sa + dst;
-        po[q] = (uint8_t)quant8(clamp01(out));
+        for (int q = 0; q < 4; ++q) {
+            const Real dst = inv255[pb[q]];
+            const Real out = clamp01(src[q]) * sa + dst;
+            po[q] = (uint8_t)quant8(clamp01(out));
+        }
+        reinterpret_cast<uchar4 *>(rgba)[(size_t)i + (size_t)(nz - 1 - j) * nr] = o;
     }
-    reinterpret_cast<uchar4 *>(rgba)[(size_t)i + (size_t)(nz - 1 - j) * nr] = o;
 }
 
 int launch_render(fsim_sim *s, uint8_t *dev_rgba, cudaStream_t st)
@@ -94,7 +97,8 @@ int launch_render(fsim_sim *s, uint8_t *dev_rgba, cudaStream_t st)
             s->bmag_valid = true;
         }
         Bracket b(s, "render", st);
-        render_kernel<Real><<<grid_for(nown, 256), 256, 0, st>>>(
+        const int64_t blocks = std::min<int64_t>((nown + 255) / 256, (int64_t)s->nsm * 8);
+        render_kernel<Real><<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, st>>>(
             (const uchar4 *)s->bmag, (const Real *)s->avg + 3 * s->plane, s->pitch, dev_rgba, s->nr, s->nz, s->row0,
             s->own0, s->own_rows);
         FSIM_CUDA(cudaGetLastError());
