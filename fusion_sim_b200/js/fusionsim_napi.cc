@@ -1,13 +1,16 @@
 // fusionsim_napi.cc -- thin N-API addon over include/fusionsim.h (SOURCE ONLY: this image has no
-// Node.js and no node_api.h, so it is not compiled or tested here).
+// Node.js and no node_api.h, so it is not built or run here; tests/test_abi.py type-checks it against a
+// declarations-only stand-in for napi.h, tests/stubs/napi.h).
 //
-// Build where Node exists:
-//   g++ -std=c++17 -shared -fPIC -I$(node -p "require('node-addon-api').include_dir") \
-//       -I../../include fusionsim_napi.cc -L../csrc -lfusionsim -Wl,-rpath,'$ORIGIN/../csrc' \
+// Build where Node exists (one command):
+//   g++ -std=c++17 -shared -fPIC -I$(node -p "require('node-addon-api').include_dir")
+//       -I../../include fusionsim_napi.cc -L../csrc -lfusionsim -Wl,-rpath,'$ORIGIN/../csrc'
 //       -o fusionsim.node
 // It owns nothing but the fsim_sim handle; typed arrays are passed straight through as host
 // pointers (the library copies during the call, as gl.texImage2D does: utilities.js:585-594).
 #include <napi.h>
+
+#include <string>
 
 #include "fusionsim.h"
 

@@ -132,3 +132,24 @@ def test_c_host_matches_the_python_mirror(built, tmp_path):
     raw = open(ppm, "rb").read()
     assert raw.startswith(b"P6\n400 800\n255\n")
     assert np.array_equal(np.frombuffer(raw[len(b"P6\n400 800\n255\n"):], np.uint8).reshape(800, 400, 3), canvas[..., :3])
+
+
+def test_node_addon_source_type_checks_and_matches_the_js_shim():
+    """No Node.js in this image: the addon cannot be built or run, but its source is type-checked against a
+    declarations-only stand-in for napi.h (tests/stubs/napi.h, written from the documented node-addon-api surface),
+    every C entry point it calls is declared in include/fusionsim.h, and every member the JS shim calls on the native
+    object is one the addon registers."""
+    js_dir = os.path.join(ROOT, "fusion_sim_b200", "js")
+    cc = os.path.join(js_dir, "fusionsim_napi.cc")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "stubs"),
+                        "-I" + os.path.join(ROOT, "include"), cc], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(cc).read()
+    registered = set(re.findall(r'InstanceMethod\("(\w+)"', src))
+    shim = open(os.path.join(js_dir, "empic_b200.js")).read()
+    called = set(re.findall(r"\bsim\.(\w+)\(", shim))
+    assert called and called <= registered, sorted(called - registered)
+    header = open(os.path.join(ROOT, "include", "fusionsim.h")).read()
+    declared = set(re.findall(r"\b(fsim_\w+)\s*\(", header))
+    used = set(re.findall(r"\b(fsim_\w+)\s*\(", src))
+    assert used and used <= declared, sorted(used - declared)
