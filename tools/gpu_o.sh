@@ -1,5 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-export FSIM_LIB_PATH=tools/scratch/ab/tune/fusion_sim_b200/csrc/libfusionsim.so
-timeout 400 python tools/tune.py c5 f32 4,31,36,37,38,39,35,34,0,4 > gpurun_out/r2_tune_occ_f32_b.txt 2>&1; echo "rc=$?"; cat gpurun_out/r2_tune_occ_f32_b.txt | tail -12
-timeout 400 python tools/tune.py c3 f32 4,31,32,0 > gpurun_out/r2_tune_occ_f32_c3.txt 2>&1; echo "rc=$?"; cat gpurun_out/r2_tune_occ_f32_c3.txt | tail -5
+for rep in 1 2; do
+timeout 300 python tools/tune_sort_interval.py c5 f64 8 >> gpurun_out/r2_exp_cellsum_base.jsonl 2>&1
+FSIM_LIB_PATH=tools/scratch/ab/exp1/fusion_sim_b200/csrc/libfusionsim.so timeout 300 python tools/tune_sort_interval.py c5 f64 8 >> gpurun_out/r2_exp_cellsum_early.jsonl 2>&1
+done
+python - <<'PY'
+import json
+for f in ("base","early"):
+    for l in open(f"gpurun_out/r2_exp_cellsum_{f}.jsonl"):
+        try:
+            d=json.loads(l); print(f, d["frame_ms"], d["cellsum"]["per_launch"], d["push2"]["per_launch"])
+        except Exception as e: print(f, l[:100])
+PY
