@@ -107,6 +107,8 @@ _SIGS = {
     "fsim_set_field": (C.c_int, [_P, C.c_char_p, _P]),
     "fsim_solve_fields": (C.c_int, [_P, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "fsim_solve_fields_stage": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_int32]),
+    "fsim_run_frames": (C.c_int, [_P, C.c_int64]),
+    "fsim_frame_graph_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fsim_em_init": (C.c_int, [_P]),
     "fsim_em_set": (C.c_int, [_P, C.c_char_p, _P]),
     "fsim_em_get": (C.c_int, [_P, C.c_char_p, _P]),

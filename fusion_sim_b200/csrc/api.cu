@@ -421,18 +421,32 @@ int post_join(fsim_sim *s)
     s->post_pending = false;
     return FSIM_OK;
 }
-// every entry point except the frame's own (step, density, migrate, canvas draws) first joins the post stream
-static int check(fsim_sim *s)
+// every entry point except the frame's own (step, density, migrate, canvas draws) first joins the post stream.
+// check / check_n are the prologue of entry points that may CHANGE what a frame launches or works on (they bump
+// config_epoch: a captured frame graph, fsim_run_frames, is dropped); check_ro / check_n_ro of those that only read.
+static int check_ro(fsim_sim *s)
 {
     FSIM_TRY(check_handle(s));
     return post_join(s);
 }
+static int check(fsim_sim *s)
+{
+    FSIM_TRY(check_ro(s));
+    s->config_epoch++;
+    return FSIM_OK;
+}
 // entry points that address particles by count: the asynchronous slab exchange keeps the exact count on
 // the device (settle_count synchronises and refreshes fsim_sim::n)
-static int check_n(fsim_sim *s)
+static int check_n_ro(fsim_sim *s)
 {
     FSIM_TRY(check_handle(s));
     return settle_count(s);
+}
+static int check_n(fsim_sim *s)
+{
+    FSIM_TRY(check_n_ro(s));
+    s->config_epoch++;
+    return FSIM_OK;
 }
 
 static int finish(fsim_sim *s, int rc)
@@ -615,6 +629,8 @@ static void free_all(fsim_sim *s)
     for (void *p : ptrs) cudaFree(p);
     cudaFree(s->phi[0]); cudaFree(s->phi[1]); cudaFree(s->rho_src); cudaFree(s->relax_coef); cudaFree(s->background);
     em_free(s);
+    if (s->frame_graph) cudaGraphExecDestroy(s->frame_graph);
+    s->frame_graph = nullptr;
     cudaFree(s->bmag); cudaFree(s->plan.send); cudaFree(s->plan.recv); cudaFree(s->plan.holes); cudaFree(s->plan.targets); cudaFree(s->plan.sources);
     if (s->n_pinned) cudaFreeHost(s->n_pinned);
     for (auto &e : s->n_event)
@@ -1065,7 +1081,7 @@ int fsim_add_spindle_cusp_plasma_field(fsim_sim *s, double r, double B_c, double
 // the solved system A [256][256] and rhs [256]; checks of the solver and its final `diff` (matrix_webgl.js:687)
 int fsim_get_spindle(fsim_sim *s, double *x, double *currents, double *A, double *rhs, int32_t *iterations, double *diff)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (s->spindle_x.empty()) return fail(FSIM_ERR_STATE, "no spindle-cusp boundary solve on this handle yet");
     if (x) memcpy(x, s->spindle_x.data(), sizeof(double) * s->spindle_x.size());
     if (currents) memcpy(currents, s->spindle_currents.data(), sizeof(double) * s->spindle_currents.size());
@@ -1156,7 +1172,7 @@ int fsim_em_set(fsim_sim *s, const char *name, const double *data)
 }
 int fsim_em_get(fsim_sim *s, const char *name, double *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     FSIM_TRY(em_ready(s));
     if (!name || !out) return fail(FSIM_ERR_INVALID, "null argument");
     const int f = em_field_index(name);
@@ -1246,6 +1262,7 @@ static int physical_sort(fsim_sim *s)
 int fsim_half_step(fsim_sim *s)
 {
     FSIM_TRY(check_handle(s));
+    s->config_epoch++;  // leaves the step()/density() cycle a captured frame graph replays
     s->fresh = false;
     return finish(s, launch_push(s, false, 1));
 }
@@ -1358,7 +1375,7 @@ int fsim_density(fsim_sim *s)
 
 int fsim_render_rgba8(fsim_sim *s, uint8_t *rgba)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (!rgba) return fail(FSIM_ERR_INVALID, "null array");
     const size_t bytes = 4 * (size_t)s->ncell_global;
     FSIM_TRY(finish(s, ensure_stage(s, bytes)));
@@ -1422,9 +1439,149 @@ int fsim_draw_canvas(fsim_sim *s)
     return canvas_draw(s, nullptr, false);
 }
 
+// ---- N frames of the page loop, launch-bound scenes through a CUDA graph ------------------------------
+// The reference's page runs step(); density() once per animation frame (fusionsim.js:170-178).  On the
+// reference's own demo scene (160 000 particles) a frame is ~14 launches of 3-30 us each: the GPU idles between
+// them.  fsim_run_frames(n) = n x (step, density, the two canvas draws), bit-identical to calling them one by
+// one; after one cycle of frames launched normally it CAPTURES the next cycle -- 2 x sort_interval frames: the
+// re-sort fused into every sort_interval-th sweep flips the two copies of the particle storage, so the kernel
+// arguments repeat with that period -- into a CUDA graph and replays it while whole cycles remain.  The host-side
+// frame state (which copy is current, frames since the re-sort, canvas image, ...) returns to its starting value
+// after a cycle, which is checked at capture; any entry point that can change what a frame launches bumps
+// config_epoch and the graph is dropped.
+static void frame_phase(const fsim_sim *s, int (&ph)[12])
+{
+    const int v[12] = {s->cur, s->steps_since_sort, s->canvas_slot, s->resort_due, s->ever_sorted, s->keys_valid, s->binned,
+                       s->counts_dirty, s->bmag_valid, s->conv_interior_done, s->tm_sums_rows, (int)s->fresh};
+    for (int k = 0; k < 12; ++k) ph[k] = v[k];
+}
+static void frame_phase_restore(fsim_sim *s, const int (&ph)[12])
+{
+    s->cur = ph[0]; s->steps_since_sort = ph[1]; s->canvas_slot = ph[2]; s->resort_due = ph[3]; s->ever_sorted = ph[4];
+    s->keys_valid = ph[5]; s->binned = ph[6]; s->counts_dirty = ph[7]; s->bmag_valid = ph[8]; s->conv_interior_done = ph[9];
+    s->tm_sums_rows = ph[10]; s->fresh = ph[11];
+}
+static bool frame_phase_is(const fsim_sim *s, const int (&want)[12])
+{
+    int ph[12];
+    frame_phase(s, ph);
+    for (int k = 0; k < 12; ++k)
+        if (ph[k] != want[k]) return false;
+    return true;
+}
+static void drop_frame_graph(fsim_sim *s)
+{
+    if (s->frame_graph) cudaGraphExecDestroy(s->frame_graph);
+    s->frame_graph = nullptr;
+}
+static int one_frame(fsim_sim *s)
+{
+    FSIM_TRY(fsim_step(s));
+    FSIM_TRY(fsim_density(s));
+    return fsim_draw_canvas(s);
+}
+// capture one cycle; on any failure the host-side state is put back and frames go on one by one
+static int capture_frame_graph(fsim_sim *s, int period)
+{
+    if (s->copy_stream && (s->copy_pending[0] || s->copy_pending[1])) {  // no read-back may be in flight on a canvas image
+        FSIM_CUDA(cudaStreamSynchronize(s->copy_stream));
+        s->copy_pending[0] = s->copy_pending[1] = false;
+    }
+    int ph0[12];
+    frame_phase(s, ph0);
+    const int64_t launches0 = s->launches;
+    std::map<std::string, int64_t> timer0;
+    for (auto &kv : s->timers) timer0[kv.first] = kv.second.launches;
+    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        s->graph_failed = true;
+        return FSIM_OK;
+    }
+    int rc = FSIM_OK;
+    for (int k = 0; k < period && rc == FSIM_OK; ++k) rc = one_frame(s);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    const bool cyclic = frame_phase_is(s, ph0);
+    const int64_t per_cycle = s->launches - launches0;
+    // nothing of the above ran: the host state goes back to where the device is
+    frame_phase_restore(s, ph0);
+    s->launches = launches0;
+    for (auto &kv : s->timers) kv.second.launches = timer0.count(kv.first) ? timer0[kv.first] : 0;
+    if (rc != FSIM_OK || e != cudaSuccess || !g || !cyclic) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        s->sticky_error = false;  // a launch refused under capture is not a device fault
+        s->graph_failed = true;
+        return FSIM_OK;
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess || !ex) {
+        cudaGetLastError();
+        s->graph_failed = true;
+        return FSIM_OK;
+    }
+    s->frame_graph = ex;
+    s->graph_epoch = s->config_epoch;
+    s->graph_frames = period;
+    s->graph_launches = per_cycle;
+    for (int k = 0; k < 12; ++k) s->graph_phase[k] = ph0[k];
+    return FSIM_OK;
+}
+
+int fsim_run_frames(fsim_sim *s, int64_t nframes)
+{
+    FSIM_TRY(check_handle(s));
+    if (nframes < 0) return fail(FSIM_ERR_INVALID, ".nframes <- must not be negative");
+    if (s->slab) return fail(FSIM_ERR_UNSUPPORTED, "run_frames on a slab: the frame of a slab has exchanges between its parts "
+                                                   "(fusion_sim_b200/dist.py drives them)");
+    const int period = 2 * sort_interval(s);
+    // a graph is worth it, and safe, on a plain handle: one stream, no per-launch timing events, no periodic self-exchange
+    const bool allow = !s->ring && !s->timing && !s->ext_stream && !(s->spec.flags & FSIM_FLAG_POST_STREAM);
+    if (s->frame_graph && (s->graph_epoch != s->config_epoch || !allow)) {
+        drop_frame_graph(s);
+        s->frames_run = 0;  // whatever changed may bring its own lazy initialisation: one cycle by hand first
+    }
+    int off_cycle = 0;
+    while (nframes > 0) {
+        if (allow && s->frame_graph && nframes >= s->graph_frames && frame_phase_is(s, s->graph_phase)) {
+            FSIM_CUDA(cudaGraphLaunch(s->frame_graph, s->stream));
+            s->launches += s->graph_launches;
+            s->graph_replays++;
+            nframes -= s->graph_frames;
+            off_cycle = 0;
+            continue;
+        }
+        if (allow && !s->frame_graph && !s->graph_failed && s->frames_run >= period && nframes >= 2 * period && s->ever_sorted &&
+            s->steps_since_sort <= sort_interval(s)) {
+            FSIM_TRY(capture_frame_graph(s, period));
+            if (s->frame_graph) continue;
+        }
+        FSIM_TRY(one_frame(s));
+        s->frames_run++;
+        nframes--;
+        // step() or density() called by hand between two run_frames shifts the cycle: the captured phase never comes back
+        if (s->frame_graph && ++off_cycle > 2 * s->graph_frames) {
+            drop_frame_graph(s);
+            off_cycle = 0;
+        }
+    }
+    return FSIM_OK;
+}
+// statistics of fsim_run_frames: frames per captured cycle (0: no graph), kernel launches per cycle, replays so far
+int fsim_frame_graph_info(fsim_sim *s, int32_t *frames_per_cycle, int64_t *launches_per_cycle, int64_t *replays)
+{
+    FSIM_TRY(check_handle(s));
+    if (frames_per_cycle) *frames_per_cycle = s->frame_graph ? s->graph_frames : 0;
+    if (launches_per_cycle) *launches_per_cycle = s->frame_graph ? s->graph_launches : 0;
+    if (replays) *replays = s->graph_replays;
+    return FSIM_OK;
+}
+
 int fsim_sync(fsim_sim *s)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     FSIM_CUDA(cudaStreamSynchronize(s->stream));
     if (s->copy_stream) {
         FSIM_CUDA(cudaStreamSynchronize(s->copy_stream));
@@ -1495,22 +1652,22 @@ static int part_out(fsim_sim *s, double *out, int width, int a0, bool with_alive
 
 int fsim_get_position(fsim_sim *s, double *out)
 {
-    FSIM_TRY(check_n(s));
+    FSIM_TRY(check_n_ro(s));
     return finish(s, part_out(s, out, 4, AX, true));
 }
 int fsim_get_velocity(fsim_sim *s, double *out)
 {
-    FSIM_TRY(check_n(s));
+    FSIM_TRY(check_n_ro(s));
     return finish(s, part_out(s, out, 3, AVX, false));
 }
 int fsim_get_rand(fsim_sim *s, double *out)
 {
-    FSIM_TRY(check_n(s));
+    FSIM_TRY(check_n_ro(s));
     return finish(s, part_out(s, out, 4, AQ0, false));
 }
 int fsim_get_ids(fsim_sim *s, uint64_t *out)
 {
-    FSIM_TRY(check_n(s));
+    FSIM_TRY(check_n_ro(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     std::vector<uint32_t> tmp((size_t)s->n);
     FSIM_CUDA(cudaMemcpyAsync(tmp.data(), s->pid[s->cur], sizeof(uint32_t) * s->n, cudaMemcpyDeviceToHost, s->stream));
@@ -1520,7 +1677,7 @@ int fsim_get_ids(fsim_sim *s, uint64_t *out)
 }
 int fsim_get_cells(fsim_sim *s, int64_t *out)
 {
-    FSIM_TRY(check_n(s));
+    FSIM_TRY(check_n_ro(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     if (s->n == 0) return FSIM_OK;
     FSIM_TRY(finish(s, ensure_stage(s, sizeof(int64_t) * s->n)));
@@ -1540,7 +1697,7 @@ int fsim_get_cells(fsim_sim *s, int64_t *out)
 
 int fsim_get_field(fsim_sim *s, const char *name, double *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (!name) return fail(FSIM_ERR_INVALID, "null field name");
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     const std::string n(name);
@@ -1575,7 +1732,7 @@ int fsim_get_field(fsim_sim *s, const char *name, double *out)
 }
 int fsim_get_cell_count(fsim_sim *s, uint32_t *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     FSIM_CUDA(cudaMemcpyAsync(out, s->cellcount, sizeof(uint32_t) * s->ncell_local, cudaMemcpyDeviceToHost, s->stream));
     FSIM_CUDA(cudaStreamSynchronize(s->stream));
@@ -1583,7 +1740,7 @@ int fsim_get_cell_count(fsim_sim *s, uint32_t *out)
 }
 int fsim_get_sink_mask(fsim_sim *s, uint8_t *out)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     FSIM_TRY(finish(s, ensure_stage(s, (size_t)s->ncell_global)));
     sink_out_kernel<<<grid_for(s->ncell_global, 256), 256, 0, s->stream>>>(s->sink, (uint8_t *)s->stage, s->ncell_global);
@@ -1599,7 +1756,7 @@ int fsim_get_sink_mask(fsim_sim *s, uint8_t *out)
 // must equal those of ids 0..N-1: no particle lost or duplicated by the migration.
 int fsim_check_digest(fsim_sim *s, uint64_t *out, double *sum_alpha)
 {
-    FSIM_TRY(check_n(s));
+    FSIM_TRY(check_n_ro(s));
     if (!out) return fail(FSIM_ERR_INVALID, "null array");
     constexpr int NB = 256;
     FSIM_TRY(finish(s, ensure_stage(s, 4 * sizeof(unsigned long long) + NB * sizeof(double))));
@@ -1649,7 +1806,7 @@ int fsim_timing_reset(fsim_sim *s)
 }
 int fsim_timing_get(fsim_sim *s, const char *name, double *ms, int64_t *launches)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (!name) return fail(FSIM_ERR_INVALID, "null kernel name");
     FSIM_TRY(collect_timers(s));
     auto it = s->timers.find(name);
@@ -1660,7 +1817,7 @@ int fsim_timing_get(fsim_sim *s, const char *name, double *ms, int64_t *launches
 
 int fsim_mark(fsim_sim *s, int slot)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (slot < 0 || slot >= 16) return fail(FSIM_ERR_INVALID, "mark slot out of range");
     if (!s->marks[slot]) FSIM_CUDA(cudaEventCreate(&s->marks[slot]));
     FSIM_CUDA(cudaEventRecord(s->marks[slot], s->stream));
@@ -1668,7 +1825,7 @@ int fsim_mark(fsim_sim *s, int slot)
 }
 int fsim_elapsed_ms(fsim_sim *s, int a, int b, double *ms)
 {
-    FSIM_TRY(check(s));
+    FSIM_TRY(check_ro(s));
     if (a < 0 || a >= 16 || b < 0 || b >= 16 || !s->marks[a] || !s->marks[b] || !ms)
         return fail(FSIM_ERR_INVALID, "elapsed: unrecorded mark");
     FSIM_CUDA(cudaEventSynchronize(s->marks[b]));

@@ -201,6 +201,17 @@ struct fsim_sim {
     double em_weight = 0.0;      // macro weight the coefficients were formed with (NaN: not uploaded)
     bool em_on = false;
 
+    // launch-bound scenes: a captured CUDA graph of one cycle of frames (fsim_run_frames, api.cu)
+    uint64_t config_epoch = 0;        // bumped by every entry point that can change what a frame launches or works on
+    cudaGraphExec_t frame_graph = nullptr;
+    uint64_t graph_epoch = 0;         // config_epoch the graph was captured under
+    int graph_frames = 0;             // frames per replay (2 x sort interval: the storage copies alternate)
+    int64_t graph_launches = 0;       // kernel launches per replay
+    int graph_phase[12] = {};         // host-side frame state at the start of the captured cycle
+    bool graph_failed = false;        // capture was tried and did not work out: frames are launched one by one
+    int64_t frames_run = 0;           // frames fsim_run_frames launched one by one (lazy initialisation is done after a cycle)
+    int64_t graph_replays = 0;
+
     // staging
     void *stage = nullptr;
     size_t stage_bytes = 0;

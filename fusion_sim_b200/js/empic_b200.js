@@ -52,6 +52,9 @@ exports.makeCylindricalParticlePusher = function (spec) {
   out.precalc = () => sim.precalc();
   out.step = () => sim.step();
   out.density = () => sim.density();
+  // n iterations of the page loop of fusionsim.js:170-178 (step(); density()) in one call: same results; a scene
+  // whose frame is bound by launch latency (the demo scene) replays a captured CUDA graph of 16 frames
+  out.runFrames = (n) => sim.runFrames(n);
   // EXTENSION (no reference counterpart): self-consistent electrostatic field solve, include/fusionsim.h
   out.solveFields = function (value) {
     for (const p of ['macro_weight', 'sweeps']) {

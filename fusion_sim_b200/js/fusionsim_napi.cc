@@ -37,6 +37,7 @@ class Sim : public Napi::ObjectWrap<Sim> {
             InstanceMethod("step", &Sim::Step),
             InstanceMethod("density", &Sim::Density),
             InstanceMethod("solveFields", &Sim::SolveFields),
+            InstanceMethod("runFrames", &Sim::RunFrames),
             InstanceMethod("halfStep", &Sim::HalfStep),
             InstanceMethod("emInit", &Sim::EmInit),
             InstanceMethod("emSet", &Sim::EmSet),
@@ -132,6 +133,13 @@ class Sim : public Napi::ObjectWrap<Sim> {
     {
         check(i.Env(), fsim_solve_fields(sim_, i[0].As<Napi::Number>().DoubleValue(), i[1].As<Napi::Number>().Int32Value(),
                                          i[2].As<Napi::Number>().DoubleValue(), i[3].As<Napi::Number>().Int32Value()));
+        return i.Env().Undefined();
+    }
+    // runFrames(n): n iterations of the page loop (step, density with its canvas draws); launch-bound scenes replay a
+    // captured CUDA graph (include/fusionsim.h, fsim_run_frames)
+    Napi::Value RunFrames(const Napi::CallbackInfo &i)
+    {
+        check(i.Env(), fsim_run_frames(sim_, i[0].As<Napi::Number>().Int64Value()));
         return i.Env().Undefined();
     }
     // EXTENSION (no reference counterpart): electromagnetic update on a Yee mesh -- emInit(), emSet(name, Float64Array),

@@ -165,6 +165,17 @@ class CylindricalParticlePusher:
     def density(self):
         check(lib().fsim_density(self._h))
 
+    def run_frames(self, nframes: int):
+        """`nframes` iterations of the page loop (fusionsim.js:170-178): step(), density() with its two canvas draws --
+        bit-identical to calling them one by one; launch-bound scenes replay a captured CUDA graph of 2 x sort_interval
+        frames (include/fusionsim.h, fsim_run_frames)."""
+        check(lib().fsim_run_frames(self._h, int(nframes)))
+
+    def frame_graph_info(self) -> dict:
+        f, l, r = C.c_int32(), C.c_int64(), C.c_int64()
+        check(lib().fsim_frame_graph_info(self._h, C.byref(f), C.byref(l), C.byref(r)))
+        return {"frames_per_cycle": f.value, "launches_per_cycle": l.value, "replays": r.value}
+
     def solveFields(self, value: dict):
         """EXTENSION (no reference counterpart): close the PIC loop.
         value = {macro_weight, sweeps, omega=1, source="avg"|"instant"}: charge density from the

@@ -169,6 +169,14 @@ int fsim_render_rows_async(fsim_sim *sim, uint8_t *rows); /* same, but `rows` ho
                                                             * [slab_rows][nr][4] (a slab rank's share)      */
 int fsim_draw_canvas(fsim_sim *sim); /* the two canvas draws of out.density (:1497-1504) into the device-
                                       * resident canvas, no read-back (the reference's canvas stays on the GPU) */
+/* extension: `nframes` iterations of the page loop (fusionsim.js:170-178) = nframes x (fsim_step, fsim_density,
+ * fsim_draw_canvas), bit-identical to calling them one by one.  Scenes whose frame is bound by launch latency (the
+ * reference's demo scene: ~14 launches of 3-30 us) gain from it: after one cycle of 2 x sort_interval frames launched
+ * one by one, the next cycle is captured into a CUDA graph and replayed while whole cycles remain; any entry point
+ * that can change what a frame launches drops the graph.  One GPU (a slab's frame has exchanges between its parts).
+ * fsim_frame_graph_info: frames and kernel launches per captured cycle (0 = no graph in use), replays so far.      */
+int fsim_run_frames(fsim_sim *sim, int64_t nframes);
+int fsim_frame_graph_info(fsim_sim *sim, int32_t *frames_per_cycle, int64_t *launches_per_cycle, int64_t *replays);
 int fsim_sort(fsim_sim *sim);      /* extension: re-sort particle storage by cell now          */
 int fsim_sync(fsim_sim *sim);      /* wait for the handle's stream                             */
 

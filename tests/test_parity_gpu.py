@@ -386,3 +386,74 @@ def test_check_digest_and_fused_resort_and_post_stream_flags():
     cnt = g0.getField("cell_count")
     assert d["deposited"] == int(cnt.sum())
     np.testing.assert_allclose(d["sum_alpha"], g0.getField("cell_sums")[:, 3].sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_run_frames_graph_replay_changes_no_bit(precision):
+    """fsim_run_frames(n) = n x (step, density, canvas draws); after one cycle launched one by one it captures a CUDA
+    graph of 2 x sort_interval frames and replays it.  Replayed frames, the frames around the capture, a tail shorter
+    than a cycle, frames after a setter dropped the graph, and frames after a hand-made step() shifted the cycle all
+    equal the same number of frames launched one by one -- particles, running average, counts, canvas."""
+    from fusion_sim_b200 import makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene
+    sc = small_scene(n=20000, speed=0.05, blob=(0.7, 0.9))
+    spec = dict(sc["spec"], precision=precision, sort_interval=3)  # cycle = 6 frames
+    a, b = makeCylindricalParticlePusher(spec), makeCylindricalParticlePusher(spec)
+    apply_scene(a, sc); apply_scene(b, sc)
+
+    def by_hand(sim, n):
+        for _ in range(n):
+            sim.step(); sim.density(); sim.draw_canvas()
+
+    def same(what):
+        assert_same(a.getPosition(), b.getPosition(), what + " position")
+        assert_same(a.getVelocity(), b.getVelocity(), what + " velocity")
+        assert_same(a.getRand(), b.getRand(), what + " rand")
+        # (the storage order inside a cell is decided by cursor atomics: it differs from run to run and changes no result)
+        assert np.array_equal(np.sort(a.getIds()), np.sort(b.getIds())), what + " ids"
+        assert_same(a.getField("moments01_avg"), b.getField("moments01_avg"), what + " running average")
+        assert_same(a.getField("cell_count"), b.getField("cell_count"), what + " counts")
+        assert_same(a.canvas, b.canvas, what + " canvas")
+
+    by_hand(a, 47); b.run_frames(47)
+    info = b.frame_graph_info()
+    assert info["frames_per_cycle"] == 6 and info["replays"] >= 5 and info["launches_per_cycle"] > 6 * 8, info
+    assert a.launch_count == b.launch_count  # replayed launches are counted
+    same("47 frames")
+    # a setter drops the graph; the next call launches a cycle one by one, captures again
+    vel = a.getVelocity() * 0.5
+    a.set({"velocity": vel * 2.998e8}); b.set({"velocity": vel * 2.998e8})
+    by_hand(a, 31); b.run_frames(31)
+    assert b.frame_graph_info()["replays"] > info["replays"]
+    same("after set(velocity)")
+    # frames by hand shift the cycle: the captured phase is never met again, the graph is dropped and re-captured later
+    by_hand(a, 2); by_hand(b, 2)
+    by_hand(a, 40); b.run_frames(40)
+    same("after frames by hand")
+    # reading does not drop it
+    r0 = b.frame_graph_info()["replays"]
+    by_hand(a, 12); b.run_frames(6); b.getPosition(); b.check_digest(); b.sync(); b.run_frames(6)
+    same("after getters")
+    assert b.frame_graph_info()["frames_per_cycle"] == 6 and b.frame_graph_info()["replays"] >= r0
+
+
+def test_run_frames_on_the_demo_scene_and_refusals():
+    from fusion_sim_b200 import Error, makeCylindricalParticlePusher
+    from fusion_sim_b200.scenes import apply_scene, c1_scene
+    sc = c1_scene(7)
+    a, b = makeCylindricalParticlePusher(sc["spec"]), makeCylindricalParticlePusher(sc["spec"])
+    apply_scene(a, sc); apply_scene(b, sc)
+    for _ in range(50):
+        a.step(); a.density(); a.draw_canvas()
+    b.run_frames(50)
+    assert b.frame_graph_info()["frames_per_cycle"] == 16 and b.frame_graph_info()["replays"] >= 1
+    assert_same(a.getPosition(), b.getPosition(), "position")
+    assert_same(a.getField("moments01_avg"), b.getField("moments01_avg"), "running average")
+    assert_same(a.canvas, b.canvas, "canvas")
+    with pytest.raises(Error, match="negative"):
+        b.run_frames(-1)
+    # per-launch timing needs its events: frames go one by one while it is on
+    b.timing(True)
+    b.run_frames(40)
+    assert b.frame_graph_info()["frames_per_cycle"] == 0
+    b.timing(False)
