@@ -15,6 +15,7 @@
 // tables come through the read-only path.  Arithmetic is IEEE, left to right as the GLSL is
 // written, compiled with -fmad=false so it rounds exactly like the CPU oracle.
 #include <algorithm>
+#include <map>
 
 #include "common.cuh"
 
@@ -31,6 +32,9 @@ struct PushArgs {
     uint32_t *id_out;
     const Real *__restrict__ ent;
     const Real *__restrict__ cellrec;
+#ifdef FSIM_TUNE
+    const Real *__restrict__ cellrec12;  // measured alternative (OPT bit 2): nine Boris entries + A per cell, 12 reals
+#endif
     const uint32_t *__restrict__ sink;  // 1 bit per GLOBAL cell (2 MB at 8192 x 2048: stays in L2)
     const Real *__restrict__ invcdf;
     uint32_t *key;      // optional deposit prepass: sort key, sprite colour, histogram
@@ -111,6 +115,22 @@ __device__ __forceinline__ void ld_rec(const float *p, float (&o)[RECSTRIDE])
         o[4 * k] = a.x; o[4 * k + 1] = a.y; o[4 * k + 2] = a.z; o[4 * k + 3] = a.w;
     }
 }
+#ifdef FSIM_TUNE
+__device__ __forceinline__ void ld_rec12(const double *p, double (&o)[12])
+{
+    ld_ro256(p, o[0], o[1], o[2], o[3]);
+    ld_ro256(p + 4, o[4], o[5], o[6], o[7]);
+    ld_ro256(p + 8, o[8], o[9], o[10], o[11]);
+}
+__device__ __forceinline__ void ld_rec12(const float *p, float (&o)[12])
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(p) + k);
+        o[4 * k] = a.x; o[4 * k + 1] = a.y; o[4 * k + 2] = a.z; o[4 * k + 3] = a.w;
+    }
+}
+#endif
 __device__ __forceinline__ void ld_ro2(const double *p, double &a, double &b)
 {
     double2 t = __ldg(reinterpret_cast<const double2 *>(p));
@@ -159,7 +179,8 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
 #pragma unroll 1
     for (int hs = 0; hs < NH; ++hs) {
         // dependent gathers: entropy texel (empic.js:802) and cell record (:763-766)
-        Real rec[V][RECSTRIDE], dx[V], dy[V];
+        constexpr int RW = (OPT & 4) ? 12 : RECSTRIDE;
+        Real rec[V][RW], dx[V], dy[V];
         if constexpr (!(OPT & 2)) gather_entropy(e);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -174,6 +195,10 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
                 if (al[k] && p0 + k < n) atomicAdd(a.oob, 1u);
                 cj = cj < 0 ? 0 : a.rows - 1;
             }
+#ifdef FSIM_TUNE
+            if constexpr ((OPT & 4) != 0) ld_rec12(a.cellrec12 + 12 * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
+            else
+#endif
             ld_rec(a.cellrec + RECSTRIDE * ((size_t)ci + (size_t)cj * a.nr), rec[k]);
         }
 
@@ -201,10 +226,18 @@ __device__ __forceinline__ void advance(const PushArgs<Real> &a, const int64_t p
             const Real vr = vx[k] * dx[k] + vy[k] * dy[k];
             const Real va = vy[k] * dx[k] - vx[k] * dy[k];
             Real R[9];  // rows of the Boris matrix, rebuilt from the record (programPre1/2/3)
-            boris_rows<Real>(rec[k], a.h, a.k13, a.k31, R);
-            const Real c0 = (R[0] * vr + R[1] * va + R[2] * vz[k]) + rec[k][REC_AX];
-            const Real c1 = (R[3] * vr + R[4] * va + R[5] * vz[k]) + rec[k][REC_AY];
-            const Real c2 = (R[6] * vr + R[7] * va + R[8] * vz[k]) + rec[k][REC_AZ];
+            Real Ax, Ay, Az;
+            if constexpr ((OPT & 4) != 0) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) R[i] = rec[k][i];
+                Ax = rec[k][9]; Ay = rec[k][10]; Az = rec[k][11];
+            } else {
+                boris_rows<Real>(rec[k], a.h, a.k13, a.k31, R);
+                Ax = rec[k][REC_AX]; Ay = rec[k][REC_AY]; Az = rec[k][REC_AZ];
+            }
+            const Real c0 = (R[0] * vr + R[1] * va + R[2] * vz[k]) + Ax;
+            const Real c1 = (R[3] * vr + R[4] * va + R[5] * vz[k]) + Ay;
+            const Real c2 = (R[6] * vr + R[7] * va + R[8] * vz[k]) + Az;
             Real nvx, nvy, nvz;
             if (al[k]) {
                 nvx = c0 * dx[k] - c1 * dy[k];
@@ -498,6 +531,34 @@ static int push_tma_impl(fsim_sim *s, const PushArgs<Real> &a)
 // Tuning build only (make EXTRA=-DFSIM_TUNE, tools/tune.py): vector width / block size / register cap
 // variants selectable at run time through fsim_tune_set().  The product compiles ONE variant per precision.
 int g_push_variant = 0;
+
+// measured alternative (variants 40-42): a 12-real cell table (nine Boris entries + A) expanded from the records
+template <typename Real>
+__global__ void __launch_bounds__(256) expand12_kernel(const Real *__restrict__ rec, Real *__restrict__ out, int64_t ncell, Real h, Real k13, Real k31)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    Real R[9];
+    boris_rows<Real>(rec + RECSTRIDE * c, h, k13, k31, R);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out[12 * c + i] = R[i];
+    out[12 * c + 9] = rec[RECSTRIDE * c + REC_AX];
+    out[12 * c + 10] = rec[RECSTRIDE * c + REC_AY];
+    out[12 * c + 11] = rec[RECSTRIDE * c + REC_AZ];
+}
+static std::map<const fsim_sim *, void *> g_rec12;
+template <typename Real>
+static const Real *rec12_of(fsim_sim *s)
+{
+    auto it = g_rec12.find(s);
+    if (it != g_rec12.end()) return (const Real *)it->second;
+    void *p = nullptr;
+    if (cudaMalloc(&p, sizeof(Real) * 12 * (size_t)s->ncell_local) != cudaSuccess) return nullptr;
+    expand12_kernel<Real><<<grid_for(s->ncell_local, 256), 256, 0, s->stream>>>((const Real *)s->cellrec, (Real *)p, s->ncell_local,
+                                                                               (Real)s->h, (Real)s->k13, (Real)s->k31);
+    g_rec12[s] = p;
+    return (const Real *)p;
+}
 #endif
 
 // resort: the sweep also performs the physical re-sort the last binning prepared (perm[] must match the
@@ -547,6 +608,9 @@ int launch_push(fsim_sim *s, bool with_hist, int nhalf, bool resort)
         case 37: return push_impl<Real, 1, 512, 3>(s, a, nhalf, resort);
         case 38: return push_impl<Real, 1, 128, 12>(s, a, nhalf, resort);
         case 39: return push_impl<Real, 1, 256, 7>(s, a, nhalf, resort);
+        case 40: { PushArgs<Real> b2 = a; b2.cellrec12 = rec12_of<Real>(s); return push_impl<Real, 1, 256, (sizeof(Real) == 4 ? 6 : 4), 4>(s, b2, nhalf, resort); }
+        case 41: { PushArgs<Real> b2 = a; b2.cellrec12 = rec12_of<Real>(s); return push_impl<Real, 1, 256, (sizeof(Real) == 4 ? 5 : 3), 4>(s, b2, nhalf, resort); }
+        case 42: { PushArgs<Real> b2 = a; b2.cellrec12 = rec12_of<Real>(s); return push_impl<Real, 1, 256, (sizeof(Real) == 4 ? 8 : 4), 4>(s, b2, nhalf, resort); }
         default: break;
         }
 #endif
