@@ -1553,7 +1553,7 @@ int fsim_run_frames(fsim_sim *s, int64_t nframes)
             off_cycle = 0;
             continue;
         }
-        if (allow && !s->frame_graph && !s->graph_failed && s->frames_run >= period && nframes >= 2 * period && s->ever_sorted &&
+        if (allow && !s->frame_graph && !s->graph_failed && s->frames_run >= period && nframes >= period && s->ever_sorted &&
             s->steps_since_sort <= sort_interval(s)) {
             FSIM_TRY(capture_frame_graph(s, period));
             if (s->frame_graph) continue;
