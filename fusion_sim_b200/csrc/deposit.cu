@@ -130,10 +130,62 @@ __global__ void __launch_bounds__(128) cellsum_kernel(const CellSumArgs<Real> a)
 // up to 100).  Lanes hold the (id, slot) pairs; an element's position in id order is the number of
 // smaller ids, counted with one shuffle per element; the colours are fetched in parallel and parked
 // in shared memory in id order; lanes 0..3 then add one channel each, sequentially.
+// NQ = 32-particle groups a lane holds: the counting loop costs k (1 + NQ) instructions per lane, so a cell of
+// 17..32 particles (the common case of the demo scene) runs the NQ = 1 instance -- 64 instead of 288.
+template <typename Real, int NQ>
+__device__ __forceinline__ void cell_medium(const CellSumArgs<Real> &a, const uint32_t c, const uint32_t s, const uint32_t k,
+                                            const int lane, Real (*s_col)[WARP_CELL_MAX], uint8_t *s_on)
+{
+    uint32_t pp[NQ], ii[NQ], rank[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const uint32_t j = q * 32 + lane;
+        pp[q] = (q * 32 < k && j < k) ? a.perm[(size_t)s + j] : KEY_CLIPPED;
+        FSIM_ASSERT(!(q * 32 < k && j < k) || ((int64_t)s + j < a.n && (int64_t)(pp[q] & KEY_MASK) < a.n));
+        ii[q] = (q * 32 < k && j < k) ? a.id[pp[q] & KEY_MASK] : 0xffffffffu;
+        rank[q] = 0;
+    }
+#pragma unroll
+    for (int qt = 0; qt < NQ; ++qt) {
+        if (qt * 32 >= k) break;  // warp-uniform
+        const int nt = min(32u, k - qt * 32);
+        for (int lt = 0; lt < nt; ++lt) {
+            const uint32_t v = __shfl_sync(0xffffffffu, ii[qt], lt);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) rank[q] += (v < ii[q]) ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        if (q * 32 >= k) break;
+        if (q * 32 + lane < k) {
+            const bool on = !(pp[q] & KEY_CLIPPED);
+            const size_t p = pp[q] & KEY_MASK;
+            const uint32_t r = rank[q];
+            s_on[r] = on ? 1 : 0;
+            s_col[0][r] = on ? a.dcol[0][p] : (Real)0;
+            s_col[1][r] = on ? a.dcol[1][p] : (Real)0;
+            s_col[2][r] = on ? (Real)FSIM_DEPOSIT_WEIGHT * a.vz[p] : (Real)0;
+        }
+    }
+    __syncwarp();
+    if (lane < 4) {
+        Real acc = (Real)0;
+        uint32_t cnt = 0;
+        for (uint32_t t = 0; t < k; ++t) {
+            if (!s_on[t]) continue;
+            acc += (lane < 3) ? s_col[lane < 3 ? lane : 0][t] : (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
+            cnt++;
+        }
+        a.S[(size_t)lane * a.plane + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr)] = acc;
+        if (lane == 3) a.count[c] = cnt;
+    }
+    __syncwarp();
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(128) cellsum_warp_kernel(const CellSumArgs<Real> a)
 {
-    constexpr int NQ = WARP_CELL_MAX / 32;
     __shared__ Real s_col[4][3][WARP_CELL_MAX];
     __shared__ uint8_t s_on[4][WARP_CELL_MAX];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -141,51 +193,10 @@ __global__ void __launch_bounds__(128) cellsum_warp_kernel(const CellSumArgs<Rea
     for (uint32_t h = blockIdx.x * 4 + w; h < nmed; h += gridDim.x * 4) {
         const uint32_t c = a.medium_list[h];
         const uint32_t s = a.starts[c], k = a.starts[c + 1] - s;
-        uint32_t pp[NQ], ii[NQ], rank[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const uint32_t j = q * 32 + lane;
-            pp[q] = (q * 32 < k && j < k) ? a.perm[(size_t)s + j] : KEY_CLIPPED;
-            FSIM_ASSERT(!(q * 32 < k && j < k) || ((int64_t)s + j < a.n && (int64_t)(pp[q] & KEY_MASK) < a.n));
-            ii[q] = (q * 32 < k && j < k) ? a.id[pp[q] & KEY_MASK] : 0xffffffffu;
-            rank[q] = 0;
-        }
-#pragma unroll
-        for (int qt = 0; qt < NQ; ++qt) {
-            if (qt * 32 >= k) break;  // warp-uniform
-            const int nt = min(32u, k - qt * 32);
-            for (int lt = 0; lt < nt; ++lt) {
-                const uint32_t v = __shfl_sync(0xffffffffu, ii[qt], lt);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) rank[q] += (v < ii[q]) ? 1u : 0u;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            if (q * 32 >= k) break;
-            if (q * 32 + lane < k) {
-                const bool on = !(pp[q] & KEY_CLIPPED);
-                const size_t p = pp[q] & KEY_MASK;
-                const uint32_t r = rank[q];
-                s_on[w][r] = on ? 1 : 0;
-                s_col[w][0][r] = on ? a.dcol[0][p] : (Real)0;
-                s_col[w][1][r] = on ? a.dcol[1][p] : (Real)0;
-                s_col[w][2][r] = on ? (Real)FSIM_DEPOSIT_WEIGHT * a.vz[p] : (Real)0;
-            }
-        }
-        __syncwarp();
-        if (lane < 4) {
-            Real acc = (Real)0;
-            uint32_t cnt = 0;
-            for (uint32_t t = 0; t < k; ++t) {
-                if (!s_on[w][t]) continue;
-                acc += (lane < 3) ? s_col[w][lane < 3 ? lane : 0][t] : (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
-                cnt++;
-            }
-            a.S[(size_t)lane * a.plane + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr)] = acc;
-            if (lane == 3) a.count[c] = cnt;
-        }
-        __syncwarp();
+        if (k <= 32) cell_medium<Real, 1>(a, c, s, k, lane, s_col[w], s_on[w]);
+        else if (k <= 64) cell_medium<Real, 2>(a, c, s, k, lane, s_col[w], s_on[w]);
+        else if (k <= 128) cell_medium<Real, 4>(a, c, s, k, lane, s_col[w], s_on[w]);
+        else cell_medium<Real, WARP_CELL_MAX / 32>(a, c, s, k, lane, s_col[w], s_on[w]);
     }
 }
 
@@ -313,7 +324,7 @@ int launch_cellsum(fsim_sim *s)
         // crowded cells (list lengths are read on the device: no host round trip)
         {
             Bracket b(s, "cellsum_warp");
-            cellsum_warp_kernel<Real><<<s->nsm * 4, 128, 0, s->stream>>>(a);
+            cellsum_warp_kernel<Real><<<s->nsm * 8, 128, 0, s->stream>>>(a);  // 8 blocks of 25.6 KB shared memory fill an SM
             FSIM_CUDA(cudaGetLastError());
         }
         {
