@@ -46,6 +46,7 @@ struct CellSumArgs {
     int nr, nz, row0;
     // scratch of the block-per-cell path (the idle half of the particle double buffer)
     uint32_t *sid, *sidx;
+    Real *scol[3];    // colours of a crowded cell in id order
 };
 
 // Register path for a cell with k <= KR particles: (id, slot) pairs are loaded once, ordered by id
@@ -235,20 +236,31 @@ __global__ void __launch_bounds__(256) cellsum_heavy_kernel(const CellSumArgs<Re
             __syncthreads();
         }
     }
-    if (threadIdx.x == 0) {
-        Real acc[4] = {(Real)0, (Real)0, (Real)0, (Real)0};
+    // the colours, gathered by all threads and parked in id order (a clipped sprite parks exact zeros: x + 0 = x
+    // for every x a sum that started at +0 can hold, so the sequential additions below need no branch) ...
+    Real *sc0 = a.scol[0] + s, *sc1 = a.scol[1] + s, *sc2 = a.scol[2] + s;
+    for (uint32_t t = threadIdx.x; t < k; t += blockDim.x) {
+        const uint32_t j = sidx[t];
+        const bool on = !(j & KEY_CLIPPED);
+        const size_t p = a.perm[(size_t)s + (j & KEY_MASK)] & KEY_MASK;
+        sc0[t] = on ? a.dcol[0][p] : (Real)0;
+        sc1[t] = on ? a.dcol[1][p] : (Real)0;
+        sc2[t] = on ? (Real)FSIM_DEPOSIT_WEIGHT * a.vz[p] : (Real)0;
+    }
+    __syncthreads();
+    // ... then one thread per channel adds them in that order: contiguous reads, nothing but the additions in the chain
+    if (threadIdx.x < 4) {
+        const int q = threadIdx.x;
+        const Real *src = q == 0 ? sc0 : (q == 1 ? sc1 : sc2);
+        Real acc = (Real)0;
         uint32_t cnt = 0;
         for (uint32_t t = 0; t < k; ++t) {
-            const uint32_t j = sidx[t];
-            if (j & KEY_CLIPPED) continue;
-            const size_t p = a.perm[(size_t)s + j] & KEY_MASK;
-            acc[0] += a.dcol[0][p]; acc[1] += a.dcol[1][p]; acc[2] += (Real)FSIM_DEPOSIT_WEIGHT * a.vz[p];
-            acc[3] += (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0;
-            cnt++;
+            const bool on = !(sidx[t] & KEY_CLIPPED);
+            acc += (q < 3) ? src[t] : (on ? (Real)FSIM_DEPOSIT_WEIGHT * (Real)1.0 : (Real)0);
+            cnt += on ? 1u : 0u;
         }
-        Real *o = a.S + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr);
-        o[0] = acc[0]; o[a.plane] = acc[1]; o[2 * a.plane] = acc[2]; o[3 * a.plane] = acc[3];
-        a.count[c] = cnt;
+        a.S[(size_t)q * a.plane + (size_t)(c / a.nr) * a.pitch + (size_t)(c % a.nr)] = acc;
+        if (q == 3) a.count[c] = cnt;
     }
     __syncthreads();
   }
@@ -315,6 +327,7 @@ int launch_cellsum(fsim_sim *s)
         a.nr = s->nr; a.nz = s->nz; a.row0 = s->row0;
         a.sid = (uint32_t *)s->part[alt][4];
         a.sidx = (uint32_t *)s->part[alt][5];
+        for (int q = 0; q < 3; ++q) a.scol[q] = (Real *)s->part[alt][6 + q];
         FSIM_CUDA(cudaMemsetAsync(s->heavy_n, 0, 2 * sizeof(uint32_t), s->stream));
         {
             Bracket b(s, "cellsum");
