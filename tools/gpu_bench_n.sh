@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/gpu_n.sh N workload [extra bench args]: one slab bench line on N GPUs
+# tools/gpu_bench_n.sh N workload [extra bench args]: one slab bench line on N GPUs
 N=$1; W=$2; shift 2
 mkdir -p gpurun_out
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $W "$@" > gpurun_out/r2_bench_${W}_n${N}_b.json 2> gpurun_out/r2_bench_${W}_n${N}_b.err; echo "rc=$?"
