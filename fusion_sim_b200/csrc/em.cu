@@ -130,6 +130,10 @@ int em_init(fsim_sim *s)
         set_error(".dt <- the Yee update needs c dt sqrt(1/dr^2 + 1/dz^2) < 1");
         return FSIM_ERR_RANGE;
     }
+    if (s->nz + 1 > 65535) {  // one block row per lattice row (gridDim.y)
+        set_error(".nz <- the electromagnetic update takes at most 65534 rows");
+        return FSIM_ERR_RANGE;
+    }
     for (int f = 0; f < 6; ++f) {
         const size_t bytes = s->rs * em_count(s, f);
         if (!s->em[f]) FSIM_CUDA(cudaMalloc(&s->em[f], bytes));
