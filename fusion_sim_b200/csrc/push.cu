@@ -8,11 +8,13 @@
 // position shader reads the old position with the new velocity (:847-848), so the fusion is
 // exact and the update can be done in place (a particle touches only its own state).
 //
-// HBM-bound: 10 reals + 1 byte read and written per particle, streamed with vector loads and
-// stores (ld.global.cs / st.global.cs keep the 126 MB L2 for the entropy and cell tables): 64-bit
-// per lane (fp64: one particle per thread at 64 registers, 32 warps per SM -- measured 12 % faster
-// than 128-bit loads, which need 128 registers and halve the occupancy: profiles/r2_push_variants.md);
-// tables come through the read-only path.  Arithmetic is IEEE, left to right as the GLSL is
+// HBM-bound: 10 reals + 1 byte read and written per particle, streamed with ld.global.cs /
+// st.global.cs (they keep the 126 MB L2 for the entropy and cell tables).  ONE particle per thread in both
+// precisions: a warp's loads of consecutive particles are whole lines either way, and what the sweep needs is
+// resident warps to cover its dependent gathers -- fp64 at 62 registers, 32 warps per SM (12 % faster than
+// 128-bit loads = 2 particles per thread = 124 registers), fp32 at 40 registers, 48 warps (24 % faster than
+// 128-bit loads = 4 particles per thread = 125 registers; ncu pair in profiles/r2_kernel_rooflines.md).
+// Tables come through the read-only path.  Arithmetic is IEEE, left to right as the GLSL is
 // written, compiled with -fmad=false so it rounds exactly like the CPU oracle.
 #include <algorithm>
 #include <map>
