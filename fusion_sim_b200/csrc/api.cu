@@ -1546,6 +1546,11 @@ int fsim_run_frames(fsim_sim *s, int64_t nframes)
     int off_cycle = 0;
     while (nframes > 0) {
         if (allow && s->frame_graph && nframes >= s->graph_frames && frame_phase_is(s, s->graph_phase)) {
+            // the replay draws into both canvas images: a read-back of one of them (fsim_render_rgba8_async) must have landed
+            if (s->copy_stream && (s->copy_pending[0] || s->copy_pending[1])) {
+                FSIM_CUDA(cudaStreamSynchronize(s->copy_stream));
+                s->copy_pending[0] = s->copy_pending[1] = false;
+            }
             FSIM_CUDA(cudaGraphLaunch(s->frame_graph, s->stream));
             s->launches += s->graph_launches;
             s->graph_replays++;

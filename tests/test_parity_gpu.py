@@ -438,18 +438,34 @@ def test_run_frames_graph_replay_changes_no_bit(precision):
 
 
 def test_run_frames_on_the_demo_scene_and_refusals():
+    import torch
     from fusion_sim_b200 import Error, makeCylindricalParticlePusher
     from fusion_sim_b200.scenes import apply_scene, c1_scene
     sc = c1_scene(7)
     a, b = makeCylindricalParticlePusher(sc["spec"]), makeCylindricalParticlePusher(sc["spec"])
     apply_scene(a, sc); apply_scene(b, sc)
-    for _ in range(50):
-        a.step(); a.density(); a.draw_canvas()
-    b.run_frames(50)
-    assert b.frame_graph_info()["frames_per_cycle"] == 16 and b.frame_graph_info()["replays"] >= 1
+
+    def by_hand(sim, n):
+        for _ in range(n):
+            sim.step(); sim.density(); sim.draw_canvas()
+
+    by_hand(a, 48)
+    b.run_frames(48)  # 16 one by one, capture, 2 replays: the handle is back at the captured phase
+    assert b.frame_graph_info()["frames_per_cycle"] == 16 and b.frame_graph_info()["replays"] == 2
     assert_same(a.getPosition(), b.getPosition(), "position")
     assert_same(a.getField("moments01_avg"), b.getField("moments01_avg"), "running average")
     assert_same(a.canvas, b.canvas, "canvas")
+    # two canvas read-backs in flight on the copy stream (one per device image) when the next replay wants to draw
+    # into those images: the replay waits for them
+    want = a.canvas.copy()
+    pinned = [torch.empty((800, 400, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    b.render_async(pinned[0].numpy()); b.render_async(pinned[1].numpy())
+    b.run_frames(16); by_hand(a, 16)
+    b.sync()
+    assert b.frame_graph_info()["replays"] == 3
+    assert_same(pinned[0].numpy(), want, "first read-back"); assert_same(pinned[1].numpy(), want, "second read-back")
+    assert_same(a.getPosition(), b.getPosition(), "position after the read-backs")
+    assert_same(a.canvas, b.canvas, "canvas after the read-backs")
     with pytest.raises(Error, match="negative"):
         b.run_frames(-1)
     # per-launch timing needs its events: frames go one by one while it is on
